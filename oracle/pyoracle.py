@@ -238,6 +238,25 @@ class RefTap:
         L.hyd_tap_cosine_lut.argtypes = [C.c_void_p]
         L.hyd_tap_luts.restype = C.c_int
         L.hyd_tap_luts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hyd_tap_prefix_stream.restype = C.c_int64
+        L.hyd_tap_prefix_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]
+
+    def prefix_stream(self, values, ctx=None, cluster_map=None, num_dists=1, custom=None,
+                      lz77_min_symbol=0, modular=0):
+        """Same contract as Oracle.prefix_stream, but through the reference's own entropy.c."""
+        v = np.ascontiguousarray(values, np.uint32)
+        cx = None if ctx is None else np.ascontiguousarray(ctx, np.uint32)
+        cm = None if cluster_map is None else np.ascontiguousarray(cluster_map, np.uint8)
+        out = np.zeros(max(1 << 16, v.size * 8), np.uint8)
+        s, m, l = custom if custom else (0, 0, 0)
+        bits = self.lib.hyd_tap_prefix_stream(v.ctypes.data, cx.ctypes.data if cx is not None else None, v.size,
+                                              cm.ctypes.data if cm is not None else None, num_dists,
+                                              1 if custom else 0, s, m, l, lz77_min_symbol, modular,
+                                              out.ctypes.data, out.nbytes)
+        if bits < 0:
+            raise RuntimeError(f"reference error {bits}")
+        return out[:(bits + 7) // 8].tobytes(), bits
 
     def encode_tile(self, image: np.ndarray, tx: int, ty: int, *, linear_light=0, is_last=-1,
                     stages: Stages | None = None, shift=0) -> bytes:

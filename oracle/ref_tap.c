@@ -258,3 +258,44 @@ int hyd_tap_luts(int sample_fmt, int linear_light, uint16_t *input_lut, float *b
     hyd_encoder_destroy(enc);
     return ret;
 }
+
+/*
+ * A prefix-coded stream straight through the reference's entropy front end
+ * (entropy.c:371-425, 502-524, 1023-1034): values[i] on context ctx[i] (NULL = 0).
+ * Returns the bit length, or a negative HYDStatusCode.
+ */
+__attribute__((visibility("default")))
+int64_t hyd_tap_prefix_stream(const uint32_t *values, const uint32_t *ctx, uint64_t n,
+                              const uint8_t *cluster_map, uint32_t num_dists, int custom_config,
+                              int split, int msb, int lsb, uint32_t lz77_min_symbol, int modular,
+                              uint8_t *dst, uint64_t cap) {
+    const char *error = NULL;
+    HYDEntropyStream stream;
+    HYDBitWriter bw;
+    static const uint8_t zeros[256];
+    HYDStatusCode ret = hyd_init_bit_writer(&bw, NULL, 0, 0, 0);
+    if (ret < HYD_ERROR_START)
+        return ret;
+    ret = hyd_entropy_init_stream(&stream, n ? n : 1, cluster_map ? cluster_map : zeros, num_dists,
+                                  custom_config, lz77_min_symbol, modular, &error);
+    if (ret < HYD_ERROR_START)
+        goto end;
+    if (custom_config)
+        hyd_entropy_set_hybrid_config(&stream, 0, 0, split, msb, lsb);
+    for (uint64_t i = 0; i < n; i++) {
+        ret = hyd_entropy_send_symbol(&stream, ctx ? ctx[i] : 0, values[i]);
+        if (ret < HYD_ERROR_START)
+            goto end;
+    }
+    ret = hyd_prefix_finalize_stream(&stream, &bw);
+    if (ret < HYD_ERROR_START)
+        goto end;
+    {
+        int64_t bits = (int64_t)snapshot_writer(&bw, dst, cap);
+        free(bw.buffer);
+        return bits;
+    }
+end:
+    free(bw.buffer);
+    return ret;
+}
