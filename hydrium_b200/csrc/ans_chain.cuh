@@ -22,9 +22,11 @@ constexpr uint32_t kAnsInitState = 0x130000u;   // reference: entropy.c:1083
 // per (cluster, token) constants for the chain
 struct AnsSymInfo {
     uint32_t m;        // reciprocal multiplier
-    uint32_t packed;   // freq:13 | shift:4 << 13 | cum:12 << 17
+    uint32_t packed;   // (freq - 1):12 | shift:4 << 12 | table base:16 << 16
 };
-HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t cum) {
+// `base` = cluster * 4096 + cumulative frequency: index of the symbol's first slot in the flat
+// inverse table inv[9 * 4096]
+HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t base) {
     AnsSymInfo s;
     uint32_t sh;
     if (!f) {
@@ -33,23 +35,23 @@ HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t cum) {
         return s;
     }
     ans_div_consts(f, s.m, sh);
-    s.packed = f | (sh << 13) | (cum << 17);
+    s.packed = (f - 1u) | (sh << 12) | (base << 16);
     return s;
 }
-HD uint32_t asi_freq(uint32_t packed) { return packed & 0x1FFFu; }
-HD uint32_t asi_shift(uint32_t packed) { return (packed >> 13) & 0xFu; }
-HD uint32_t asi_cum(uint32_t packed) { return packed >> 17; }
+HD uint32_t asi_freq(uint32_t packed) { return (packed & 0xFFFu) + 1u; }
+HD uint32_t asi_shift(uint32_t packed) { return (packed >> 12) & 0xFu; }
+HD uint32_t asi_base(uint32_t packed) { return packed >> 16; }
 
 // Code one symbol.  In: x (renormalised state), this symbol's constants, the next symbol's
 // frequency (the one that will be coded after this one, i.e. the PREVIOUS symbol in stream
 // order; pass 0x7FFFFFFF for "none").  Out: x for the next step, whether that step's
 // renormalisation fires, and the 16-bit word it emits.
-HD void ans_step(uint32_t &x, uint32_t m, uint32_t packed, const uint16_t *inv_cluster,
+HD void ans_step(uint32_t &x, uint32_t m, uint32_t packed, const uint16_t *inv,
                  uint32_t f_next, bool &flush, uint32_t &word) {
     const uint32_t f = asi_freq(packed);
     const uint32_t q = ans_div(x, m, asi_shift(packed));
-    const uint32_t idx = asi_cum(packed) + (x - q * f);
-    const uint32_t slot = inv_cluster[idx];
+    const uint32_t idx = asi_base(packed) + (x - q * f);
+    const uint32_t slot = inv[idx];
     const uint32_t s = (q << 12) | slot;
     flush = (q >> 8) >= f_next;
     word = s & 0xFFFFu;

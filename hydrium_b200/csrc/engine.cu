@@ -1,0 +1,534 @@
+// hydrium_b200/csrc/engine.cu
+//
+// The thin C-ABI CUDA layer: device workspace, kernel sequencing on CUDA streams, and the hydb_*
+// entry points of include/hydrium_b200.h.  The nine libhydrium entry points live in hyd_api.c
+// (portable C) and call into this file.
+//
+// Pipeline per batch of tiles (all asynchronous on the engine stream `st`; the LF coder runs on a
+// second stream, concurrent with the HF tokeniser, and is joined before the ANS kernel):
+//
+//   st : [descs H2D] -> k_xyb_dct_quant -+-> k_hf_tokens ------+-> k_ans_encode -> k_frame_offsets -> k_gather_frames
+//   st2:                                  +-> k_lf_group -------+
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hydrium_b200.h"
+#include "headers.cuh"
+#include "kernels.h"
+
+using namespace hydb;
+
+struct HydbEngine {
+    int device = 0;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_lf = nullptr;
+    uint32_t max_batch = 0;
+    Workspace ws{};
+    LutSet luts{};
+    uint16_t *lut8_srgb = nullptr, *lut8_lin = nullptr, *lut16_srgb = nullptr, *lut16_lin = nullptr;
+    float *bias = nullptr;
+    Templates templ{};
+    std::vector<uint32_t> shapes;   // (vbw << 16) | vbh, index = shape id
+    uint32_t *d_shape_dims = nullptr;
+    uint32_t *d_overflow = nullptr;
+    uint32_t *h_err = nullptr;      // pinned [max_batch + 1]; last entry = gather overflow flag
+    uint64_t *h_total = nullptr;    // pinned [1]
+    uint32_t last_n = 0;
+    uint64_t last_base = 0;
+    bool taps = false;
+    uint64_t launches = 0;
+    std::string error;
+    std::vector<TileDesc> h_tiles;
+};
+
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            eng->error = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+            return HYD_INTERNAL_ERROR;                                                  \
+        }                                                                               \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+
+static const char *tile_error_text(uint32_t bits) {
+    if (bits & kErrAlphabet) return "HF token alphabet exceeds 64 symbols";
+    if (bits & kErrHuffman) return "couldn't find target";               // reference: entropy.c:635
+    if (bits & kErrAlias) return "empty underfull during alias table gen";   // reference: entropy.c:219
+    if (bits & kErrAnsGap) return "rANS renormalisation gap exceeds 65535 symbols";
+    if (bits & kErrLfCapacity) return "LF stream scratch exhausted";
+    if (bits & kErrLfAlphabet) return "LF token alphabet exceeds the sparse coder";
+    if (bits & kErrSlab) return "encoded tile exceeds the output slab";
+    return "unknown device-side error";
+}
+
+extern "C" {
+
+HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batch_tiles) {
+    if (!out || !max_batch_tiles)
+        return HYD_API_ERROR;
+    *out = nullptr;
+    HydbEngine *eng = new (std::nothrow) HydbEngine();
+    if (!eng)
+        return HYD_NOMEM;
+    auto fail = [&](HYDStatusCode rc) {
+        fprintf(stderr, "hydrium_b200: engine creation failed: %s\n", eng->error.c_str());
+        hydb_engine_destroy(eng);
+        return rc;
+    };
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        eng->error = "no CUDA device available (the B200 encoder has no CPU path)";
+        return fail(HYD_INTERNAL_ERROR);
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess)
+            device = 0;
+    }
+    eng->device = device;
+    eng->max_batch = max_batch_tiles;
+    const size_t T = max_batch_tiles;
+    cudaError_t e = cudaSetDevice(device);
+    Workspace &w = eng->ws;
+    w.capacity = max_batch_tiles;
+#define A(call) if (e == cudaSuccess) e = (call)
+    A(cudaStreamCreateWithFlags(&eng->st, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&eng->st2, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&eng->ev_front, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&eng->ev_lf, cudaEventDisableTiming));
+    A(dalloc(&w.tiles, T));
+    A(dalloc(&w.coef, T * kMaxBlocks * 3 * 64));
+    A(dalloc(&w.nzinfo, T * kMaxBlocks * 3));
+    A(dalloc(&w.lfq, T * 3 * kMaxBlocks));
+    A(dalloc(&w.syms, T * kMaxHfSyms));
+    A(dalloc(&w.nsyms, T));
+    A(dalloc(&w.resbits, T));
+    A(dalloc(&w.hist, T * kHfClusters * kHfTokens));
+    A(dalloc(&w.lfbits, T * kLfBitsWords));
+    A(dalloc(&w.lfbitlen, T));
+    A(dalloc(&w.flags, T * (kMaxHfSyms / 32)));
+    A(dalloc(&w.fwords, T * kMaxHfSyms));
+    A(dalloc(&w.slab, T * kSlabBytes));
+    A(dalloc(&w.frame_off, T));
+    A(dalloc(&w.frame_len, T));
+    A(dalloc(&w.out_off, T + 1));
+    A(dalloc(&w.tile_err, T));
+    A(dalloc(&eng->lut8_srgb, 256));
+    A(dalloc(&eng->lut8_lin, 256));
+    A(dalloc(&eng->lut16_srgb, 65536));
+    A(dalloc(&eng->lut16_lin, 65536));
+    A(dalloc(&eng->bias, 65536));
+    A(dalloc(&eng->templ.words, (size_t)(1 + kMaxShapes) * kTemplWords));
+    A(dalloc(&eng->templ.bits, 1 + kMaxShapes));
+    A(dalloc(&eng->d_shape_dims, 2 * kMaxShapes));
+    A(dalloc(&eng->d_overflow, 1));
+    A(cudaMallocHost((void **)&eng->h_err, (T + 1) * sizeof(uint32_t)));
+    A(cudaMallocHost((void **)&eng->h_total, sizeof(uint64_t)));
+    A(cudaMemsetAsync(eng->templ.words, 0, (size_t)(1 + kMaxShapes) * kTemplWords * sizeof(uint32_t), eng->st));
+    A(cudaMemsetAsync(w.lfbits, 0, T * kLfBitsWords * sizeof(uint32_t), eng->st));
+    A(cudaMemsetAsync(w.slab, 0, T * kSlabBytes, eng->st));
+#undef A
+    if (e != cudaSuccess) {
+        eng->error = std::string("CUDA allocation failed: ") + cudaGetErrorString(e);
+        return fail(e == cudaErrorMemoryAllocation ? HYD_NOMEM : HYD_INTERNAL_ERROR);
+    }
+    eng->luts = LutSet{eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias};
+    launch_build_luts(eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias, eng->st);
+    launch_build_templates(eng->templ, eng->d_shape_dims, 0, 0, true, eng->st);
+    eng->launches += 2;
+    e = cudaStreamSynchronize(eng->st);
+    if (e == cudaSuccess)
+        e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        eng->error = std::string("CUDA initialisation kernels failed: ") + cudaGetErrorString(e);
+        return fail(HYD_INTERNAL_ERROR);
+    }
+    *out = eng;
+    return HYD_OK;
+}
+
+void hydb_engine_destroy(HydbEngine *eng) {
+    if (!eng)
+        return;
+    cudaSetDevice(eng->device);
+    if (eng->st) cudaStreamSynchronize(eng->st);
+    if (eng->st2) cudaStreamSynchronize(eng->st2);
+    Workspace &w = eng->ws;
+    void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags,
+                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.dbg_xyb, w.dbg_dct,
+                   w.dbg_freqs, w.dbg_sect, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
+                   eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (eng->h_err) cudaFreeHost(eng->h_err);
+    if (eng->h_total) cudaFreeHost(eng->h_total);
+    if (eng->ev_front) cudaEventDestroy(eng->ev_front);
+    if (eng->ev_lf) cudaEventDestroy(eng->ev_lf);
+    if (eng->st) cudaStreamDestroy(eng->st);
+    if (eng->st2) cudaStreamDestroy(eng->st2);
+    delete eng;
+}
+
+const char *hydb_engine_error(const HydbEngine *eng) { return eng ? eng->error.c_str() : "no engine"; }
+uint32_t hydb_engine_max_batch(const HydbEngine *eng) { return eng ? eng->max_batch : 0; }
+uint64_t hydb_engine_stream(const HydbEngine *eng) { return eng ? (uint64_t)(uintptr_t)eng->st : 0; }
+uint64_t hydb_engine_launch_count(const HydbEngine *eng) { return eng ? eng->launches : 0; }
+
+HYDStatusCode hydb_engine_enable_taps(HydbEngine *eng, int enable) {
+    if (!eng)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    Workspace &w = eng->ws;
+    const size_t T = eng->max_batch;
+    if (enable && !eng->taps) {
+        CK(dalloc(&w.dbg_xyb, T * 65536 * 3));
+        CK(dalloc(&w.dbg_dct, T * 65536 * 3));
+        CK(dalloc(&w.dbg_freqs, T * kHfClusters * kHfTokens));
+        CK(dalloc(&w.dbg_sect, T * 4));
+        CK(cudaMemset(w.dbg_xyb, 0, T * 65536 * 3 * sizeof(float)));
+        CK(cudaMemset(w.dbg_dct, 0, T * 65536 * 3 * sizeof(float)));
+        eng->taps = true;
+    } else if (!enable && eng->taps) {
+        CK(cudaStreamSynchronize(eng->st));
+        cudaFree(w.dbg_xyb); cudaFree(w.dbg_dct); cudaFree(w.dbg_freqs); cudaFree(w.dbg_sect);
+        w.dbg_xyb = w.dbg_dct = nullptr;
+        w.dbg_freqs = w.dbg_sect = nullptr;
+        eng->taps = false;
+    }
+    return HYD_OK;
+}
+
+// shape id of a (vbw, vbh) tile; builds its section-B template on first use
+static int shape_of(HydbEngine *eng, uint32_t vbw, uint32_t vbh, std::vector<uint32_t> &fresh) {
+    const uint32_t key = (vbw << 16) | vbh;
+    for (size_t i = 0; i < eng->shapes.size(); i++)
+        if (eng->shapes[i] == key)
+            return (int)i;
+    if (eng->shapes.size() >= (size_t)kMaxShapes)
+        return -1;
+    eng->shapes.push_back(key);
+    fresh.push_back(key);
+    return (int)eng->shapes.size() - 1;
+}
+
+HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, uint8_t *d_out,
+                                       uint64_t d_out_cap, uint64_t d_out_pos) {
+    if (!eng || !tiles || !n || n > eng->max_batch || !d_out) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_encode_tiles";
+        return HYD_API_ERROR;
+    }
+    CK(cudaSetDevice(eng->device));
+    std::vector<uint32_t> fresh;
+    const uint32_t first_fresh = (uint32_t)eng->shapes.size();
+    eng->h_tiles.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const HydbTile &s = tiles[i];
+        if (!s.width || !s.height || s.width > 256 || s.height > 256 || (s.x0 & 255) || (s.y0 & 255) ||
+            (s.sample_fmt != HYD_UINT8 && s.sample_fmt != HYD_UINT16) || !s.plane[0] || !s.plane[1] || !s.plane[2]) {
+            eng->error = "invalid tile descriptor";
+            return HYD_API_ERROR;
+        }
+        const int shape = shape_of(eng, (s.width + 7) >> 3, (s.height + 7) >> 3, fresh);
+        if (shape < 0) {
+            eng->error = "too many distinct tile shapes in one engine";
+            return HYD_API_ERROR;
+        }
+        TileDesc &d = eng->h_tiles[i];
+        d.plane[0] = s.plane[0];
+        d.plane[1] = s.plane[1];
+        d.plane[2] = s.plane[2];
+        d.row_stride = s.row_stride;
+        d.pixel_stride = s.pixel_stride;
+        d.w = s.width;
+        d.h = s.height;
+        d.x0 = s.x0;
+        d.y0 = s.y0;
+        d.shape = (uint32_t)shape;
+        d.flags = (s.is_last ? kTileLast : 0u) |
+                  ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
+                  (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.linear_light ? kTileLinear : 0u);
+    }
+    cudaStream_t st = eng->st;
+    if (!fresh.empty()) {
+        std::vector<uint32_t> dims;
+        for (uint32_t k : fresh) {
+            dims.push_back(k >> 16);
+            dims.push_back(k & 0xFFFF);
+        }
+        CK(cudaMemcpyAsync(eng->d_shape_dims, dims.data(), dims.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        launch_build_templates(eng->templ, eng->d_shape_dims, first_fresh, (uint32_t)fresh.size(), false, st);
+        eng->launches++;
+        CK(cudaStreamSynchronize(st));   // dims is a stack-lifetime buffer
+    }
+    // pageable source: the runtime stages it before returning, so h_tiles may be reused immediately
+    CK(cudaMemcpyAsync(eng->ws.tiles, eng->h_tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(eng->ws.tile_err, 0, n * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(eng->d_overflow, 0, sizeof(uint32_t), st));
+    launch_xyb_dct_quant(eng->ws, eng->luts, n, st);
+    CK(cudaEventRecord(eng->ev_front, st));
+    CK(cudaStreamWaitEvent(eng->st2, eng->ev_front, 0));
+    launch_lf_group(eng->ws, n, eng->st2);
+    CK(cudaEventRecord(eng->ev_lf, eng->st2));
+    launch_hf_tokens(eng->ws, n, st);
+    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));
+    launch_ans_encode(eng->ws, eng->templ, n, st);
+    launch_gather(eng->ws, n, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    eng->launches += 6;
+    CK(cudaMemcpyAsync(eng->h_err, eng->ws.tile_err, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(eng->h_err + eng->max_batch, eng->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(eng->h_total, eng->ws.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    eng->last_n = n;
+    eng->last_base = d_out_pos;
+    return HYD_OK;
+}
+
+HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
+    if (!eng)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaStreamSynchronize(eng->st));
+    CK(cudaGetLastError());
+    for (uint32_t i = 0; i < eng->last_n; i++) {
+        if (eng->h_err[i]) {
+            eng->error = tile_error_text(eng->h_err[i]);
+            return HYD_INTERNAL_ERROR;
+        }
+    }
+    if (eng->last_n && eng->h_err[eng->max_batch]) {
+        eng->error = "device output buffer too small";
+        return HYD_NEED_MORE_OUTPUT;
+    }
+    if (batch_bytes)
+        *batch_bytes = eng->last_n ? *eng->h_total : 0;
+    return HYD_OK;
+}
+
+int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap) {
+    // reference: encoder.c:23-30 (level-10 container prefix), libhydrium.c:67-68 (when it applies)
+    static const uint8_t kLevel10[49] = {
+        0, 0, 0, 0x0c, 'J', 'X', 'L', ' ', 0x0d, 0x0a, 0x87, 0x0a, 0, 0, 0, 0x14, 'f', 't', 'y', 'p',
+        'j', 'x', 'l', ' ', 0, 0, 0, 0, 'j', 'x', 'l', ' ', 0, 0, 0, 9, 'j', 'x', 'l', 'l', 0x0a,
+        0, 0, 0, 0, 'j', 'x', 'l', 'c',
+    };
+    uint64_t n = 0;
+    const uint64_t w64 = width, h64 = height;
+    if (w64 > (1u << 20) || h64 > (1u << 20) || w64 * h64 > (1u << 28)) {
+        if (cap < sizeof(kLevel10))
+            return HYD_API_ERROR;
+        memcpy(dst, kLevel10, sizeof(kLevel10));
+        n = sizeof(kLevel10);
+    }
+    uint32_t words[8] = {0};
+    BitSink bw;
+    bw.init(words, 8);
+    put_image_header(bw, width, height);
+    bw.flush_partial();
+    const uint32_t bytes = bw.bitlen() >> 3;
+    if (bw.overflow || n + bytes > cap)
+        return HYD_API_ERROR;
+    for (uint32_t i = 0; i < bytes; i++)
+        dst[n + i] = (uint8_t)(words[i >> 2] >> (8 * (i & 3)));
+    return (int64_t)(n + bytes);
+}
+
+HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, uint32_t width, uint32_t height,
+                                       uint32_t channels, int64_t row_stride, int sample_fmt, int linear_light,
+                                       uint32_t tile_row_begin, uint32_t tile_row_end, int with_header, uint8_t *d_out,
+                                       uint64_t d_out_cap, uint64_t *out_len) {
+    if (!eng || !d_pixels || !d_out || !out_len || !width || !height || channels < 3 ||
+        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16)) {
+        if (eng) eng->error = "invalid arguments to hydb_encode_image_device";
+        return HYD_API_ERROR;
+    }
+    const uint32_t tiles_x = (width + 255) >> 8, tiles_y = (height + 255) >> 8;
+    if (tile_row_end > tiles_y)
+        tile_row_end = tiles_y;
+    if (tile_row_begin >= tile_row_end) {
+        eng->error = "empty tile row range";
+        return HYD_API_ERROR;
+    }
+    CK(cudaSetDevice(eng->device));
+    uint64_t pos = 0;
+    if (with_header) {
+        uint8_t hdr[64];
+        const int64_t hb = hydb_image_header(width, height, hdr, sizeof(hdr));
+        if (hb < 0 || (uint64_t)hb > d_out_cap) {
+            eng->error = "device output buffer too small";
+            return HYD_NEED_MORE_OUTPUT;
+        }
+        CK(cudaMemcpyAsync(d_out, hdr, (size_t)hb, cudaMemcpyHostToDevice, eng->st));
+        CK(cudaStreamSynchronize(eng->st));
+        pos = (uint64_t)hb;
+    }
+    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+    const uint64_t ntiles = (uint64_t)tiles_x * (tile_row_end - tile_row_begin);
+    std::vector<HydbTile> batch;
+    batch.reserve(eng->max_batch);
+    for (uint64_t first = 0; first < ntiles; first += eng->max_batch) {
+        const uint32_t n = (uint32_t)((ntiles - first) < eng->max_batch ? (ntiles - first) : eng->max_batch);
+        batch.clear();
+        for (uint32_t k = 0; k < n; k++) {
+            const uint64_t idx = first + k;
+            const uint32_t tx = (uint32_t)(idx % tiles_x), ty = tile_row_begin + (uint32_t)(idx / tiles_x);
+            HydbTile t;
+            memset(&t, 0, sizeof(t));
+            const uint8_t *p = (const uint8_t *)d_pixels +
+                               ((int64_t)(ty - tile_row_begin) * 256 * row_stride + (int64_t)tx * 256 * channels) * (int64_t)item;
+            t.plane[0] = p;
+            t.plane[1] = p + item;
+            t.plane[2] = p + 2 * item;
+            t.row_stride = row_stride;
+            t.pixel_stride = channels;
+            t.x0 = tx * 256;
+            t.y0 = ty * 256;
+            t.width = width - t.x0 < 256 ? width - t.x0 : 256;
+            t.height = height - t.y0 < 256 ? height - t.y0 : 256;
+            t.image_width = width;
+            t.image_height = height;
+            t.is_last = (tx + 1 == tiles_x && ty + 1 == tiles_y) ? 1 : 0;   // encoder.c:482-485
+            t.sample_fmt = sample_fmt;
+            t.linear_light = linear_light;
+            batch.push_back(t);
+        }
+        HYDStatusCode rc = hydb_engine_encode_tiles(eng, batch.data(), n, d_out, d_out_cap, pos);
+        if (rc < HYD_ERROR_START)
+            return rc;
+        uint64_t total = 0;
+        rc = hydb_engine_finish(eng, &total);
+        if (rc != HYD_OK)
+            return rc;
+        pos += total;
+    }
+    *out_len = pos;
+    return HYD_OK;
+}
+
+void *hydb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void hydb_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *hydb_device_alloc(size_t bytes) {
+    void *p = nullptr;
+    return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void hydb_device_free(void *p) { if (p) cudaFree(p); }
+int hydb_memcpy_h2d(void *dst, const void *src, size_t bytes) {
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+}
+int hydb_memcpy_d2h(void *dst, const void *src, size_t bytes) {
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+int hydb_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint32_t width, uint32_t height,
+                                     uint32_t channels, int sample_fmt, int linear_light, uint8_t *h_out,
+                                     uint64_t h_out_cap, uint64_t *out_len) {
+    if (!eng || !h_pixels || !h_out || !out_len)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+    const size_t in_bytes = (size_t)width * height * channels * item;
+    void *d_in = nullptr;
+    uint8_t *d_out = nullptr;
+    CK(cudaMalloc(&d_in, in_bytes));
+    cudaError_t e = cudaMalloc((void **)&d_out, h_out_cap);
+    if (e != cudaSuccess) {
+        cudaFree(d_in);
+        eng->error = "device allocation failed";
+        return HYD_NOMEM;
+    }
+    HYDStatusCode rc = HYD_OK;
+    e = cudaMemcpyAsync(d_in, h_pixels, in_bytes, cudaMemcpyHostToDevice, eng->st);
+    if (e != cudaSuccess) {
+        eng->error = cudaGetErrorString(e);
+        rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc == HYD_OK)
+        rc = hydb_encode_image_device(eng, d_in, width, height, channels, (int64_t)width * channels, sample_fmt,
+                                      linear_light, 0, (height + 255) >> 8, 1, d_out, h_out_cap, out_len);
+    if (rc == HYD_OK) {
+        e = cudaMemcpy(h_out, d_out, *out_len, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            eng->error = cudaGetErrorString(e);
+            rc = HYD_INTERNAL_ERROR;
+        }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int hydb_synth_fill(HydbEngine *eng, void *d_dst, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0,
+                    uint32_t full_width, uint32_t full_height, int bits, uint32_t seed, int smooth) {
+    if (!eng || !d_dst || (bits != 8 && bits != 16))
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    launch_synth_fill(d_dst, width, height, x0, y0, full_width, full_height, bits, seed, smooth, eng->st);
+    CK(cudaStreamSynchronize(eng->st));
+    CK(cudaGetLastError());
+    return HYD_OK;
+}
+
+int64_t hydb_engine_read_tap(HydbEngine *eng, int what, uint32_t tile, void *dst, uint64_t cap) {
+    if (!eng || tile >= eng->last_n || !dst)
+        return HYD_API_ERROR;
+    if (cudaSetDevice(eng->device) != cudaSuccess || cudaStreamSynchronize(eng->st) != cudaSuccess)
+        return HYD_INTERNAL_ERROR;
+    const Workspace &w = eng->ws;
+    const void *src = nullptr;
+    uint64_t bytes = 0;
+    uint32_t tmp = 0;
+    auto read_u32 = [&](const uint32_t *p) {
+        return cudaMemcpy(&tmp, p, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+    switch (what) {
+    case HYDB_TAP_XYB: src = w.dbg_xyb ? w.dbg_xyb + (size_t)tile * 65536 * 3 : nullptr; bytes = 65536 * 3 * 4; break;
+    case HYDB_TAP_DCT: src = w.dbg_dct ? w.dbg_dct + (size_t)tile * 65536 * 3 : nullptr; bytes = 65536 * 3 * 4; break;
+    case HYDB_TAP_COEF: src = w.coef + (size_t)tile * kMaxBlocks * 3 * 64; bytes = kMaxBlocks * 3 * 64 * 2; break;
+    case HYDB_TAP_NZINFO: src = w.nzinfo + (size_t)tile * kMaxBlocks * 3; bytes = kMaxBlocks * 3 * 2; break;
+    case HYDB_TAP_LFQ: src = w.lfq + (size_t)tile * 3 * kMaxBlocks; bytes = 3 * kMaxBlocks * 4; break;
+    case HYDB_TAP_SYMS:
+        if (!read_u32(w.nsyms + tile)) return HYD_INTERNAL_ERROR;
+        src = w.syms + (size_t)tile * kMaxHfSyms; bytes = (uint64_t)tmp * 4; break;
+    case HYDB_TAP_FREQS: src = w.dbg_freqs ? w.dbg_freqs + (size_t)tile * kHfClusters * kHfTokens : nullptr;
+        bytes = kHfClusters * kHfTokens * 4; break;
+    case HYDB_TAP_LFBITS:
+        if (!read_u32(w.lfbitlen + tile)) return HYD_INTERNAL_ERROR;
+        src = w.lfbits + (size_t)tile * kLfBitsWords; bytes = (((uint64_t)tmp + 31) / 32) * 4; break;
+    case HYDB_TAP_SECT: src = w.dbg_sect ? w.dbg_sect + (size_t)tile * 4 : nullptr; bytes = 16; break;
+    case HYDB_TAP_PAYLOAD: {
+        uint32_t off = 0;
+        if (!read_u32(w.frame_off + tile)) return HYD_INTERNAL_ERROR;
+        off = tmp;
+        if (!read_u32(w.frame_len + tile)) return HYD_INTERNAL_ERROR;
+        if (tmp < kSlabHeaderReserve - off) return HYD_INTERNAL_ERROR;
+        src = w.slab + (size_t)tile * kSlabBytes + kSlabHeaderReserve; bytes = tmp - (kSlabHeaderReserve - off); break;
+    }
+    case HYDB_TAP_NSYMS: src = w.nsyms + tile; bytes = 4; break;
+    case HYDB_TAP_LFBITLEN: src = w.lfbitlen + tile; bytes = 4; break;
+    default: return HYD_API_ERROR;
+    }
+    if (!src)
+        return HYD_API_ERROR;
+    if (bytes > cap)
+        return HYD_NEED_MORE_OUTPUT;
+    if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return HYD_INTERNAL_ERROR;
+    return (int64_t)bytes;
+}
+
+}  // extern "C"
+

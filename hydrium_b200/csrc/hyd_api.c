@@ -1,0 +1,403 @@
+/*
+ * hydrium_b200/csrc/hyd_api.c -- the nine libhydrium entry points, portable C99.
+ *
+ * Host side of the drop-in boundary: encoder object, argument validation with the reference's
+ * status codes and error strings, the output-buffer hand-off protocol, tile staging, and the
+ * calls into the C-ABI CUDA layer (engine.cu, hydb_* in include/hydrium_b200.h).  No pixel is
+ * touched here except to copy it into page-locked staging memory; all codec work is on the GPU
+ * and there is no CPU fallback.
+ *
+ * Reference behaviour mirrored (file:line of the reference in each function):
+ *   - libhydrium.c:16-203   lifecycle, metadata validation, buffer protocol, hyd_send_tile
+ *   - encoder.c:437-508     tile bounds, tile size at image edges, last-tile rule, header once
+ * Differences, by design (DESIGN.md "Boundary"):
+ *   - every byte (image header, frame header, TOC, payload) surfaces through hyd_flush, in send
+ *     order; the reference writes the header fields straight into the lent buffer during
+ *     hyd_send_tile.  The concatenation of all surfaced bytes is identical.
+ *   - with hydb_encoder_set_batch(n > 1) tiles are encoded n at a time; hyd_flush then returns
+ *     HYD_OK with nothing written until a batch completes.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/hydrium_b200.h"
+
+#define TILE 256u
+/* worst-case staged bytes of one tile: 256 rows x 256 px x 4 samples x 2 bytes */
+#define TILE_STAGE_BYTES (256u * 256u * 4u * 2u)
+/* device output bytes reserved per queued tile (the engine reports overflow, never overruns) */
+#define TILE_OUT_BYTES (768u * 1024u)
+
+struct HYDEncoder {
+    HYDImageMetadata metadata;
+    int have_metadata;
+    int one_frame;
+    const char *error;
+
+    /* lent output buffer (libhydrium.c:114-145) */
+    uint8_t *out;
+    size_t out_len, out_pos;
+
+    /* bytes produced but not yet handed to the caller */
+    uint8_t *pend;
+    size_t pend_len, pend_cap, pend_pos;
+
+    int wrote_header;
+    int last_tile;
+
+    /* GPU side */
+    int device;
+    uint32_t batch;
+    HydbEngine *engine;
+    uint8_t *stage_host;   /* page-locked, batch * TILE_STAGE_BYTES */
+    uint8_t *stage_dev;
+    uint8_t *out_dev;      /* batch * TILE_OUT_BYTES */
+    HydbTile *tiles;
+    uint32_t queued;
+    size_t stage_used;
+    char errbuf[256];
+};
+
+static uint32_t env_u32(const char *name, uint32_t fallback) {
+    const char *v = getenv(name);
+    if (!v || !*v)
+        return fallback;
+    char *end = NULL;
+    unsigned long x = strtoul(v, &end, 10);
+    return (end && *end == 0 && x > 0 && x <= 65536) ? (uint32_t)x : fallback;
+}
+
+HYDRIUM_EXPORT HYDEncoder *hyd_encoder_new(void) { /* libhydrium.c:16-19 */
+    HYDEncoder *enc = calloc(1, sizeof(*enc));
+    if (!enc)
+        return NULL;
+    enc->device = -1;
+    const char *dev = getenv("HYDRIUM_B200_DEVICE");
+    if (dev && *dev)
+        enc->device = atoi(dev);
+    enc->batch = env_u32("HYDRIUM_B200_BATCH", 1);
+    return enc;
+}
+
+static void release_gpu(HYDEncoder *enc) {
+    if (enc->stage_host) hydb_host_free(enc->stage_host);
+    if (enc->stage_dev) hydb_device_free(enc->stage_dev);
+    if (enc->out_dev) hydb_device_free(enc->out_dev);
+    if (enc->engine) hydb_engine_destroy(enc->engine);
+    free(enc->tiles);
+    enc->stage_host = enc->stage_dev = enc->out_dev = NULL;
+    enc->engine = NULL;
+    enc->tiles = NULL;
+    enc->queued = 0;
+    enc->stage_used = 0;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydrium.c:21-44 */
+    if (!enc)
+        return HYD_OK;
+    release_gpu(enc);
+    free(enc->pend);
+    free(enc);
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *enc, uint32_t tiles) {
+    if (!enc || !tiles || tiles > 65536 || enc->engine) {
+        if (enc)
+            enc->error = "batch size must be set before the first tile";
+        return HYD_API_ERROR;
+    }
+    enc->batch = tiles;
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_device(HYDEncoder *enc, int device) {
+    if (!enc || enc->engine) {
+        if (enc)
+            enc->error = "device must be set before the first tile";
+        return HYD_API_ERROR;
+    }
+    enc->device = device;
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMetadata *md) { /* libhydrium.c:46-112 */
+    if (!md->width || !md->height) {
+        enc->error = "invalid zero-width or zero-height";
+        return HYD_API_ERROR;
+    }
+    const uint64_t w = md->width, h = md->height;
+    if (w > (UINT64_C(1) << 30) || h > (UINT64_C(1) << 30)) {
+        enc->error = "width or height out of bounds";
+        return HYD_API_ERROR;
+    }
+    if (w * h > (UINT64_C(1) << 40)) {
+        enc->error = "width times height out of bounds";
+        return HYD_API_ERROR;
+    }
+    if (md->tile_size_shift_x < -1 || md->tile_size_shift_x > 3 ||
+        md->tile_size_shift_y < -1 || md->tile_size_shift_y > 3) {
+        enc->error = "tile_size_shift_y must be between -1 and 3"; /* sic, for x too (libhydrium.c:70-77) */
+        return HYD_API_ERROR;
+    }
+    const int one_frame = md->tile_size_shift_x < 0 || md->tile_size_shift_y < 0;
+    if (one_frame ? (w > TILE || h > TILE) : (md->tile_size_shift_x != 0 || md->tile_size_shift_y != 0)) {
+        /* multi-group frames are outside this library's accelerated path (scope) */
+        enc->error = "tile size not supported by the B200 encoder (use tile_size_shift 0/0)";
+        return HYD_API_ERROR;
+    }
+    enc->metadata = *md;
+    enc->one_frame = one_frame;
+    enc->have_metadata = 1;
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_provide_output_buffer(HYDEncoder *enc, uint8_t *buffer, size_t buffer_len) {
+    /* libhydrium.c:114-135 */
+    if (buffer_len < 64) {
+        enc->error = "provided buffer must be at least 64 bytes long";
+        return HYD_API_ERROR;
+    }
+    if (enc->out) {
+        enc->error = "buffer was already provided";
+        return HYD_API_ERROR;
+    }
+    if (!buffer) {
+        enc->error = "buffer may not be null";
+        return HYD_API_ERROR;
+    }
+    enc->out = buffer;
+    enc->out_len = buffer_len;
+    enc->out_pos = 0;
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_release_output_buffer(HYDEncoder *enc, size_t *written) { /* libhydrium.c:137-145 */
+    if (!enc->out) {
+        enc->error = "buffer was never provided";
+        return HYD_API_ERROR;
+    }
+    *written = enc->out_pos;
+    enc->out = NULL;
+    return HYD_OK;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-166 */
+    if (enc->one_frame && !enc->last_tile)
+        return HYD_OK;
+    if (!enc->out) {
+        enc->error = "buffer was never provided";
+        return HYD_API_ERROR;
+    }
+    size_t n = enc->out_len - enc->out_pos;
+    if (n > enc->pend_len - enc->pend_pos)
+        n = enc->pend_len - enc->pend_pos;
+    memcpy(enc->out + enc->out_pos, enc->pend + enc->pend_pos, n);
+    enc->out_pos += n;
+    enc->pend_pos += n;
+    if (enc->pend_pos >= enc->pend_len) {
+        enc->pend_pos = enc->pend_len = 0;
+        return HYD_OK;
+    }
+    return HYD_NEED_MORE_OUTPUT;
+}
+
+HYDRIUM_EXPORT const char *hyd_error_message_get(HYDEncoder *enc) { return enc->error; } /* libhydrium.c:168-170 */
+
+HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *enc, const uint8_t *icc_data, size_t icc_size) {
+    /* libhydrium.c:242-259.  ICC tagging is one-frame-only in the reference and outside the
+     * accelerated path; clearing is a no-op, setting reports the tile-mode error. */
+    if (!icc_data && !icc_size)
+        return HYD_OK;
+    if (!enc->one_frame) {
+        enc->error = "one-frame mode required to set the suggested ICC profile";
+        return HYD_API_ERROR;
+    }
+    if (!icc_size || !icc_data || icc_size > UINT32_MAX) {
+        enc->error = "invalid ICC size or data buffer";
+        return HYD_API_ERROR;
+    }
+    enc->error = "ICC tagging is not supported by the B200 encoder";
+    return HYD_API_ERROR;
+}
+
+static HYDStatusCode pend_reserve(HYDEncoder *enc, size_t extra) {
+    if (enc->pend_len + extra <= enc->pend_cap)
+        return HYD_OK;
+    size_t cap = enc->pend_cap ? enc->pend_cap : 4096;
+    while (cap < enc->pend_len + extra)
+        cap *= 2;
+    uint8_t *p = realloc(enc->pend, cap);
+    if (!p)
+        return HYD_NOMEM;
+    enc->pend = p;
+    enc->pend_cap = cap;
+    return HYD_OK;
+}
+
+static HYDStatusCode gpu_error(HYDEncoder *enc, HYDStatusCode rc) {
+    const char *msg = enc->engine ? hydb_engine_error(enc->engine) : "CUDA engine unavailable";
+    strncpy(enc->errbuf, msg, sizeof(enc->errbuf) - 1);
+    enc->errbuf[sizeof(enc->errbuf) - 1] = 0;
+    enc->error = enc->errbuf;
+    return rc < HYD_ERROR_START ? rc : HYD_INTERNAL_ERROR;
+}
+
+static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
+    if (enc->engine)
+        return HYD_OK;
+    HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->batch);
+    if (rc < HYD_ERROR_START) {
+        enc->error = "could not create the CUDA engine (no usable GPU? this encoder has no CPU path)";
+        return rc;
+    }
+    enc->stage_host = hydb_host_alloc((size_t)enc->batch * TILE_STAGE_BYTES);
+    enc->stage_dev = hydb_device_alloc((size_t)enc->batch * TILE_STAGE_BYTES);
+    enc->out_dev = hydb_device_alloc((size_t)enc->batch * TILE_OUT_BYTES);
+    enc->tiles = calloc(enc->batch, sizeof(HydbTile));
+    if (!enc->stage_host || !enc->stage_dev || !enc->out_dev || !enc->tiles) {
+        release_gpu(enc);
+        enc->error = "out of memory allocating tile staging";
+        return HYD_NOMEM;
+    }
+    return HYD_OK;
+}
+
+/* encode everything queued and move the frames to the pending-output queue */
+static HYDStatusCode run_batch(HYDEncoder *enc) {
+    if (!enc->queued)
+        return HYD_OK;
+    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    HYDStatusCode rc = hydb_engine_encode_tiles(enc->engine, enc->tiles, enc->queued, enc->out_dev,
+                                                (uint64_t)enc->batch * TILE_OUT_BYTES, 0);
+    if (rc < HYD_ERROR_START)
+        return gpu_error(enc, rc);
+    uint64_t bytes = 0;
+    rc = hydb_engine_finish(enc->engine, &bytes);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    rc = pend_reserve(enc, (size_t)bytes);
+    if (rc < HYD_ERROR_START)
+        return rc;
+    if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    enc->pend_len += (size_t)bytes;
+    enc->queued = 0;
+    enc->stage_used = 0;
+    return HYD_OK;
+}
+
+/* copy one tile's samples into staging and fill its device-side descriptor */
+static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3], ptrdiff_t row_stride,
+                       ptrdiff_t pixel_stride, size_t item) {
+    uint8_t *dst = enc->stage_host + enc->stage_used;
+    uint8_t *ddst = enc->stage_dev + enc->stage_used;
+    const uint8_t *p[3] = {buffer[0], buffer[1], buffer[2]};
+    const uint32_t w = t->width, h = t->height;
+    const uint8_t *lo = p[0] < p[1] ? (p[0] < p[2] ? p[0] : p[2]) : (p[1] < p[2] ? p[1] : p[2]);
+    const uint8_t *hi = p[0] > p[1] ? (p[0] > p[2] ? p[0] : p[2]) : (p[1] > p[2] ? p[1] : p[2]);
+    size_t used;
+    if (pixel_stride > 0 && pixel_stride <= 4 && (size_t)(hi - lo) < (size_t)pixel_stride * item) {
+        /* interleaved (RGB / RGBA ...): copy whole row spans, keep the caller's sample offsets */
+        const size_t span = (size_t)w * (size_t)pixel_stride * item;
+        for (uint32_t y = 0; y < h; y++)
+            memcpy(dst + (size_t)y * span, lo + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
+        for (int k = 0; k < 3; k++)
+            t->plane[k] = ddst + (p[k] - lo);
+        t->row_stride = (int64_t)w * pixel_stride;
+        t->pixel_stride = pixel_stride;
+        used = span * h;
+    } else if (pixel_stride == 1) {
+        /* planar: three contiguous planes */
+        const size_t span = (size_t)w * item;
+        for (int k = 0; k < 3; k++) {
+            uint8_t *pd = dst + (size_t)k * span * h;
+            for (uint32_t y = 0; y < h; y++)
+                memcpy(pd + (size_t)y * span, p[k] + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
+            t->plane[k] = ddst + (size_t)k * span * h;
+        }
+        t->row_stride = w;
+        t->pixel_stride = 1;
+        used = 3 * span * h;
+    } else {
+        /* anything else: gather to packed RGB */
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                const ptrdiff_t o = ((ptrdiff_t)y * row_stride + (ptrdiff_t)x * pixel_stride) * (ptrdiff_t)item;
+                uint8_t *q = dst + ((size_t)y * w + x) * 3 * item;
+                for (int k = 0; k < 3; k++)
+                    memcpy(q + k * item, p[k] + o, item);
+            }
+        for (int k = 0; k < 3; k++)
+            t->plane[k] = ddst + k * item;
+        t->row_stride = (int64_t)w * 3;
+        t->pixel_stride = 3;
+        used = (size_t)w * h * 3 * item;
+    }
+    enc->stage_used += (used + 255) & ~(size_t)255;
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const buffer[3], uint32_t tile_x,
+                                           uint32_t tile_y, ptrdiff_t row_stride, ptrdiff_t pixel_stride,
+                                           int is_last, HYDSampleFormat sample_fmt) {
+    /* libhydrium.c:172-203 */
+    if (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16 && sample_fmt != HYD_FLOAT32) {
+        enc->error = "Invalid Sample Format";
+        return HYD_API_ERROR;
+    }
+    if (!enc->have_metadata) {
+        enc->error = "hyd_set_metadata must be called before hyd_send_tile";
+        return HYD_API_ERROR;
+    }
+    /* encoder.c:437-472: bounds and the tile's real size */
+    const uint64_t W = enc->metadata.width, H = enc->metadata.height;
+    const uint64_t span = enc->one_frame ? 2048 : TILE;
+    if (tile_x >= (W + span - 1) / span || tile_y >= (H + span - 1) / span) {
+        enc->error = "tile out of bounds";
+        return HYD_API_ERROR;
+    }
+    if (sample_fmt == HYD_FLOAT32) {
+        enc->error = "HYD_FLOAT32 input is not supported by the B200 encoder";
+        return HYD_API_ERROR;
+    }
+    HYDStatusCode rc = ensure_gpu(enc);
+    if (rc < HYD_ERROR_START)
+        return rc;
+    const uint32_t tw = (uint32_t)(((uint64_t)tile_x + 1) * span > W ? W - (uint64_t)tile_x * span : span);
+    const uint32_t th = (uint32_t)(((uint64_t)tile_y + 1) * span > H ? H - (uint64_t)tile_y * span : span);
+    /* encoder.c:482-485 */
+    enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span >= W && ((uint64_t)tile_y + 1) * span >= H) : !!is_last;
+
+    if (!enc->wrote_header) { /* encoder.c:490-494: image header precedes the first frame */
+        rc = pend_reserve(enc, 64);
+        if (rc < HYD_ERROR_START)
+            return rc;
+        const int64_t hb = hydb_image_header((uint32_t)W, (uint32_t)H, enc->pend + enc->pend_len, 64);
+        if (hb < 0)
+            return HYD_INTERNAL_ERROR;
+        enc->pend_len += (size_t)hb;
+        enc->wrote_header = 1;
+    }
+
+    HydbTile *t = &enc->tiles[enc->queued];
+    memset(t, 0, sizeof(*t));
+    t->width = tw;
+    t->height = th;
+    t->x0 = tile_x * TILE;
+    t->y0 = tile_y * TILE;
+    t->image_width = (uint32_t)W;
+    t->image_height = (uint32_t)H;
+    t->is_last = enc->one_frame || enc->last_tile; /* encoder.c:339 */
+    t->sample_fmt = sample_fmt;
+    t->linear_light = enc->metadata.linear_light != 0;
+    stage_tile(enc, t, buffer, row_stride, pixel_stride, sample_fmt == HYD_UINT8 ? 1 : 2);
+    enc->queued++;
+
+    if (enc->queued == enc->batch || enc->last_tile) {
+        rc = run_batch(enc);
+        if (rc < HYD_ERROR_START)
+            return rc;
+    }
+    return HYD_OK; /* never HYD_NEED_MORE_OUTPUT, like the reference (libhydrium.c:195-202) */
+}

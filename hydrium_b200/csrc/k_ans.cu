@@ -1,0 +1,450 @@
+// hydrium_b200/csrc/k_ans.cu
+//
+// Stage 4: everything after tokenisation, one CTA per tile:
+//   1. ANS model from the tile's histograms: normalisation, alias split, inverse slot table,
+//      exact reciprocals                                   (reference: entropy.c:943-978, 184-301)
+//   2. section D (ANS stream header tail)                  (entropy.c:563-572, 303-369, 980-1001)
+//   3. payload prefix  A | L | B | D  spliced bit-exactly into the tile's output slab
+//                                                          (encoder.c:834-843, 959-967, bitwriter.c:80-108)
+//   4. the reverse rANS state chain                        (entropy.c:1083-1120)
+//   5. forward bit packing of [state][renorm words + residue bits]   (entropy.c:1122-1147)
+//   6. frame header + TOC entry                            (encoder.c:327-435, 992-1005)
+//
+// The chain (4) is the one inherently serial part of the codec: one 32-bit state threads
+// through every symbol of the group.  It runs in warp 0 with every lane carrying the same state
+// (so the slot-table read is a shared-memory broadcast and nothing diverges); the lanes differ
+// only in which symbol's constants they hold: each lane fetches one symbol of the current
+// 32-symbol batch and its (m, packed) constants, and the unrolled step loop broadcasts them with
+// shuffles that do not depend on the state.  See ans_chain.cuh for the per-step critical path.
+// All other warps build tables before and pack bits after the chain.
+#include "ans_chain.cuh"
+#include "headers.cuh"
+#include "kernels.h"
+#include "prefix_coder.cuh"
+
+namespace hydb {
+
+constexpr int kAnsThreads = 256;
+constexpr int kDBitsWords = 384;
+
+struct AnsShared {
+    uint16_t inv[kHfClusters * kAnsTotal];              // 73,728 B inverse alias table
+    AnsSymInfo info[kHfClusters * kHfTokens];           //  4,608 B
+    AnsCluster cl[kHfClusters];                         //  5,256 B
+    uint32_t hist[kHfClusters * kHfTokens];             //  2,304 B
+    uint32_t dbits[kDBitsWords];                        //  1,536 B
+    uint32_t scan_a[kAnsThreads], scan_b[kAnsThreads];  //  2,048 B
+    uint32_t alpha[kHfClusters];
+    int log_alpha;
+    uint32_t dbitlen, nwords, final_state, err, ebits_total;
+};
+
+int ans_encode_smem_bytes() { return (int)sizeof(AnsShared); }
+
+// 32 bits of `src` starting at bit `sb` (may be negative / run past the end); bits outside
+// [0, nbits) read as zero
+__device__ __forceinline__ uint32_t fetch32(const uint32_t *__restrict__ src, uint32_t nbits, int64_t sb) {
+    const int64_t i = sb >> 5;
+    const uint32_t r = (uint32_t)(sb & 31);
+    const int64_t nw = ((int64_t)nbits + 31) >> 5;
+    auto word = [&](int64_t k) -> uint32_t {
+        if (k < 0 || k >= nw)
+            return 0u;
+        uint32_t v = src[k];
+        if (k == nw - 1 && (nbits & 31))
+            v &= (1u << (nbits & 31)) - 1u;
+        return v;
+    };
+    const uint32_t a = word(i), b = word(i + 1);
+    return r ? ((a >> r) | (b << (32 - r))) : a;
+}
+
+// CTA-cooperative append of a bit string at an arbitrary bit offset.  Destination words fully
+// covered by this string are stored, boundary words are OR-ed (destination pre-zeroed).
+__device__ __forceinline__ void append_bits(uint32_t *__restrict__ dst, uint64_t dbit, const uint32_t *__restrict__ src,
+                                            uint32_t nbits, uint32_t tid, uint32_t nthreads) {
+    if (!nbits)
+        return;
+    const uint64_t first = dbit >> 5, last = (dbit + nbits - 1) >> 5;
+    for (uint64_t w = first + tid; w <= last; w += nthreads) {
+        const uint32_t v = fetch32(src, nbits, (int64_t)(w * 32) - (int64_t)dbit);
+        const bool full = w * 32 >= dbit && w * 32 + 32 <= dbit + nbits;
+        if (full)
+            dst[w] = v;
+        else if (v)
+            atomicOr(&dst[w], v);
+    }
+}
+
+// block-wide exclusive scan of two values per thread (256 threads)
+__device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *sa, uint32_t *sb, uint32_t tid,
+                                            uint32_t &total_a, uint32_t &total_b) {
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t va = __shfl_up_sync(0xFFFFFFFFu, ia, d), vb = __shfl_up_sync(0xFFFFFFFFu, ib, d);
+        if (lane >= (uint32_t)d) {
+            ia += va;
+            ib += vb;
+        }
+    }
+    if (lane == 31) {
+        sa[warp] = ia;
+        sb[warp] = ib;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wa = lane < kAnsThreads / 32 ? sa[lane] : 0, wb = lane < kAnsThreads / 32 ? sb[lane] : 0;
+        uint32_t xa = wa, xb = wb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t va = __shfl_up_sync(0xFFFFFFFFu, xa, d), vb = __shfl_up_sync(0xFFFFFFFFu, xb, d);
+            if (lane >= (uint32_t)d) {
+                xa += va;
+                xb += vb;
+            }
+        }
+        if (lane < kAnsThreads / 32) {
+            sa[lane] = xa - wa;
+            sb[lane] = xb - wb;
+        }
+        if (lane == kAnsThreads / 32 - 1) {
+            sa[32] = xa;
+            sb[32] = xb;
+        }
+    }
+    __syncthreads();
+    const uint32_t ea = sa[warp] + ia - a, eb = sb[warp] + ib - b;
+    total_a = sa[32];
+    total_b = sb[32];
+    a = ea;
+    b = eb;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kAnsThreads)
+k_ans_encode(Workspace ws, Templates tp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AnsShared &s = *reinterpret_cast<AnsShared *>(smem_raw);
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileDesc t = ws.tiles[tile];
+    const uint32_t N = ws.nsyms[tile];
+    const uint32_t *__restrict__ sy = ws.syms + (size_t)tile * kMaxHfSyms;
+    uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
+    uint16_t *__restrict__ fwords = ws.fwords + (size_t)tile * kMaxHfSyms;
+    uint8_t *slab = ws.slab + (size_t)tile * kSlabBytes;
+    uint32_t *payload = reinterpret_cast<uint32_t *>(slab + kSlabHeaderReserve);
+    constexpr uint32_t kPayloadCapBits = (uint32_t)(kSlabBytes - kSlabHeaderReserve) * 8u - 64u;
+
+    // ---- 1. model ---------------------------------------------------------------------------
+    for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kAnsThreads)
+        s.hist[i] = ws.hist[(size_t)tile * kHfClusters * kHfTokens + i];
+    if (tid == 0) {
+        s.err = 0;
+        s.nwords = 0;
+    }
+    __syncthreads();
+    if (tid < (uint32_t)kHfClusters) {
+        uint32_t a = 0;
+        for (uint32_t k = 0; k < (uint32_t)kHfTokens; k++)
+            if (s.hist[tid * kHfTokens + k])
+                a = k + 1;
+        s.alpha[tid] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t mx = 0;
+        for (int c = 0; c < kHfClusters; c++)
+            mx = s.alpha[c] > mx ? s.alpha[c] : mx;
+        int la = mx ? ceil_log2_u32(mx) : 0;
+        s.log_alpha = la < 5 ? 5 : la;   // reference: entropy.c:952 (<= 6 because tokens < 64)
+    }
+    __syncthreads();
+    const int log_alpha = s.log_alpha;
+    if (tid < (uint32_t)kHfClusters) {
+        const uint32_t c = tid, a = s.alpha[c];
+        AnsCluster &cl = s.cl[c];
+        if (!a) {
+            cl.alpha = 0;
+            cl.single = 0;
+            for (int k = 0; k < kHfTokens; k++) {
+                cl.freq[k] = 0;
+                cl.cum[k] = 0;
+            }
+        } else {
+            const int single = ans_normalise(&s.hist[c * kHfTokens], a);
+            if (single < 0 || !ans_build_alias(cl, &s.hist[c * kHfTokens], a, log_alpha, single > 0))
+                atomicOr(&s.err, (uint32_t)kErrAlias);
+        }
+        for (uint32_t k = 0; k < (uint32_t)kHfTokens; k++) {
+            s.info[c * kHfTokens + k] = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
+            if (ws.dbg_freqs)
+                ws.dbg_freqs[((size_t)tile * kHfClusters + c) * kHfTokens + k] = cl.freq[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t idx = tid; idx < kHfClusters * kAnsTotal; idx += kAnsThreads) {
+        const uint32_t c = idx >> 12, slot = idx & (kAnsTotal - 1);
+        if (s.alpha[c]) {
+            uint32_t sym, off;
+            ans_slot_symbol(s.cl[c], slot, log_alpha, sym, off);
+            s.inv[c * kAnsTotal + s.cl[c].cum[sym] + off] = (uint16_t)slot;
+        }
+    }
+    // ---- 2. section D -------------------------------------------------------------------------
+    if (tid == 0) {
+        BitSink bw;
+        bw.init(s.dbits, kDBitsWords);
+        bw.put_bool(0);                               // use_prefix_codes = 0
+        bw.put((uint32_t)(log_alpha - 5), 2);
+        for (int c = 0; c < kHfClusters; c++)
+            ps_put_hybrid_cfg(bw, 4, 1, 0, log_alpha);
+        for (int c = 0; c < kHfClusters; c++)
+            ans_put_histogram(bw, s.cl[c].freq, s.alpha[c]);
+        bw.flush_partial();
+        s.dbitlen = bw.bitlen();
+        if (bw.overflow)
+            s.err |= kErrSlab;
+    }
+    __syncthreads();
+
+    // ---- 3. payload prefix A | L | B | D ---------------------------------------------------------
+    const uint32_t la = tp.bits[0], lb = tp.bits[1 + t.shape], ll = ws.lfbitlen[tile], ld = s.dbitlen;
+    const uint32_t e_start = la + ll + lb + ld;
+    const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !s.err && N > 0 && log_alpha <= 6;
+    for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kAnsThreads)
+        payload[w] = 0;
+    __syncthreads();
+    if (sane) {
+        append_bits(payload, 0, tp.words, la, tid, kAnsThreads);
+        append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kAnsThreads);
+        append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kAnsThreads);
+        append_bits(payload, (uint64_t)la + ll + lb, s.dbits, ld, tid, kAnsThreads);
+    }
+    __syncthreads();
+
+    // ---- 4. the chain ------------------------------------------------------------------------------
+    if (warp == 0 && sane) {
+        const uint32_t FULL = 0xFFFFFFFFu;
+        const int nbatch = (int)((N + 31) >> 5);
+        auto fetch = [&](int bi, uint32_t &m, uint32_t &pk) {
+            m = 0;
+            pk = 0;
+            if (bi >= 0) {
+                const uint32_t p = (uint32_t)bi * 32u + lane;
+                if (p < N) {
+                    const uint32_t sym = sy[p];
+                    const AnsSymInfo inf = s.info[hf_cluster(sym) * kHfTokens + hf_token(sym)];
+                    m = inf.m;
+                    pk = inf.packed;
+                }
+            }
+        };
+        uint32_t cur_m, cur_pk, nxt_m, nxt_pk;
+        fetch(nbatch - 1, cur_m, cur_pk);
+        fetch(nbatch - 2, nxt_m, nxt_pk);
+        // virtual step that "produced" the initial state 0x130000 = (0x130 << 12) | 0
+        uint32_t x;
+        uint32_t carry_flag, carry_word;
+        {
+            const uint32_t f_first = asi_freq(__shfl_sync(FULL, cur_pk, (N - 1) & 31));
+            carry_flag = ((kAnsInitState >> 20) >= f_first) ? 1u : 0u;
+            carry_word = kAnsInitState & 0xFFFFu;
+            x = carry_flag ? (kAnsInitState >> 16) : kAnsInitState;
+        }
+        uint32_t cnt = 0;
+        uint32_t lowest_flag = 0xFFFFFFFFu;   // position of the most recent (lowest) flagged symbol
+        uint32_t gap_err = 0;
+        for (int bi = nbatch - 1; bi >= 0; --bi) {
+            const uint32_t base = (uint32_t)bi * 32u;
+            const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
+            // frequency of the symbol coded after each lane's symbol (= previous in stream order)
+            const uint32_t f_cur = asi_freq(cur_pk);
+            const uint32_t f_up = __shfl_up_sync(FULL, f_cur, 1);
+            const uint32_t f_nx = asi_freq(__shfl_sync(FULL, nxt_pk, 31));
+            const uint32_t f_prev = lane ? f_up : (bi ? f_nx : 0x7FFFFFFFu);
+            uint32_t mask = carry_flag << jtop;
+            uint32_t myword = carry_word;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+                if (j <= jtop) {   // warp-uniform
+                    const uint32_t m = __shfl_sync(FULL, cur_m, j);
+                    const uint32_t pk = __shfl_sync(FULL, cur_pk, j);
+                    const uint32_t fn = __shfl_sync(FULL, f_prev, j);
+                    bool fl;
+                    uint32_t word;
+                    ans_step(x, m, pk, s.inv, fn, fl, word);
+                    if (j > 0) {
+                        mask |= (fl ? 1u : 0u) << (j > 0 ? j - 1 : 0);
+                        if (fl && lane == (uint32_t)(j - 1))
+                            myword = word;
+                    } else {
+                        carry_flag = fl ? 1u : 0u;
+                        carry_word = word;
+                    }
+                }
+            }
+            // record this batch's flags and words (words in chain order = descending position)
+            if (lane == 0)
+                flags[bi] = mask;
+            if ((mask >> lane) & 1u) {
+                const uint32_t above = __popc(mask & ~((2u << lane) - 1u));
+                fwords[cnt + above] = (uint16_t)myword;
+            }
+            if (mask) {
+                const uint32_t hi = base + 31u - (uint32_t)__clz(mask), lo = base + (uint32_t)__ffs(mask) - 1u;
+                if (lowest_flag != 0xFFFFFFFFu && lowest_flag - hi >= 65536u)
+                    gap_err = 1;
+                lowest_flag = lo;
+            }
+            cnt += __popc(mask);
+            cur_m = nxt_m;
+            cur_pk = nxt_pk;
+            fetch(bi - 2, nxt_m, nxt_pk);
+        }
+        if (lowest_flag != 0xFFFFFFFFu && lowest_flag >= 65536u)
+            gap_err = 1;   // the reference keeps this distance in a uint16_t (entropy.c:16, 1094, 1123)
+        if (lane == 0) {
+            s.nwords = cnt;
+            s.final_state = x;
+            if (gap_err)
+                s.err |= kErrAnsGap;
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. forward packing of section E -------------------------------------------------------------
+    const uint32_t W = s.nwords;
+    const uint64_t total_bits64 = (uint64_t)e_start + 32u + ws.resbits[tile] + 16ull * W;
+    const bool fits = sane && total_bits64 <= kPayloadCapBits;
+    if (tid == 0 && sane && !fits)
+        s.err |= kErrSlab;
+    const uint32_t total_bits = fits ? (uint32_t)total_bits64 : 0;
+    if (fits) {
+        for (uint32_t w = (e_start >> 5) + 3 + tid; w <= (total_bits >> 5) + 1; w += kAnsThreads)
+            payload[w] = 0;
+    }
+    __syncthreads();
+    {
+        const uint32_t nchunks = (N + 31) >> 5, cpt = (nchunks + kAnsThreads - 1) / kAnsThreads;
+        const uint32_t c0 = tid * cpt < nchunks ? tid * cpt : nchunks;
+        const uint32_t c1 = c0 + cpt < nchunks ? c0 + cpt : nchunks;
+        uint32_t bits = 0, nfl = 0;
+        if (fits) {
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t fl = flags[c];
+                nfl += __popc(fl);
+                const uint4 *q = reinterpret_cast<const uint4 *>(sy + (size_t)c * 32);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 v = q[k];
+                    const uint32_t p = c * 32 + k * 4;
+                    bits += (p + 0 < N ? hf_nbits(v.x) : 0) + (p + 1 < N ? hf_nbits(v.y) : 0) +
+                            (p + 2 < N ? hf_nbits(v.z) : 0) + (p + 3 < N ? hf_nbits(v.w) : 0);
+                }
+            }
+            bits += 16 * nfl;
+        }
+        uint32_t tot_bits, tot_fl;
+        block_scan2(bits, nfl, s.scan_a, s.scan_b, tid, tot_bits, tot_fl);
+        if (fits) {
+            if (tid == 0) {
+                s.ebits_total = 32u + tot_bits;
+                if (tot_fl != W || (uint64_t)e_start + 32u + tot_bits != total_bits64)
+                    s.err |= kErrSlab;   // internal consistency check
+                // final state, low half first (entropy.c:1127-1130)
+                const uint32_t st = s.final_state, sh = e_start & 31u, w0 = e_start >> 5;
+                atomicOr(&payload[w0], st << sh);
+                if (sh)
+                    atomicOr(&payload[w0 + 1], st >> (32 - sh));
+            }
+            const uint64_t start = (uint64_t)e_start + 32u + bits;
+            uint32_t wpos = (uint32_t)(start >> 5);
+            uint32_t nacc = (uint32_t)(start & 31u);
+            uint64_t acc = 0;
+            bool first = nacc != 0;
+            int widx = (int)W - 1 - (int)nfl;   // next renormalisation word in forward order
+            auto put = [&](uint32_t v, uint32_t n) {
+                acc |= (uint64_t)v << nacc;
+                nacc += n;
+                if (nacc >= 32) {
+                    if (first)
+                        atomicOr(&payload[wpos], (uint32_t)acc);
+                    else
+                        payload[wpos] = (uint32_t)acc;
+                    first = false;
+                    wpos++;
+                    acc >>= 32;
+                    nacc -= 32;
+                }
+            };
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t fl = flags[c];
+                const uint4 *q = reinterpret_cast<const uint4 *>(sy + (size_t)c * 32);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 v = q[k];
+                    const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t p = c * 32 + k * 4 + u;
+                        if (p < N) {
+                            if ((fl >> (k * 4 + u)) & 1u)
+                                put(fwords[widx--], 16);
+                            const uint32_t nb = hf_nbits(sv[u]);
+                            if (nb)
+                                put(hf_residue(sv[u]), nb);
+                        }
+                    }
+                }
+            }
+            if (nacc && (uint32_t)acc)
+                atomicOr(&payload[wpos], (uint32_t)acc);
+        }
+    }
+    __syncthreads();
+
+    // ---- 6. frame header + TOC, lengths ------------------------------------------------------------
+    if (tid == 0) {
+        uint32_t err = s.err;
+        if (!sane && !err)
+            err |= kErrSlab;
+        uint32_t flen = 0, foff = kSlabHeaderReserve;
+        if (fits && !err) {
+            const uint32_t payload_bytes = (total_bits + 7) >> 3;
+            uint32_t hw[12];
+            BitSink bw;
+            bw.init(hw, 12);
+            put_frame_header(bw, (t.flags & kTileCrop) != 0, t.x0, t.y0, t.w, t.h, (t.flags & kTileLast) != 0);
+            const bool ok = put_toc_entry(bw, payload_bytes);
+            bw.flush_partial();
+            const uint32_t hb = bw.bitlen() >> 3;
+            if (!ok || bw.overflow || hb > (uint32_t)kSlabHeaderReserve) {
+                err |= kErrSlab;
+            } else {
+                foff = kSlabHeaderReserve - hb;
+                for (uint32_t i = 0; i < hb; i++)
+                    slab[foff + i] = (uint8_t)(hw[i >> 2] >> (8 * (i & 3)));
+                flen = hb + payload_bytes;
+            }
+        }
+        ws.frame_off[tile] = foff;
+        ws.frame_len[tile] = flen;
+        if (err)
+            atomicOr(&ws.tile_err[tile], err);
+        if (ws.dbg_sect) {
+            ws.dbg_sect[tile * 4 + 0] = la + ll + lb;
+            ws.dbg_sect[tile * 4 + 1] = ld;
+            ws.dbg_sect[tile * 4 + 2] = fits ? s.ebits_total : 0;
+            ws.dbg_sect[tile * 4 + 3] = total_bits;
+        }
+    }
+}
+
+void launch_ans_encode(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st) {
+    cudaFuncSetAttribute(k_ans_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
+    k_ans_encode<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws, t);
+}
+
+}  // namespace hydb

@@ -1,0 +1,181 @@
+// hydrium_b200/csrc/k_hf_tokens.cu
+//
+// Stage 2: quantised HF coefficients -> the tile's ANS symbol stream + per-cluster histograms.
+// Replaces initialize_hf_coeffs / hyd_entropy_send_symbol for the HF stream
+// (reference: encoder.c:689-750, entropy.c:427-471, 526-544).
+//
+// The reference walks blocks, channels (Y, X, B) and scan positions serially and stops a block
+// after its last non-zero.  Here a warp owns one (block, channel): two ballots give the 64-bit
+// non-zero mask, from which every lane derives, for its own scan position j,
+//   * whether the symbol exists            (j <= last non-zero)
+//   * "non-zeros left" before j            nz - popc(mask below j)
+//   * "previous coefficient non-zero"      bit j-1 of the mask (or nz <= 4 for the first)
+// and therefore its context cluster, with no serial dependence.  Only the CLUSTER of a context
+// matters for the bitstream (the context map collapses the 1485 contexts onto 9 clusters,
+// encoder.c:862-877):
+//   non-zero-count symbol of channel index i      -> cluster i           (ctx = 3*g(pred)+i, ctx % 3)
+//   coefficient, ctx = 458 i + 111 + prev + 2 (n+f) -> 3 + prev + 2 ((i + n + f) mod 3)
+// so the neighbour-predicted count of encoder.c:670-687 never influences the output.
+// Symbol offsets come from one CTA-wide exclusive scan over the <= 3072 (block, channel) counts.
+#include "common.cuh"
+#include "kernels.h"
+#include "tables.cuh"
+
+namespace hydb {
+
+__constant__ uint8_t c_freq_ctx[64] = {HYDB_FREQ_CTX};
+
+constexpr int kTokThreads = 1024;
+
+__global__ void __launch_bounds__(kTokThreads)
+k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef, const uint16_t *__restrict__ nzinfo,
+            uint32_t *__restrict__ syms, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ resbits,
+            uint32_t *__restrict__ hist, uint32_t *__restrict__ tile_err) {
+    __shared__ uint16_t s_info[3 * kMaxBlocks];      // nz | last << 8, symbol order
+    __shared__ uint32_t s_off[3 * kMaxBlocks];       // exclusive symbol offsets
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_hist[kHfClusters * kHfTokens];
+    __shared__ uint32_t s_resbits, s_err;
+
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileDesc t = tiles[tile];
+    const uint32_t vbw = (t.w + 7) >> 3, vbh = (t.h + 7) >> 3, nb = vbw * vbh, ne = 3 * nb;
+
+    for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)
+        s_hist[i] = 0;
+    if (tid == 0) {
+        s_resbits = 0;
+        s_err = 0;
+    }
+    // entry e = (block raster index) * 3 + channel index i ; channel c = Y, X, B for i = 0, 1, 2
+    for (uint32_t e = tid; e < ne; e += kTokThreads) {
+        const uint32_t blk = e / 3, i = e - blk * 3, c = i < 2 ? 1 - i : i;
+        const uint32_t by = blk / vbw, bx = blk - by * vbw;
+        s_info[e] = nzinfo[((size_t)tile * kMaxBlocks + by * kBlocksPerRow + bx) * 3 + c];
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of symbol counts: 3 consecutive entries per thread --------------------
+    uint32_t cnt[3], local = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t e = tid * 3 + k;
+        uint32_t c = 0;
+        if (e < ne) {
+            const uint32_t info = s_info[e];
+            c = 1 + ((info & 0xFF) ? (info >> 8) : 0);
+        }
+        cnt[k] = c;
+        local += c;
+    }
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d)
+            incl += v;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d)
+                wi += v;
+        }
+        s_warp[lane] = wi - w;   // exclusive warp base
+        if (lane == 31)
+            nsyms[tile] = wi;
+    }
+    __syncthreads();
+    {
+        uint32_t run = s_warp[warp] + incl - local;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t e = tid * 3 + k;
+            if (e < ne)
+                s_off[e] = run;
+            run += cnt[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- one warp per (block, channel) ---------------------------------------------------------
+    uint32_t *out = syms + (size_t)tile * kMaxHfSyms;
+    uint32_t my_resbits = 0, my_err = 0;
+    for (uint32_t e = warp; e < ne; e += kTokThreads / 32) {
+        const uint32_t blk = e / 3, i = e - blk * 3, c = i < 2 ? 1 - i : i;
+        const uint32_t by = blk / vbw, bx = blk - by * vbw;
+        const uint32_t info = s_info[e], nz = info & 0xFF, last = info >> 8;
+        const uint32_t base = s_off[e];
+        if (lane == 0) {
+            // non-zero count on cluster i, hybrid config (4, 1, 0) (encoder.c:908)
+            uint32_t res, nbits;
+            uint32_t tok = hybrid_token(nz, 4, 1, 0, res, nbits);
+            out[base] = hf_pack(tok, i, nbits, res);
+            atomicAdd(&s_hist[i * kHfTokens + tok], 1u);
+            my_resbits += nbits;
+        }
+        if (!nz)
+            continue;
+        const int16_t *q = coef + (((size_t)tile * kMaxBlocks + by * kBlocksPerRow + bx) * 3 + c) * 64;
+        const int q_lo = q[lane], q_hi = q[lane + 32];
+        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, q_lo != 0);
+        const uint32_t m_hi = __ballot_sync(0xFFFFFFFFu, q_hi != 0);
+        const uint64_t mask = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t j = lane + 32 * half;
+            const int qv = half ? q_hi : q_lo;
+            const bool valid = j >= 1 && j <= last;
+            uint32_t key = 0xFFFFFFFFu;
+            if (valid) {
+                const uint32_t below = __popcll(mask & ((1ull << j) - 1ull));
+                const uint32_t left = nz - below;
+                const uint32_t prev = j == 1 ? (nz <= 4 ? 1u : 0u) : (uint32_t)((mask >> (j - 1)) & 1ull);
+                const uint32_t cluster = 3 + prev + 2 * ((i + nnz_context(left) + c_freq_ctx[j]) % 3);
+                uint32_t res, nbits;
+                uint32_t tok = hybrid_token(pack_signed(qv), 4, 1, 0, res, nbits);
+                if (tok >= (uint32_t)kHfTokens) {
+                    my_err |= kErrAlphabet;
+                    tok = kHfTokens - 1;
+                }
+                out[base + j] = hf_pack(tok, cluster, nbits, res);
+                my_resbits += nbits;
+                key = cluster * kHfTokens + tok;
+            }
+            // warp-aggregated histogram update
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+            if (valid && lane == (uint32_t)(__ffs(peers) - 1))
+                atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_resbits += __shfl_down_sync(0xFFFFFFFFu, my_resbits, d);
+        my_err |= __shfl_down_sync(0xFFFFFFFFu, my_err, d);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_resbits, my_resbits);
+        if (my_err)
+            atomicOr(&s_err, my_err);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)
+        hist[(size_t)tile * kHfClusters * kHfTokens + i] = s_hist[i];
+    if (tid == 0) {
+        resbits[tile] = s_resbits;
+        if (s_err)
+            atomicOr(&tile_err[tile], s_err);
+    }
+}
+
+void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
+    k_hf_tokens<<<ntiles, kTokThreads, 0, st>>>(ws.tiles, ws.coef, ws.nzinfo, ws.syms, ws.nsyms, ws.resbits, ws.hist,
+                                                ws.tile_err);
+}
+
+}  // namespace hydb

@@ -1,0 +1,253 @@
+// hydrium_b200/csrc/k_xyb_dct.cu
+//
+// Stage 1 of the tile pipeline: RGB samples -> XYB -> 8x8 forward DCT -> quantised coefficients.
+// Replaces hyd_populate_xyb_buffer (reference: format.c:142-194), forward_dct (encoder.c:631-668),
+// the HF quantisation loop (encoder.c:783-823) and the LF quantisation (encoder.c:573, 582).
+//
+// B200 mapping: one CTA per row of 32 varblocks of a tile (grid = 32 x tiles, 256 threads).
+// Thread (block b, row r) converts its 8 pixels and runs the three row transforms in registers,
+// rows are exchanged through a conflict-free padded shared-memory tile, thread (b, column t) runs
+// the three column transforms, quantises, and the CTA writes 12 KB of int16 coefficients in scan
+// order with coalesced 16-byte stores.  Nothing is a dense contraction that could use tensor
+// cores without changing the result: the summation ORDER is part of the format (SURVEY.md
+// Appendix B), every product and sum is a separate IEEE round-to-nearest op (no FMA).
+#include "common.cuh"
+#include "kernels.h"
+#include "tables.cuh"
+
+namespace hydb {
+
+__constant__ uint32_t c_cos_bits[7][8] = {HYDB_COS_BITS};
+__constant__ uint8_t c_scan_index[64] = {HYDB_SCAN_INDEX};
+__constant__ uint16_t c_hf_weights[3][64] = {HYDB_HF_WEIGHTS};
+
+// ---- lookup tables (reference: format.c:15-36, 58-83) -------------------------------------
+__device__ __forceinline__ float srgb_to_linear(float x) {
+    if (x <= 0.0404482362771082f)
+        return __fmul_rn(0.07739938080495357f, x);
+    float t = __fadd_rn(0.72007737769f, __fmul_rn(0.2852804880f, x));
+    t = __fadd_rn(-0.009982599f, __fmul_rn(x, t));
+    return __fadd_rn(0.003094300919832f, __fmul_rn(x, t));
+}
+
+__device__ __forceinline__ float fast_cbrt(float x) {
+    uint32_t zi = 0x548c39cbu - __float_as_uint(x) / 3u;
+    float z = __uint_as_float(zi);
+    // z *= c0 - c1 * x * z * z * z, evaluated left to right as ((((c1*x)*z)*z)*z)
+    float t = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.534850249f, x), z), z), z);
+    z = __fmul_rn(z, __fsub_rn(1.5015480449f, t));
+    t = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.33333333f, x), z), z), z);
+    z = __fmul_rn(z, __fsub_rn(1.333333985f, t));
+    return __fdiv_rn(1.0f, z);
+}
+
+__global__ void k_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_srgb, uint16_t *lut16_lin,
+                             float *bias) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536)
+        return;
+    const float step16 = __fdiv_rn(1.0f, __fsub_rn(65536.0f, 1.0f));
+    const float f16 = __fmul_rn((float)i, step16);
+    {
+        const float b = __fsub_rn(fast_cbrt(__fadd_rn(f16, 0.0037930732552754493f)), 0.155954f);
+        bias[i] = b;
+    }
+    auto to_u16 = [](float x) -> uint16_t {
+        int v = __float2int_rz(__fadd_rn(__fmul_rn(x, 65535.f), 0.5f));
+        return (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+    };
+    lut16_lin[i] = to_u16(f16);
+    lut16_srgb[i] = to_u16(srgb_to_linear(f16));
+    if (i < 256) {
+        const float step8 = __fdiv_rn(1.0f, __fsub_rn(256.0f, 1.0f));
+        const float f8 = __fmul_rn((float)i, step8);
+        lut8_lin[i] = to_u16(f8);
+        lut8_srgb[i] = to_u16(srgb_to_linear(f8));
+    }
+}
+
+// ---- 8-point transform, reference summation order (encoder.c:641-648) ----------------------
+__device__ __forceinline__ void dct8(const float (&v)[8], float (&o)[8]) {
+    float dc = v[0];
+#pragma unroll
+    for (int n = 1; n < 8; n++)
+        dc = __fadd_rn(dc, v[n]);
+    o[0] = __fmul_rn(dc, 0.125f);
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        // the reference starts from +0.0f; 0.0f + p differs from p only in the sign of a zero,
+        // which no consumer can observe (every consumer truncates to int)
+        float acc = __fmul_rn(v[0], __uint_as_float(c_cos_bits[k - 1][0]));
+#pragma unroll
+        for (int n = 1; n < 8; n++)
+            acc = __fadd_rn(acc, __fmul_rn(v[n], __uint_as_float(c_cos_bits[k - 1][n])));
+        o[k] = acc;
+    }
+}
+
+constexpr int kRowPad = 9;                  // 8 + 1: conflict-free row/column exchange
+constexpr int kBlkPad = 8 * kRowPad;        // 72 floats per block and channel
+
+template <typename Sample>
+__device__ __forceinline__ void load_xyb(const TileDesc &t, const uint16_t *in_lut, const float *__restrict__ bias,
+                                         uint32_t px0, uint32_t y, float (&X)[8], float (&Y)[8], float (&B)[8]) {
+    const Sample *p0 = (const Sample *)t.plane[0];
+    const Sample *p1 = (const Sample *)t.plane[1];
+    const Sample *p2 = (const Sample *)t.plane[2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t px = px0 + i;
+        float x = 0.0f, yy = 0.0f, b = 0.0f;   // zero padding of partial blocks (format.c:182-191)
+        if (px < t.w && y < t.h) {
+            const int64_t o = (int64_t)y * t.row_stride + (int64_t)px * t.pixel_stride;
+            const uint32_t r = in_lut[__ldg(p0 + o)];
+            const uint32_t g = in_lut[__ldg(p1 + o)];
+            const uint32_t bl = in_lut[__ldg(p2 + o)];
+            // format.c:48-56
+            const float l = __ldg(bias + (((19661u * r + 40761u * g + 5112u * bl) >> 16) & 0xFFFFu));
+            const float m = __ldg(bias + (((15073u * r + 45350u * g + 5112u * bl) >> 16) & 0xFFFFu));
+            const float s = __ldg(bias + (((15953u * r + 13419u * g + 36163u * bl) >> 16) & 0xFFFFu));
+            yy = __fmul_rn(__fadd_rn(l, m), 0.5f);
+            x = __fsub_rn(yy, m);
+            b = __fsub_rn(s, yy);
+        }
+        X[i] = x;
+        Y[i] = yy;
+        B[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__restrict__ coef,
+                uint16_t *__restrict__ nzinfo, int32_t *__restrict__ lfq, float *__restrict__ dbg_xyb,
+                float *__restrict__ dbg_dct) {
+    __shared__ float s_rows[3 * 32 * kBlkPad];            // 27,648 B
+    __shared__ __align__(16) int16_t s_q[32 * 3 * 64];    // 12,288 B
+    __shared__ uint16_t s_lut8[256];
+    __shared__ float s_w[3 * 64];
+    __shared__ uint8_t s_scan[64];
+
+    const uint32_t tile = blockIdx.y, by = blockIdx.x;
+    const TileDesc t = tiles[tile];
+    const uint32_t vbw = (t.w + 7) >> 3, vbh = (t.h + 7) >> 3;
+    if (by >= vbh)
+        return;
+    const uint32_t tid = threadIdx.x, b = tid >> 3, r = tid & 7;
+    const bool fmt16 = (t.flags & kTileFmt16) != 0, linear = (t.flags & kTileLinear) != 0;
+
+    if (!fmt16)
+        s_lut8[tid] = (linear ? luts.lut8_lin : luts.lut8_srgb)[tid];
+    if (tid < 192)
+        s_w[tid] = (float)c_hf_weights[tid >> 6][tid & 63];
+    if (tid < 64)
+        s_scan[tid] = c_scan_index[tid];
+    __syncthreads();
+
+    // ---- colour transform + row pass --------------------------------------------------------
+    if (b < vbw) {
+        float v[3][8];
+        if (fmt16)
+            load_xyb<uint16_t>(t, linear ? luts.lut16_lin : luts.lut16_srgb, luts.bias, b * 8, by * 8 + r, v[0], v[1], v[2]);
+        else
+            load_xyb<uint8_t>(t, s_lut8, luts.bias, b * 8, by * 8 + r, v[0], v[1], v[2]);
+        if (dbg_xyb) {
+            float *d = dbg_xyb + ((size_t)tile * 65536 + (size_t)(by * 8 + r) * 256 + b * 8) * 3;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                d[i * 3 + 0] = v[0][i];
+                d[i * 3 + 1] = v[1][i];
+                d[i * 3 + 2] = v[2][i];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float o[8];
+            dct8(v[c], o);
+            float *dst = s_rows + (c * 32 + b) * kBlkPad + r * kRowPad;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                dst[k] = o[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- column pass + quantisation ---------------------------------------------------------
+    // thread (b, t): horizontal frequency kh = t, produces vertical frequencies kv = 0..7
+    if (b < vbw) {
+        const uint32_t kh = r;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float v[8], o[8];
+            const float *src = s_rows + (c * 32 + b) * kBlkPad + kh;
+#pragma unroll
+            for (int n = 0; n < 8; n++)
+                v[n] = src[n * kRowPad];
+            dct8(v, o);
+            if (dbg_dct) {
+                // stored transposed like the reference: position (row = kh, col = kv)
+                float *d = dbg_dct + ((size_t)tile * 65536 + (size_t)(by * 8 + kh) * 256 + b * 8) * 3 + c;
+#pragma unroll
+                for (int kv = 0; kv < 8; kv++)
+                    d[kv * 3] = o[kv];
+            }
+            int16_t *qd = s_q + (b * 3 + c) * 64;
+#pragma unroll
+            for (int kv = 0; kv < 8; kv++) {
+                const uint32_t j = s_scan[kv * 8 + kh];
+                if (j == 0) {
+                    // LF: trunc(dc * {8192, 1024, 512}) (encoder.c:573, 582)
+                    const float scale = c == 0 ? 8192.f : (c == 1 ? 1024.f : 512.f);
+                    lfq[((size_t)tile * 3 + c) * kMaxBlocks + by * kBlocksPerRow + b] = __float2int_rz(__fmul_rn(o[kv], scale));
+                    qd[0] = 0;
+                } else {
+                    // HF: trunc((f * w) * 5), dead zone |q| < 2 -> 0 (encoder.c:808-810)
+                    int q = __float2int_rz(__fmul_rn(__fmul_rn(o[kv], s_w[c * 64 + j]), 5.0f));
+                    if (q > -2 && q < 2)
+                        q = 0;
+                    qd[j] = (int16_t)q;
+                }
+            }
+        }
+    } else {
+        // blocks beyond the tile edge: keep the staging buffer defined
+        for (int i = r; i < 3 * 64; i += 8)
+            s_q[b * 3 * 64 + i] = 0;
+    }
+    __syncthreads();
+
+    // ---- per block and channel: number of non-zeros and scan index of the last one -----------
+    {
+        const uint32_t warp = tid >> 5, lane = tid & 31;
+        for (uint32_t bc = warp; bc < 96; bc += 8) {
+            const int16_t *qd = s_q + bc * 64;
+            const uint32_t lo = __ballot_sync(0xFFFFFFFFu, qd[lane] != 0);
+            const uint32_t hi = __ballot_sync(0xFFFFFFFFu, qd[lane + 32] != 0);
+            if (lane == 0) {
+                const uint32_t nz = __popc(lo) + __popc(hi);
+                const uint32_t last = hi ? 63 - __clz(hi) : (lo ? 31 - __clz(lo) : 0);
+                const uint32_t blk = bc / 3, c = bc - blk * 3;
+                if (blk < vbw)
+                    nzinfo[((size_t)tile * kMaxBlocks + by * kBlocksPerRow + blk) * 3 + c] = (uint16_t)(nz | (last << 8));
+            }
+        }
+    }
+    // ---- coalesced store of the coefficient rows ----------------------------------------------
+    {
+        const uint4 *src = (const uint4 *)s_q;
+        uint4 *dst = (uint4 *)(coef + ((size_t)tile * kMaxBlocks + by * kBlocksPerRow) * 3 * 64);
+        for (uint32_t i = tid; i < 32 * 3 * 64 * 2 / 16; i += 256)
+            dst[i] = src[i];
+    }
+}
+
+void launch_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_srgb, uint16_t *lut16_lin, float *bias,
+                       cudaStream_t st) {
+    k_build_luts<<<65536 / 256, 256, 0, st>>>(lut8_srgb, lut8_lin, lut16_srgb, lut16_lin, bias);
+}
+
+void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st) {
+    k_xyb_dct_quant<<<dim3(kBlocksPerRow, ntiles), 256, 0, st>>>(ws.tiles, luts, ws.coef, ws.nzinfo, ws.lfq, ws.dbg_xyb,
+                                                                 ws.dbg_dct);
+}
+
+}  // namespace hydb

@@ -1,0 +1,67 @@
+// hydrium_b200/csrc/kernels.h
+//
+// Workspace layout and kernel launchers shared by the .cu translation units and engine.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace hydb {
+
+struct LutSet {
+    const uint16_t *lut8_srgb, *lut8_lin;     // 256 entries   (reference: format.c:58-71)
+    const uint16_t *lut16_srgb, *lut16_lin;   // 65536 entries
+    const float *bias;                        // 65536 entries (reference: format.c:73-83)
+};
+
+// Per-batch device workspace.  Everything is indexed [tile][...] with fixed strides, so kernels
+// never need a global scan except for the final compaction.
+struct Workspace {
+    uint32_t capacity;        // tiles
+    TileDesc *tiles;          // [T]
+    int16_t *coef;            // [T][1024 blocks (row stride 32)][3 channels X,Y,B][64 scan order]
+    uint16_t *nzinfo;         // [T][1024][3]  nz count | last scan index << 8
+    int32_t *lfq;             // [T][3][1024]  quantised LF ints
+    uint32_t *syms;           // [T][kMaxHfSyms] HF symbol records (hf_pack)
+    uint32_t *nsyms;          // [T]
+    uint32_t *resbits;        // [T] sum of residue bits of the HF symbols
+    uint32_t *hist;           // [T][9][64] raw token counts
+    uint32_t *lfbits;         // [T][kLfBitsWords] LF stream bit string (section L)
+    uint32_t *lfbitlen;       // [T]
+    uint32_t *flags;          // [T][kMaxHfSyms / 32] renormalisation flag per symbol
+    uint16_t *fwords;         // [T][kMaxHfSyms] renormalisation words in chain (reverse) order
+    uint8_t *slab;            // [T][kSlabBytes] frames: header+TOC right-justified before byte 64
+    uint32_t *frame_off;      // [T] first byte of the frame inside its slab
+    uint32_t *frame_len;      // [T]
+    uint64_t *out_off;        // [T+1] exclusive scan of frame_len (compaction offsets)
+    uint32_t *tile_err;       // [T] TileError bits
+    // optional stage taps for the parity tests (NULL in production)
+    float *dbg_xyb, *dbg_dct; // [T][256][256][3]
+    uint32_t *dbg_freqs;      // [T][9][64] normalised frequencies
+    uint32_t *dbg_sect;       // [T][4] bit lengths of sections prefix(A+L+B), D, E, total
+};
+
+// Shape-constant sections cached in HBM: entry 0 is section A, entry 1 + s is section B of shape s.
+struct Templates {
+    uint32_t *words;          // [1 + kMaxShapes][kTemplWords]
+    uint32_t *bits;           // [1 + kMaxShapes]
+};
+constexpr int kMaxShapes = 64;
+
+void launch_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_srgb, uint16_t *lut16_lin,
+                       float *bias, cudaStream_t st);
+void launch_build_templates(const Templates &t, const uint32_t *d_shape_dims /*[n][2]*/, uint32_t first_shape,
+                            uint32_t n_shapes, bool build_a, cudaStream_t st);
+void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st);
+void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
+void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
+void launch_ans_encode(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
+// compaction: out[prefix_len + out_off[i] ...] = frame i ; total written to ws.out_off[ntiles]
+void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
+                   uint32_t *d_overflow, cudaStream_t st);
+void launch_synth_fill(void *dst, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t full_w,
+                       uint32_t full_h, int bits, uint32_t seed, int smooth, cudaStream_t st);
+int ans_encode_smem_bytes();
+
+}  // namespace hydb

@@ -1,0 +1,204 @@
+/*
+ * include/hydrium_b200.h -- C ABI of libhydrium_b200.so
+ *
+ * Part 1 is the drop-in boundary: the nine entry points, enums and the metadata struct of
+ * libhydrium 0.6.0, with identical names, signatures, values and struct layout, so a program
+ * compiled against the reference header links and runs against this library unchanged
+ * (reference: src/include/libhydrium/libhydrium.h; each declaration cites the lines it replaces).
+ * `include/libhydrium/libhydrium.h` in this tree just includes this file.
+ *
+ * Part 2 is additive (hydb_*): device selection, batching control, and entry points that take
+ * images already resident in GPU memory.  Nothing in part 2 changes the behaviour of part 1.
+ *
+ * The encoder behind both parts is CUDA-only (sm_100a).  There is no CPU implementation: without
+ * a usable device hyd_set_metadata / hydb_engine_create fail with HYD_INTERNAL_ERROR.
+ */
+#ifndef HYDRIUM_B200_H_
+#define HYDRIUM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* version of the API this library is a drop-in for (libhydrium.h:17-51) */
+#define HYDRIUM_VERSION_MAJOR 0
+#define HYDRIUM_VERSION_MINOR 6
+#define HYDRIUM_VERSION_POINT 0
+#define HYDRIUM_COMPUTE_VERSION(ma, mi, po) \
+    (UINT64_C(0x1000000000) | ((uint64_t)(ma) << 24) | ((uint64_t)(mi) << 12) | ((uint64_t)(po)))
+#define HYDRIUM_VERSION_INT \
+    HYDRIUM_COMPUTE_VERSION(HYDRIUM_VERSION_MAJOR, HYDRIUM_VERSION_MINOR, HYDRIUM_VERSION_POINT)
+#define HYDRIUM_VERSION_STRING "0.6.0"
+
+#if defined(__GNUC__) || defined(__clang__)
+#define HYDRIUM_EXPORT __attribute__((visibility("default")))
+#else
+#define HYDRIUM_EXPORT
+#endif
+
+/* ===================================================================== part 1: libhydrium ABI */
+
+/* libhydrium.h:67-101.  Errors are < HYD_ERROR_START. */
+typedef enum HYDStatusCode {
+    HYD_OK = 0,
+    HYD_DEFAULT = -1,
+    HYD_NEED_MORE_OUTPUT = -2,
+    HYD_NEED_MORE_INPUT = -3,
+    HYD_ERROR_START = -10,
+    HYD_NOMEM = -13,
+    HYD_API_ERROR = -14,
+    HYD_INTERNAL_ERROR = -15
+} HYDStatusCode;
+
+/* libhydrium.h:103-107 */
+typedef enum HYDSampleFormat {
+    HYD_UINT8 = 0,
+    HYD_UINT16 = 1,
+    HYD_FLOAT32 = 2
+} HYDSampleFormat;
+
+/* libhydrium.h:109-155.  tile_size_shift_{x,y}: 0..3 => 256<<shift pixel tiles, -1 => one frame.
+ * This library encodes tile mode with shift 0/0 (one 256x256 group per frame), and one-frame
+ * mode for images that fit a single group; other values are rejected with HYD_API_ERROR
+ * ("tile size not supported by the B200 encoder"), see DESIGN.md. */
+typedef struct HYDImageMetadata {
+    size_t width;
+    size_t height;
+    int linear_light;
+    int tile_size_shift_x;
+    int tile_size_shift_y;
+} HYDImageMetadata;
+
+typedef struct HYDEncoder HYDEncoder;
+
+/* libhydrium.h:165 */
+HYDRIUM_EXPORT HYDEncoder *hyd_encoder_new(void);
+/* libhydrium.h:173 */
+HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *encoder);
+/* libhydrium.h:183 */
+HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *encoder, const HYDImageMetadata *metadata);
+/* libhydrium.h:193 */
+HYDRIUM_EXPORT HYDStatusCode hyd_provide_output_buffer(HYDEncoder *encoder, uint8_t *buffer, size_t buffer_len);
+/* libhydrium.h:260-262.  Strides are in samples; the three planes may alias (packed RGB/RGBA).
+ * The sample buffers are only read during the call. */
+HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *encoder, const void *const buffer[3],
+                                           uint32_t tile_x, uint32_t tile_y, ptrdiff_t row_stride,
+                                           ptrdiff_t pixel_stride, int is_last, HYDSampleFormat sample_fmt);
+/* libhydrium.h:275 */
+HYDRIUM_EXPORT HYDStatusCode hyd_release_output_buffer(HYDEncoder *encoder, size_t *written);
+/* libhydrium.h:288 */
+HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *encoder);
+/* libhydrium.h:295 */
+HYDRIUM_EXPORT const char *hyd_error_message_get(HYDEncoder *encoder);
+/* libhydrium.h:313-314.  ICC tagging is a one-frame-mode side feature outside the accelerated
+ * path: NULL/0 clears (HYD_OK); anything else returns HYD_API_ERROR with the reference's message
+ * for tile mode. */
+HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *encoder, const uint8_t *icc_data,
+                                                           size_t icc_size);
+
+/* ===================================================================== part 2: additive API */
+
+/* How many tiles hyd_send_tile may queue before it launches the GPU pipeline.  1 = every
+ * hyd_send_tile encodes synchronously and the following hyd_flush returns that tile's bytes,
+ * exactly like the reference.  N > 1 = tiles are staged and encoded N at a time (or when the last
+ * tile arrives); hyd_flush then returns bytes in send order as batches complete, and the
+ * concatenation of everything surfaced is byte-identical.  Default: env HYDRIUM_B200_BATCH, else 1.
+ * Must be called before the first hyd_send_tile. */
+HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *encoder, uint32_t tiles);
+/* CUDA device ordinal for this encoder.  Default: env HYDRIUM_B200_DEVICE, else the current device. */
+HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_device(HYDEncoder *encoder, int device);
+
+/* ---- engine: batch encoder over device-resident images ------------------------------------ */
+typedef struct HydbEngine HydbEngine;
+
+/* One tile to encode; pointers are DEVICE pointers (same meaning as hyd_send_tile's arguments). */
+typedef struct HydbTile {
+    const void *plane[3];
+    int64_t row_stride;      /* samples */
+    int64_t pixel_stride;    /* samples */
+    uint32_t width, height;  /* tile size in pixels, <= 256 */
+    uint32_t x0, y0;         /* origin in the image, multiples of 256 */
+    uint32_t image_width, image_height;
+    int32_t is_last;         /* 0 / 1 */
+    int32_t sample_fmt;      /* HYD_UINT8 / HYD_UINT16 */
+    int32_t linear_light;
+    int32_t reserved;
+} HydbTile;
+
+/* max_batch_tiles bounds the tiles per hydb_engine_encode_tiles call (workspace ~2.4 MB / tile). */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_create(HydbEngine **engine, int device, uint32_t max_batch_tiles);
+HYDRIUM_EXPORT void hydb_engine_destroy(HydbEngine *engine);
+HYDRIUM_EXPORT const char *hydb_engine_error(const HydbEngine *engine);
+HYDRIUM_EXPORT uint32_t hydb_engine_max_batch(const HydbEngine *engine);
+/* the cudaStream_t the engine launches on (as an integer handle), for CUDA-event timing */
+HYDRIUM_EXPORT uint64_t hydb_engine_stream(const HydbEngine *engine);
+/* number of kernel launches issued by the engine so far */
+HYDRIUM_EXPORT uint64_t hydb_engine_launch_count(const HydbEngine *engine);
+
+/* Encode n tiles (n <= max batch) and append their frames, in order, to d_out (device memory)
+ * starting at byte d_out_pos.  Asynchronous on the engine stream; call hydb_engine_finish to
+ * synchronise, collect per-tile errors and learn how many bytes the batch appended. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_tiles(HydbEngine *engine, const HydbTile *tiles, uint32_t n,
+                                                      uint8_t *d_out, uint64_t d_out_cap, uint64_t d_out_pos);
+/* Synchronise, check per-tile error flags of the last batch, return total bytes appended by it. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_finish(HydbEngine *engine, uint64_t *batch_bytes);
+
+/* Whole image, tile mode shift 0/0, raster tile order restricted to tile rows
+ * [tile_row_begin, tile_row_end): d_pixels points at the first sample of tile row tile_row_begin
+ * (interleaved, `channels` samples per pixel, row_stride samples per row).  Writes
+ * [image header if with_header] + frames to d_out; *out_len = bytes.  Synchronous. */
+HYDRIUM_EXPORT HYDStatusCode hydb_encode_image_device(HydbEngine *engine, const void *d_pixels, uint32_t width,
+                                                      uint32_t height, uint32_t channels, int64_t row_stride,
+                                                      int sample_fmt, int linear_light, uint32_t tile_row_begin,
+                                                      uint32_t tile_row_end, int with_header, uint8_t *d_out,
+                                                      uint64_t d_out_cap, uint64_t *out_len);
+/* Same with HOST buffers: pixels are copied to the device, the codestream is copied back.
+ * h_pixels / h_out should be page-locked for full PCIe speed (hydb_host_alloc). */
+HYDRIUM_EXPORT HYDStatusCode hydb_encode_image_host(HydbEngine *engine, const void *h_pixels, uint32_t width,
+                                                    uint32_t height, uint32_t channels, int sample_fmt,
+                                                    int linear_light, uint8_t *h_out, uint64_t h_out_cap,
+                                                    uint64_t *out_len);
+
+/* image header bytes (with the level-10 container prefix where the reference emits it) */
+HYDRIUM_EXPORT int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap);
+
+/* page-locked host memory / device memory helpers for callers without a CUDA runtime of their own */
+HYDRIUM_EXPORT void *hydb_host_alloc(size_t bytes);
+HYDRIUM_EXPORT void hydb_host_free(void *p);
+HYDRIUM_EXPORT void *hydb_device_alloc(size_t bytes);
+HYDRIUM_EXPORT void hydb_device_free(void *p);
+HYDRIUM_EXPORT int hydb_memcpy_h2d(void *dst, const void *src, size_t bytes);
+HYDRIUM_EXPORT int hydb_memcpy_d2h(void *dst, const void *src, size_t bytes);
+HYDRIUM_EXPORT int hydb_device_count(void);
+
+/* closed-form synthetic RGB image generated directly in device memory (benchmarks) */
+HYDRIUM_EXPORT int hydb_synth_fill(HydbEngine *engine, void *d_dst, uint32_t width, uint32_t height, uint32_t x0,
+                                   uint32_t y0, uint32_t full_width, uint32_t full_height, int bits, uint32_t seed,
+                                   int smooth);
+
+/* stage taps for the parity tests: enable before encoding, then copy a stage of one tile of the
+ * last batch to host memory.  Returns bytes copied or a negative status. */
+enum {
+    HYDB_TAP_XYB = 0,      /* float [256][256][3]                  */
+    HYDB_TAP_DCT = 1,      /* float [256][256][3]                  */
+    HYDB_TAP_COEF = 2,     /* int16 [1024][3][64] scan order       */
+    HYDB_TAP_NZINFO = 3,   /* uint16 [1024][3]                     */
+    HYDB_TAP_LFQ = 4,      /* int32 [3][1024]                      */
+    HYDB_TAP_SYMS = 5,     /* uint32 [nsyms] packed records        */
+    HYDB_TAP_FREQS = 6,    /* uint32 [9][64] normalised            */
+    HYDB_TAP_LFBITS = 7,   /* uint32 words, section L              */
+    HYDB_TAP_SECT = 8,     /* uint32 [4] section bit lengths       */
+    HYDB_TAP_PAYLOAD = 9,  /* bytes: payload of the frame          */
+    HYDB_TAP_NSYMS = 10,   /* uint32 [1]                           */
+    HYDB_TAP_LFBITLEN = 11 /* uint32 [1]                           */
+};
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_enable_taps(HydbEngine *engine, int enable);
+HYDRIUM_EXPORT int64_t hydb_engine_read_tap(HydbEngine *engine, int what, uint32_t tile, void *dst, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRIUM_B200_H_ */

@@ -120,7 +120,7 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
             return kErrAlias;
         for (uint32_t k = 0; k < (uint32_t)kHfTokens; k++) {
             freqs_out[c * kHfTokens + k] = cl[c].freq[k];
-            info[c][k] = ans_sym_info(cl[c].freq[k], cl[c].cum[k]);
+            info[c][k] = ans_sym_info(cl[c].freq[k], (uint32_t)c * kAnsTotal + cl[c].cum[k]);
         }
         for (uint32_t s = 0; s < (uint32_t)kAnsTotal; s++) {
             uint32_t sym, off;
@@ -165,7 +165,7 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
         const uint32_t f_next = p ? asi_freq(info[hf_cluster(syms[p - 1])][hf_token(syms[p - 1])].packed) : 0x7FFFFFFFu;
         bool fl;
         uint32_t word;
-        ans_step(x, info[c][t].m, info[c][t].packed, inv[c], f_next, fl, word);
+        ans_step(x, info[c][t].m, info[c][t].packed, &inv[0][0], f_next, fl, word);
         if (fl) {
             flag[p - 1] = 1;
             words.push_back((uint16_t)word);
