@@ -45,6 +45,14 @@ struct HydbEngine {
     uint64_t launches = 0;
     std::string error;
     std::vector<TileDesc> h_tiles;
+    // grow-only device buffers behind hydb_encode_image_host
+    void *host_in = nullptr;
+    uint8_t *host_out = nullptr;
+    size_t host_in_cap = 0, host_out_cap = 0;
+    // optional per-stage timing with CUDA events on the launching streams
+    bool timing = false, timed_pending = false;
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, lev[2] = {nullptr, nullptr};
+    double stage_ms[6] = {0, 0, 0, 0, 0, 0};   // xyb_dct, hf_tokens, ans, gather, lf_group, batches
 };
 
 #define CK(call)                                                                        \
@@ -168,6 +176,10 @@ void hydb_engine_destroy(HydbEngine *eng) {
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
     for (void *p : dev)
         if (p) cudaFree(p);
+    if (eng->host_in) cudaFree(eng->host_in);
+    if (eng->host_out) cudaFree(eng->host_out);
+    for (cudaEvent_t ev : eng->tev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : eng->lev) if (ev) cudaEventDestroy(ev);
     if (eng->h_err) cudaFreeHost(eng->h_err);
     if (eng->h_total) cudaFreeHost(eng->h_total);
     if (eng->ev_front) cudaEventDestroy(eng->ev_front);
@@ -272,15 +284,24 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     CK(cudaMemcpyAsync(eng->ws.tiles, eng->h_tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(eng->ws.tile_err, 0, n * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(eng->d_overflow, 0, sizeof(uint32_t), st));
+    const bool tm = eng->timing;
+    if (tm) CK(cudaEventRecord(eng->tev[0], st));
     launch_xyb_dct_quant(eng->ws, eng->luts, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[1], st));
     CK(cudaEventRecord(eng->ev_front, st));
     CK(cudaStreamWaitEvent(eng->st2, eng->ev_front, 0));
+    if (tm) CK(cudaEventRecord(eng->lev[0], eng->st2));
     launch_lf_group(eng->ws, n, eng->st2);
+    if (tm) CK(cudaEventRecord(eng->lev[1], eng->st2));
     CK(cudaEventRecord(eng->ev_lf, eng->st2));
     launch_hf_tokens(eng->ws, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[2], st));
     CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));
     launch_ans_encode(eng->ws, eng->templ, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[3], st));
     launch_gather(eng->ws, n, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    if (tm) CK(cudaEventRecord(eng->tev[4], st));
+    eng->timed_pending = tm;
     eng->launches += 6;
     CK(cudaMemcpyAsync(eng->h_err, eng->ws.tile_err, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(eng->h_err + eng->max_batch, eng->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -297,6 +318,18 @@ HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     CK(cudaSetDevice(eng->device));
     CK(cudaStreamSynchronize(eng->st));
     CK(cudaGetLastError());
+    if (eng->timed_pending) {
+        CK(cudaStreamSynchronize(eng->st2));
+        float ms = 0;
+        for (int k = 0; k < 4; k++) {
+            CK(cudaEventElapsedTime(&ms, eng->tev[k], eng->tev[k + 1]));
+            eng->stage_ms[k] += ms;
+        }
+        CK(cudaEventElapsedTime(&ms, eng->lev[0], eng->lev[1]));
+        eng->stage_ms[4] += ms;
+        eng->stage_ms[5] += 1;
+        eng->timed_pending = false;
+    }
     for (uint32_t i = 0; i < eng->last_n; i++) {
         if (eng->h_err[i]) {
             eng->error = tile_error_text(eng->h_err[i]);
@@ -433,42 +466,65 @@ int hydb_device_count(void) {
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
+static HYDStatusCode grow_device(HydbEngine *eng, void **p, size_t *cap, size_t need) {
+    if (*cap >= need)
+        return HYD_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (cudaMalloc(p, need) != cudaSuccess) {
+        eng->error = "device allocation failed";
+        return HYD_NOMEM;
+    }
+    *cap = need;
+    return HYD_OK;
+}
+
 HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint32_t width, uint32_t height,
                                      uint32_t channels, int sample_fmt, int linear_light, uint8_t *h_out,
                                      uint64_t h_out_cap, uint64_t *out_len) {
-    if (!eng || !h_pixels || !h_out || !out_len)
+    if (!eng || !h_pixels || !h_out || !out_len || (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16))
         return HYD_API_ERROR;
     CK(cudaSetDevice(eng->device));
     const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
     const size_t in_bytes = (size_t)width * height * channels * item;
-    void *d_in = nullptr;
-    uint8_t *d_out = nullptr;
-    CK(cudaMalloc(&d_in, in_bytes));
-    cudaError_t e = cudaMalloc((void **)&d_out, h_out_cap);
-    if (e != cudaSuccess) {
-        cudaFree(d_in);
-        eng->error = "device allocation failed";
-        return HYD_NOMEM;
-    }
-    HYDStatusCode rc = HYD_OK;
-    e = cudaMemcpyAsync(d_in, h_pixels, in_bytes, cudaMemcpyHostToDevice, eng->st);
-    if (e != cudaSuccess) {
-        eng->error = cudaGetErrorString(e);
-        rc = HYD_INTERNAL_ERROR;
-    }
+    HYDStatusCode rc = grow_device(eng, &eng->host_in, &eng->host_in_cap, in_bytes);
     if (rc == HYD_OK)
-        rc = hydb_encode_image_device(eng, d_in, width, height, channels, (int64_t)width * channels, sample_fmt,
-                                      linear_light, 0, (height + 255) >> 8, 1, d_out, h_out_cap, out_len);
-    if (rc == HYD_OK) {
-        e = cudaMemcpy(h_out, d_out, *out_len, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            eng->error = cudaGetErrorString(e);
-            rc = HYD_INTERNAL_ERROR;
-        }
+        rc = grow_device(eng, (void **)&eng->host_out, &eng->host_out_cap, (size_t)h_out_cap);
+    if (rc != HYD_OK)
+        return rc;
+    CK(cudaMemcpyAsync(eng->host_in, h_pixels, in_bytes, cudaMemcpyHostToDevice, eng->st));
+    rc = hydb_encode_image_device(eng, eng->host_in, width, height, channels, (int64_t)width * channels, sample_fmt,
+                                  linear_light, 0, (height + 255) >> 8, 1, eng->host_out, h_out_cap, out_len);
+    if (rc != HYD_OK)
+        return rc;
+    CK(cudaMemcpyAsync(h_out, eng->host_out, *out_len, cudaMemcpyDeviceToHost, eng->st));
+    CK(cudaStreamSynchronize(eng->st));
+    return HYD_OK;
+}
+
+HYDStatusCode hydb_engine_enable_timing(HydbEngine *eng, int enable) {
+    if (!eng)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    if (enable && !eng->tev[0]) {
+        for (cudaEvent_t &ev : eng->tev) CK(cudaEventCreate(&ev));
+        for (cudaEvent_t &ev : eng->lev) CK(cudaEventCreate(&ev));
     }
-    cudaFree(d_in);
-    cudaFree(d_out);
-    return rc;
+    eng->timing = enable != 0;
+    for (double &v : eng->stage_ms) v = 0;
+    return HYD_OK;
+}
+
+// accumulated device milliseconds since the last call: xyb_dct, hf_tokens, ans, gather, lf_group, #batches
+HYDStatusCode hydb_engine_stage_ms(HydbEngine *eng, double out[6]) {
+    if (!eng || !out)
+        return HYD_API_ERROR;
+    for (int k = 0; k < 6; k++) {
+        out[k] = eng->stage_ms[k];
+        eng->stage_ms[k] = 0;
+    }
+    return HYD_OK;
 }
 
 int hydb_synth_fill(HydbEngine *eng, void *d_dst, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0,

@@ -142,6 +142,17 @@ class Engine:
                                              height if full_height is None else full_height, bits, seed,
                                              1 if smooth else 0))
 
+    # -- per-kernel timing ---------------------------------------------------------------------
+    def enable_timing(self, on: bool = True) -> None:
+        self._check(self.lib.hydb_engine_enable_timing(self._h, 1 if on else 0))
+
+    def stage_ms(self) -> dict:
+        """Device ms accumulated since the last call (CUDA events on the launching streams)."""
+        arr = (C.c_double * 6)()
+        self._check(self.lib.hydb_engine_stage_ms(self._h, C.byref(arr)))
+        keys = ("xyb_dct_quant", "hf_tokens", "ans_encode", "gather", "lf_group", "batches")
+        return dict(zip(keys, list(arr)))
+
     # -- stage taps (parity tests) -----------------------------------------------------------
     def enable_taps(self, on: bool = True) -> None:
         self._check(self.lib.hydb_engine_enable_taps(self._h, 1 if on else 0))

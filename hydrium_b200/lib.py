@@ -21,7 +21,7 @@ HYDB_SYMBOLS = (
     "hydb_engine_encode_tiles", "hydb_engine_finish", "hydb_encode_image_device", "hydb_encode_image_host",
     "hydb_image_header", "hydb_host_alloc", "hydb_host_free", "hydb_device_alloc", "hydb_device_free",
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
-    "hydb_engine_read_tap",
+    "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms",
 )
 
 
@@ -98,5 +98,9 @@ def load_library() -> C.CDLL:
     lib.hydb_engine_enable_taps.argtypes = [vp, C.c_int]
     lib.hydb_engine_read_tap.restype = i64
     lib.hydb_engine_read_tap.argtypes = [vp, C.c_int, u32, vp, u64]
+    lib.hydb_engine_enable_timing.restype = C.c_int
+    lib.hydb_engine_enable_timing.argtypes = [vp, C.c_int]
+    lib.hydb_engine_stage_ms.restype = C.c_int
+    lib.hydb_engine_stage_ms.argtypes = [vp, C.POINTER(C.c_double * 6)]
     _lib = lib
     return lib

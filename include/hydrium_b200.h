@@ -162,6 +162,12 @@ HYDRIUM_EXPORT HYDStatusCode hydb_encode_image_host(HydbEngine *engine, const vo
                                                     int linear_light, uint8_t *h_out, uint64_t h_out_cap,
                                                     uint64_t *out_len);
 
+/* Per-kernel device time, measured with CUDA events on the launching streams.  stage_ms returns and
+ * resets the milliseconds accumulated since the last call:
+ * [0] xyb_dct_quant [1] hf_tokens [2] ans_encode [3] offsets+gather [4] lf_group (2nd stream) [5] #batches */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_enable_timing(HydbEngine *engine, int enable);
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_stage_ms(HydbEngine *engine, double out[6]);
+
 /* image header bytes (with the level-10 container prefix where the reference emits it) */
 HYDRIUM_EXPORT int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap);
 

@@ -169,11 +169,12 @@ class Oracle:
         return buf[:n].tobytes()
 
     def encode_tile(self, image: np.ndarray, tx: int, ty: int, *, linear_light=0, is_last=-1,
-                    stages: Stages | None = None, image_size=None) -> bytes:
-        """Frame bytes for tile (tx, ty) of `image` (H, W, C interleaved, uint8/uint16)."""
+                    stages: Stages | None = None, image_size=None, window=False) -> bytes:
+        """Frame bytes for tile (tx, ty) of `image` (H, W, C interleaved, uint8/uint16).
+        With `window=True`, `image` is just that tile's pixels and `image_size` the real image."""
         image = np.ascontiguousarray(image)
         h, w, _ = image.shape
-        planes, rs, ps = _tile_args(image, tx, ty)
+        planes, rs, ps = _tile_args(image, 0 if window else tx, 0 if window else ty)
         t = _OrcTile()
         t.image_width, t.image_height = (w, h) if image_size is None else image_size
         t.linear_light = linear_light

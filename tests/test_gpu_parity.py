@@ -1,0 +1,290 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+inputs (bit-exact: integer / byte output; the float stages are compared bit-for-bit as well,
+except that a zero may differ in sign in the DCT tap, which no later stage can observe).
+
+Everything here needs a B200 (`-m gpu`).  /root/reference is not used at run time."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hydrium_b200 import engine as E
+from hydrium_b200.abi import HYD_UINT8, HYD_UINT16
+from hydrium_b200.encoder import HYDEncoder, encode_cli_loop, tile_grid
+from hydrium_b200.lib import HydbTile
+from hydrium_b200.synth import synth_image
+from oracle.pyoracle import Stages
+from util import GOLDEN, image_set, kat_image, kat_table, sha256
+
+pytestmark = pytest.mark.gpu
+
+SCAN_V = [0, 1, 0, 0, 1, 2, 3, 2, 1, 0, 0, 1, 2, 3, 4, 5, 4, 3, 2, 1, 0, 0, 1, 2, 3, 4, 5, 6, 7, 6, 5, 4,
+          3, 2, 1, 0, 1, 2, 3, 4, 5, 6, 7, 7, 6, 5, 4, 3, 2, 3, 4, 5, 6, 7, 7, 6, 5, 4, 5, 6, 7, 7, 6, 7]
+SCAN_H = [0, 0, 1, 2, 1, 0, 0, 1, 2, 3, 4, 3, 2, 1, 0, 0, 1, 2, 3, 4, 5, 6, 5, 4, 3, 2, 1, 0, 0, 1, 2, 3,
+          4, 5, 6, 7, 7, 6, 5, 4, 3, 2, 1, 2, 3, 4, 5, 6, 7, 7, 6, 5, 4, 3, 4, 5, 6, 7, 7, 6, 5, 6, 7, 7]
+
+
+def _tile_desc(d_img, img, tx, ty, linear, image_size=None, origin=None):
+    h, w, ch = img.shape
+    item = img.dtype.itemsize
+    t = HydbTile()
+    if origin is None:
+        p = d_img + (ty * 256 * w * ch + tx * 256 * ch) * item
+        t.width, t.height = min(256, w - tx * 256), min(256, h - ty * 256)
+    else:   # `img` is the tile window itself
+        p = d_img
+        t.width, t.height = w, h
+    t.plane = (C.c_void_p * 3)(p, p + item, p + 2 * item)
+    t.row_stride, t.pixel_stride = w * ch, ch
+    t.x0, t.y0 = tx * 256, ty * 256
+    iw, ih = (w, h) if image_size is None else image_size
+    t.image_width, t.image_height = iw, ih
+    t.is_last = int((tx + 1) * 256 >= iw and (ty + 1) * 256 >= ih)
+    t.sample_fmt = HYD_UINT8 if img.dtype == np.uint8 else HYD_UINT16
+    t.linear_light = linear
+    return t
+
+
+def test_every_stage_matches_oracle(engine, oracle):
+    """T0..T7 of SURVEY.md section 4 for a spread of tiles, via the engine's stage taps."""
+    engine.enable_taps(True)
+    rng = np.random.default_rng(3)
+    try:
+        for name, img, lin in image_set(rng):
+            h, w, ch = img.shape
+            d_img = engine.upload(img)
+            d_out = engine.device_alloc(1 << 20)
+            try:
+                for ty in range((h + 255) // 256):
+                    for tx in range((w + 255) // 256):
+                        st = Stages()
+                        want = oracle.encode_tile(img, tx, ty, linear_light=lin, stages=st)
+                        n = engine.encode_tiles([_tile_desc(d_img, img, tx, ty, lin)], d_out, 1 << 20)
+                        got = engine.download(d_out, n)
+                        vbw, vbh = st.vbw, st.vbh
+                        sw, sh = vbw * 8, vbh * 8
+                        tag = (name, tx, ty)
+                        xyb = engine.read_tap(E.TAP_XYB, 0, np.float32).reshape(256, 256, 3)[:sh, :sw]
+                        assert np.array_equal(xyb.view(np.uint32), st.xyb[:sh * sw * 3].reshape(sh, sw, 3).view(np.uint32)), (tag, "xyb")
+                        dct = engine.read_tap(E.TAP_DCT, 0, np.float32).reshape(256, 256, 3)[:sh, :sw]
+                        assert np.array_equal(dct, st.dct[:sh * sw * 3].reshape(sh, sw, 3)), (tag, "dct")
+                        coef = engine.read_tap(E.TAP_COEF, 0, np.int16).reshape(32, 32, 3, 64)[:vbh, :vbw]
+                        oq = st.quant[:sh * sw * 3].reshape(vbh, 8, vbw, 8, 3)
+                        for j in range(1, 64):
+                            assert np.array_equal(coef[:, :, :, j], oq[:, SCAN_H[j], :, SCAN_V[j], :]), (tag, "coef", j)
+                        lfq = engine.read_tap(E.TAP_LFQ, 0, np.int32).reshape(3, 32, 32)[:, :vbh, :vbw]
+                        assert np.array_equal(lfq, oq[:, 0, :, 0, :].transpose(2, 0, 1)), (tag, "lf ints")
+                        nz = engine.read_tap(E.TAP_NZINFO, 0, np.uint16).reshape(32, 32, 3)[:vbh, :vbw] & 0xFF
+                        assert np.array_equal(nz, st.nonzeroes[:vbh * vbw * 3].reshape(vbh, vbw, 3)), (tag, "nz")
+                        syms = engine.read_tap(E.TAP_SYMS, 0, np.uint32)
+                        s = st.hf_syms[:st.n_syms]
+                        assert np.array_equal(syms, (s[:, 0] | (s[:, 1] << 8) | (s[:, 2] << 12) | (s[:, 3] << 16)).astype(np.uint32)), (tag, "symbols")
+                        assert np.array_equal(engine.read_tap(E.TAP_FREQS, 0, np.uint32).reshape(9, 64), st.freqs[:, :64]), (tag, "freqs")
+                        sect = engine.read_tap(E.TAP_SECT, 0, np.uint32)
+                        assert int(sect[0] + sect[1]) == st.pre_bitlen and int(sect[2]) == st.ans_bitlen, (tag, "section lengths")
+                        assert got == want, (tag, "frame")
+            finally:
+                engine.device_free(d_img)
+                engine.device_free(d_out)
+    finally:
+        engine.enable_taps(False)
+
+
+@pytest.mark.parametrize("name", [k for k, v in kat_table().items() if "width" in v and "ref_only" not in k and v["shift"] == 0])
+def test_golden_known_answers(engine, name):
+    """Committed reference outputs (tests/golden/kat.json) -- no oracle involved."""
+    e = kat_table()[name]
+    out = engine.encode_image(kat_image(e), linear_light=e["linear_light"])
+    assert len(out) == e["length"] and sha256(out) == e["sha256"]
+
+
+def test_golden_files(engine):
+    t = kat_table()
+    for fname, key in [("synth_40x24.jxl", "T_40x24"), ("synth_300x260.jxl", "Q_300x260")]:
+        assert engine.encode_image(kat_image(t[key])) == open(f"{GOLDEN}/{fname}", "rb").read()
+
+
+def test_whole_images_device_and_host_paths(engine, oracle):
+    rng = np.random.default_rng(5)
+    for name, img, lin in image_set(rng):
+        want = oracle.encode_image(img, linear_light=lin)
+        assert engine.encode_image(img, linear_light=lin) == want, (name, "device path")
+        assert engine.encode_image_host(img, linear_light=lin) == want, (name, "host path")
+
+
+def test_batches_larger_than_the_workspace(product_lib, oracle):
+    """An image with more tiles than max_batch_tiles goes through several launches."""
+    img = synth_image(1300, 1100, 8, seed=2)   # 6 x 5 = 30 tiles
+    with E.Engine(device=0, max_batch_tiles=7) as eng:
+        assert eng.encode_image(img) == oracle.encode_image(img)
+
+
+def test_nine_symbol_api_cli_loop(product_lib, oracle):
+    """The reference CLI's call sequence (hydrium.c:402-480) against our library, per-tile
+    synchronous mode: every tile's bytes surface in the flush loop that follows it."""
+    for img, lin in [(synth_image(700, 600, 8), 0), (synth_image(300, 520, 16, seed=3), 1)]:
+        per = []
+        out = encode_cli_loop(product_lib, img, linear_light=lin, per_tile=per)
+        assert out == oracle.encode_image(img, linear_light=lin)
+        h, w, _ = img.shape
+        hdr = oracle.image_header(w, h)
+        k = 0
+        for ty in range((h + 255) // 256):
+            for tx in range((w + 255) // 256):
+                want = oracle.encode_tile(img, tx, ty, linear_light=lin)
+                assert per[k] == (hdr + want if k == 0 else want), (tx, ty)
+                k += 1
+
+
+def test_nine_symbol_api_small_output_buffer(product_lib, oracle):
+    """HYD_NEED_MORE_OUTPUT back-pressure (libhydrium.c:147-166): 64-byte output buffer."""
+    img = synth_image(300, 260, 8, seed=1)
+    assert encode_cli_loop(product_lib, img, out_buf_size=64) == oracle.encode_image(img)
+
+
+def test_nine_symbol_api_one_frame_single_group(product_lib, oracle):
+    """BASELINE config 1: 256x256 through the CLI-default one-frame mode."""
+    e = kat_table()["A_256_oneframe"]
+    out = encode_cli_loop(product_lib, kat_image(e), shift_x=-1, shift_y=-1)
+    assert sha256(out) == e["sha256"]
+    img = synth_image(200, 131, 8, seed=8)
+    assert encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1) == oracle.encode_image(img)
+
+
+def test_nine_symbol_api_batched_mode(product_lib, oracle):
+    """hydb_encoder_set_batch: output is deferred but the concatenation is identical."""
+    img = synth_image(1100, 800, 8, seed=6)   # 5 x 4 tiles
+    want = oracle.encode_image(img)
+    h, w, ch = img.shape
+    for batch in (3, 20, 64):
+        enc = HYDEncoder(product_lib)
+        assert product_lib.hydb_encoder_set_batch(enc._enc, batch) == 0
+        enc.check(enc.set_metadata(w, h, 0, 0, 0))
+        obuf = np.empty(1 << 16, np.uint8)
+        enc.check(enc.provide_output_buffer(obuf))
+        out = bytearray()
+        _, _, ntx, nty = tile_grid(w, h, 0, 0)
+        for ty in range(nty):
+            for tx in range(ntx):
+                p = img.ctypes.data + (ty * 256 * w + tx * 256) * ch
+                enc.check(enc.send_tile((p, p + 1, p + 2), tx, ty, w * ch, ch, -1, HYD_UINT8))
+                while True:
+                    ret = enc.flush()
+                    _, n = enc.release_output_buffer()
+                    out += obuf[:n].tobytes()
+                    enc.check(enc.provide_output_buffer(obuf))
+                    if ret != -2:
+                        break
+                enc.check(ret)
+        enc.destroy()
+        assert bytes(out) == want, batch
+
+
+def test_sample_layouts(product_lib, oracle):
+    """Planar, RGBA-interleaved, BGR-ordered, negative row stride and odd strides (libhydrium.h:202-220)."""
+    rgb = synth_image(300, 270, 8, seed=12)
+    want = oracle.encode_image(rgb)
+    h, w, _ = rgb.shape
+
+    def run(planes_of_tile, row_stride, pixel_stride, fmt=HYD_UINT8):
+        enc = HYDEncoder(product_lib)
+        enc.check(enc.set_metadata(w, h, 0, 0, 0))
+        obuf = np.empty(1 << 20, np.uint8)
+        enc.check(enc.provide_output_buffer(obuf))
+        out = bytearray()
+        for ty in range((h + 255) // 256):
+            for tx in range((w + 255) // 256):
+                enc.check(enc.send_tile(planes_of_tile(tx, ty), tx, ty, row_stride, pixel_stride, -1, fmt))
+                enc.check(enc.flush())
+                _, n = enc.release_output_buffer()
+                out += obuf[:n].tobytes()
+                enc.check(enc.provide_output_buffer(obuf))
+        enc.destroy()
+        return bytes(out)
+
+    planar = np.ascontiguousarray(rgb.transpose(2, 0, 1))
+    base = planar.ctypes.data
+    assert run(lambda tx, ty: tuple(base + c * w * h + ty * 256 * w + tx * 256 for c in range(3)), w, 1) == want, "planar"
+    rgba = np.concatenate([rgb, np.full((h, w, 1), 77, np.uint8)], axis=2).copy()
+    b4 = rgba.ctypes.data
+    assert run(lambda tx, ty: tuple(b4 + (ty * 256 * w + tx * 256) * 4 + c for c in range(3)), w * 4, 4) == want, "rgba"
+    bgr = np.ascontiguousarray(rgb[:, :, ::-1])
+    b3 = bgr.ctypes.data
+    assert run(lambda tx, ty: tuple(b3 + (ty * 256 * w + tx * 256) * 3 + c for c in (2, 1, 0)), w * 3, 3) == want, "bgr"
+    flipped = np.ascontiguousarray(rgb[::-1])
+    bf = flipped.ctypes.data
+    assert run(lambda tx, ty: tuple(bf + ((h - 1 - ty * 256) * w + tx * 256) * 3 + c for c in range(3)), -w * 3, 3) == want, "negative row stride"
+    wide = np.zeros((h, w, 7), np.uint8)
+    wide[:, :, [0, 3, 6]] = rgb
+    bw = wide.ctypes.data
+    assert run(lambda tx, ty: tuple(bw + (ty * 256 * w + tx * 256) * 7 + c for c in (0, 3, 6)), w * 7, 7) == want, "stride 7"
+    rgba16 = np.zeros((h, w, 4), np.uint16)
+    img16 = synth_image(w, h, 16, seed=12)
+    rgba16[:, :, :3] = img16
+    b16 = rgba16.ctypes.data
+    got = run(lambda tx, ty: tuple(b16 + ((ty * 256 * w + tx * 256) * 4 + c) * 2 for c in range(3)), w * 4, 4, HYD_UINT16)
+    assert got == oracle.encode_image(img16), "rgba16 (the CLI's 16-bit layout, hydrium.c:445-449)"
+
+
+def test_far_tiles_of_huge_images(engine, oracle):
+    """Frame headers of tiles deep inside config-3 / config-5 sized images, and the level-10 container."""
+    buf = np.zeros(128, np.uint8)
+    n = engine.lib.hydb_image_header(65536, 65536, buf.ctypes.data, 128)
+    assert buf[:n].tobytes() == oracle.image_header(65536, 65536) and n == 59
+    d_out = engine.device_alloc(1 << 20)
+    try:
+        for (iw, ih, tx, ty, bits) in [(65536, 65536, 255, 255, 8), (65536, 65536, 200, 3, 8), (16384, 16384, 63, 63, 16),
+                                       (16384, 16384, 9, 40, 16), (1 << 20, 300, 4095, 1, 8)]:
+            tw, th = min(256, iw - tx * 256), min(256, ih - ty * 256)
+            win = synth_image(tw, th, bits, x0=tx * 256, y0=ty * 256, full_width=iw, full_height=ih)
+            d_img = engine.upload(win)
+            lin = int(bits == 16)
+            got = engine.download(d_out, engine.encode_tiles([_tile_desc(d_img, win, tx, ty, lin, (iw, ih), origin=True)], d_out, 1 << 20))
+            engine.device_free(d_img)
+            assert got == oracle.encode_tile(win, tx, ty, linear_light=lin, image_size=(iw, ih), window=True), (iw, tx, ty)
+    finally:
+        engine.device_free(d_out)
+
+
+def test_device_synth_generator_matches_numpy(engine):
+    for (w, h, bits, smooth, seed) in [(300, 200, 8, False, 0), (129, 77, 16, False, 5), (256, 256, 8, True, 2), (64, 64, 16, True, 9)]:
+        n = w * h * 3 * (bits // 8)
+        d = engine.device_alloc(n)
+        engine.synth_fill(d, w, h, bits=bits, seed=seed, smooth=smooth)
+        got = np.frombuffer(engine.download(d, n), np.uint8 if bits == 8 else np.uint16).reshape(h, w, 3)
+        engine.device_free(d)
+        assert np.array_equal(got, synth_image(w, h, bits, seed=seed, smooth=smooth)), (w, h, bits, smooth)
+    d = engine.device_alloc(256 * 256 * 3)
+    engine.synth_fill(d, 256, 256, bits=8, x0=256 * 200, y0=256 * 3, full_width=65536, full_height=65536)
+    got = np.frombuffer(engine.download(d, 256 * 256 * 3), np.uint8).reshape(256, 256, 3)
+    engine.device_free(d)
+    assert np.array_equal(got, synth_image(256, 256, 8, x0=256 * 200, y0=256 * 3, full_width=65536, full_height=65536))
+
+
+def test_config2_full_size(product_lib, oracle):
+    """BASELINE configs[1] at full size: 4096x4096 sRGB8, 256 tiles, full compare with the oracle,
+    plus size-independent properties: tile frames are position- but not order-dependent, and a
+    band-sharded encode concatenates to the same stream (what the multi-GPU run relies on)."""
+    w = h = 4096
+    with E.Engine(device=0, max_batch_tiles=256) as eng:
+        n_in = w * h * 3
+        d_in = eng.device_alloc(n_in)
+        cap = E.output_bound(w, h)
+        d_out = eng.device_alloc(cap)
+        eng.synth_fill(d_in, w, h, bits=8, seed=0)
+        n = eng.encode_image_device(d_in, w, h, 3, d_out=d_out, d_out_cap=cap)
+        full = eng.download(d_out, n)
+        img = np.frombuffer(eng.download(d_in, n_in), np.uint8).reshape(h, w, 3)
+        assert np.array_equal(img, synth_image(w, h, 8))
+        assert full == oracle.encode_image(img)
+        # idempotence
+        assert eng.download(d_out, eng.encode_image_device(d_in, w, h, 3, d_out=d_out, d_out_cap=cap)) == full
+        # sharded by tile rows == whole (ranks own contiguous bands; only rank 0 writes the header)
+        parts = []
+        for r in range(4):
+            band = d_in + r * 4 * 256 * w * 3
+            m = eng.encode_image_device(band, w, h, 3, tile_rows=(r * 4, r * 4 + 4), with_header=(r == 0), d_out=d_out, d_out_cap=cap)
+            parts.append(eng.download(d_out, m))
+        assert b"".join(parts) == full
+        eng.device_free(d_in)
+        eng.device_free(d_out)
