@@ -308,15 +308,15 @@ def run_ours(args) -> int:
     if rank == 0:
         peak, peak_src = measured_peaks()
         nb = max(stages["batches"], 1.0)
-        ans_ms = stages["ans_encode"] / nb
+        ans_ms = stages["ans_chain"] / nb
         b_in, b_out = float(n_in), float(out_bytes)
         achieved = (b_in + b_out) / (ans_ms / 1e3) / 1e9 if ans_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_ans_encode_dram_bytes_per_launch")
-        per_stage = {k: stages[k] / nb for k in ("xyb_dct_quant", "hf_tokens", "lf_group", "ans_encode", "gather")}
+                traffic = json.load(f).get("k_ans_chain_dram_bytes_per_launch")
+        per_stage = {k: stages[k] / nb for k in ("xyb_dct_quant", "hf_tokens", "lf_group", "ans_chain", "ans_pack", "gather")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -325,7 +325,7 @@ def run_ours(args) -> int:
                        "l2": "flushed between timed steps (512 MB write)", "bytes_in_per_px": 3,
                        "bytes_out_per_px": out_bytes / (WIDTH * HEIGHT),
                        "timing": "CUDA events on the engine stream, per step, max over ranks"},
-            "roofline": {"bound": "hbm", "kernel": "k_ans_encode", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_ans_chain", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_in + b_out,
                          "kernel_ms": ans_ms,

@@ -19,43 +19,47 @@ namespace hydb {
 
 constexpr uint32_t kAnsInitState = 0x130000u;   // reference: entropy.c:1083
 
-// per (cluster, token) constants for the chain
+// per (cluster, token) constants for the chain (16 bytes, one LDS.128)
 struct AnsSymInfo {
-    uint32_t m;        // reciprocal multiplier
-    uint32_t packed;   // (freq - 1):12 | shift:4 << 12 | table base:16 << 16
+    uint32_t m;     // reciprocal multiplier (ans_div_consts)
+    uint32_t w1;    // (32 + shift) in bits 0..7, frequency in bits 8..
+    uint32_t nf2;   // -2 * frequency (mod 2^32)
+    uint32_t b2;    // byte offset of the symbol's first slot in the flat uint16 inverse table
 };
-// `base` = cluster * 4096 + cumulative frequency: index of the symbol's first slot in the flat
-// inverse table inv[9 * 4096]
+// `base` = cluster * 4096 + cumulative frequency
 HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t base) {
     AnsSymInfo s;
-    uint32_t sh;
-    if (!f) {
-        s.m = 0;
-        s.packed = 0;
+    s.m = 0;
+    s.w1 = 32u | (1u << 8);
+    s.nf2 = 0;
+    s.b2 = 0;
+    if (!f)
         return s;
-    }
+    uint32_t sh;
     ans_div_consts(f, s.m, sh);
-    s.packed = (f - 1u) | (sh << 12) | (base << 16);
+    s.w1 = (32u + sh) | (f << 8);
+    s.nf2 = 0u - 2u * f;
+    s.b2 = 2u * base;
     return s;
 }
-HD uint32_t asi_freq(uint32_t packed) { return (packed & 0xFFFu) + 1u; }
-HD uint32_t asi_shift(uint32_t packed) { return (packed >> 12) & 0xFu; }
-HD uint32_t asi_base(uint32_t packed) { return packed >> 16; }
+HD uint32_t asi_freq(const AnsSymInfo &s) { return s.w1 >> 8; }
+constexpr uint32_t kAnsNoNext = 0xFFFFFFu;   // "no further symbol": never triggers a renormalisation
 
-// Code one symbol.  In: x (renormalised state), this symbol's constants, the next symbol's
-// frequency (the one that will be coded after this one, i.e. the PREVIOUS symbol in stream
-// order; pass 0x7FFFFFFF for "none").  Out: x for the next step, whether that step's
-// renormalisation fires, and the 16-bit word it emits.
-HD void ans_step(uint32_t &x, uint32_t m, uint32_t packed, const uint16_t *inv,
-                 uint32_t f_next, bool &flush, uint32_t &word) {
-    const uint32_t f = asi_freq(packed);
-    const uint32_t q = ans_div(x, m, asi_shift(packed));
-    const uint32_t idx = asi_base(packed) + (x - q * f);
-    const uint32_t slot = inv[idx];
-    const uint32_t s = (q << 12) | slot;
-    flush = (q >> 8) >= f_next;
-    word = s & 0xFFFFu;
-    x = flush ? (q >> 4) : s;
+// Code one symbol.  `w1n` = this symbol's shift in bits 0..7 and, in bits 8.., the frequency of
+// the symbol that will be coded NEXT (the previous one in stream order; kAnsNoNext for none).
+// `lookup(byte_offset)` reads the uint16 slot table.  Out: x for the next step, whether that
+// step's renormalisation fires (p), and the 16-bit word it would emit.
+template <typename Lookup>
+HD void ans_step(uint32_t &x, uint32_t m, uint32_t w1n, uint32_t nf2, uint32_t b2, Lookup lookup,
+                 uint32_t &p, uint32_t &word) {
+    const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
+    const uint32_t q = (uint32_t)(t >> (w1n & 63u));
+    const uint32_t slot = lookup(q * nf2 + (2u * x + b2));   // 2 * (base + x - q * f), mod 2^32
+    p = (q >> 8) >= (w1n >> 8) ? 1u : 0u;
+    const uint32_t a = p ? (q >> 4) : (q << 12);
+    const uint32_t keep = p ? 0u : 0xFFFFu;
+    word = ((q << 12) | slot) & 0xFFFFu;
+    x = a | (slot & keep);
 }
 
 }  // namespace hydb

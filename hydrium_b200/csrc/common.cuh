@@ -33,6 +33,7 @@ constexpr int kAnsTotal = 4096;          // 12-bit ANS precision, reference: ent
 constexpr int kLfBitsWords = 4096;       // LF stream scratch (u32 words) per tile
 constexpr int kSlabBytes = 768 * 1024;   // worst-case frame: header + TOC + payload
 constexpr int kSlabHeaderReserve = 64;   // frame header + TOC are right-justified before this
+constexpr int kDBitsWords = 384;         // section D (ANS header tail) scratch per tile
 constexpr int kTemplWords = 256;         // per-shape constant bit strings (u32 words each)
 
 // error bits reported per tile (engine maps them to HYD_INTERNAL_ERROR + message)

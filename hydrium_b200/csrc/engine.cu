@@ -51,8 +51,8 @@ struct HydbEngine {
     size_t host_in_cap = 0, host_out_cap = 0;
     // optional per-stage timing with CUDA events on the launching streams
     bool timing = false, timed_pending = false;
-    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, lev[2] = {nullptr, nullptr};
-    double stage_ms[6] = {0, 0, 0, 0, 0, 0};   // xyb_dct, hf_tokens, ans, gather, lf_group, batches
+    cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, lev[2] = {nullptr, nullptr};
+    double stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};   // xyb_dct, hf_tokens, ans_chain, ans_pack(+LF wait), gather, lf_group, batches
 };
 
 #define CK(call)                                                                        \
@@ -122,6 +122,8 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(dalloc(&w.hist, T * kHfClusters * kHfTokens));
     A(dalloc(&w.lfbits, T * kLfBitsWords));
     A(dalloc(&w.lfbitlen, T));
+    A(dalloc(&w.dbits, T * kDBitsWords));
+    A(dalloc(&w.chain_out, T * 4));
     A(dalloc(&w.flags, T * (kMaxHfSyms / 32)));
     A(dalloc(&w.fwords, T * kMaxHfSyms));
     A(dalloc(&w.slab, T * kSlabBytes));
@@ -170,7 +172,7 @@ void hydb_engine_destroy(HydbEngine *eng) {
     if (eng->st) cudaStreamSynchronize(eng->st);
     if (eng->st2) cudaStreamSynchronize(eng->st2);
     Workspace &w = eng->ws;
-    void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags,
+    void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags, w.dbits, w.chain_out,
                    w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.dbg_xyb, w.dbg_dct,
                    w.dbg_freqs, w.dbg_sect, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
@@ -296,13 +298,15 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     CK(cudaEventRecord(eng->ev_lf, eng->st2));
     launch_hf_tokens(eng->ws, n, st);
     if (tm) CK(cudaEventRecord(eng->tev[2], st));
-    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));
-    launch_ans_encode(eng->ws, eng->templ, n, st);
+    launch_ans_chain(eng->ws, n, st);
     if (tm) CK(cudaEventRecord(eng->tev[3], st));
-    launch_gather(eng->ws, n, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));   // the LF stream is first needed by the packer
+    launch_ans_pack(eng->ws, eng->templ, n, st);
     if (tm) CK(cudaEventRecord(eng->tev[4], st));
+    launch_gather(eng->ws, n, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    if (tm) CK(cudaEventRecord(eng->tev[5], st));
     eng->timed_pending = tm;
-    eng->launches += 6;
+    eng->launches += 7;
     CK(cudaMemcpyAsync(eng->h_err, eng->ws.tile_err, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(eng->h_err + eng->max_batch, eng->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(eng->h_total, eng->ws.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -321,13 +325,13 @@ HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     if (eng->timed_pending) {
         CK(cudaStreamSynchronize(eng->st2));
         float ms = 0;
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 5; k++) {
             CK(cudaEventElapsedTime(&ms, eng->tev[k], eng->tev[k + 1]));
             eng->stage_ms[k] += ms;
         }
         CK(cudaEventElapsedTime(&ms, eng->lev[0], eng->lev[1]));
-        eng->stage_ms[4] += ms;
-        eng->stage_ms[5] += 1;
+        eng->stage_ms[5] += ms;
+        eng->stage_ms[6] += 1;
         eng->timed_pending = false;
     }
     for (uint32_t i = 0; i < eng->last_n; i++) {
@@ -516,11 +520,12 @@ HYDStatusCode hydb_engine_enable_timing(HydbEngine *eng, int enable) {
     return HYD_OK;
 }
 
-// accumulated device milliseconds since the last call: xyb_dct, hf_tokens, ans, gather, lf_group, #batches
-HYDStatusCode hydb_engine_stage_ms(HydbEngine *eng, double out[6]) {
+// accumulated device milliseconds since the last call:
+// xyb_dct, hf_tokens, ans_chain, ans_pack (incl. any wait for lf_group), gather, lf_group, #batches
+HYDStatusCode hydb_engine_stage_ms(HydbEngine *eng, double out[7]) {
     if (!eng || !out)
         return HYD_API_ERROR;
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 7; k++) {
         out[k] = eng->stage_ms[k];
         eng->stage_ms[k] = 0;
     }

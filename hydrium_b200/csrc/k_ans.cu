@@ -1,22 +1,25 @@
 // hydrium_b200/csrc/k_ans.cu
 //
-// Stage 4: everything after tokenisation, one CTA per tile:
+// Stage 4: everything after tokenisation, two kernels, one CTA per tile each.
+//
+// k_ans_chain (needs only the HF symbols + histograms):
 //   1. ANS model from the tile's histograms: normalisation, alias split, inverse slot table,
 //      exact reciprocals                                   (reference: entropy.c:943-978, 184-301)
-//   2. section D (ANS stream header tail)                  (entropy.c:563-572, 303-369, 980-1001)
-//   3. payload prefix  A | L | B | D  spliced bit-exactly into the tile's output slab
+//   2. section D (ANS stream header tail) -> HBM           (entropy.c:563-572, 303-369, 980-1001)
+//   3. the reverse rANS state chain                        (entropy.c:1083-1120)
+// k_ans_pack (also needs the LF stream of k_lf_group, which ran concurrently with the chain):
+//   4. payload prefix  A | L | B | D  spliced bit-exactly into the tile's output slab
 //                                                          (encoder.c:834-843, 959-967, bitwriter.c:80-108)
-//   4. the reverse rANS state chain                        (entropy.c:1083-1120)
 //   5. forward bit packing of [state][renorm words + residue bits]   (entropy.c:1122-1147)
 //   6. frame header + TOC entry                            (encoder.c:327-435, 992-1005)
 //
-// The chain (4) is the one inherently serial part of the codec: one 32-bit state threads
+// The chain (3) is the one inherently serial part of the codec: one 32-bit state threads
 // through every symbol of the group.  It runs in warp 0 with every lane carrying the same state
-// (so the slot-table read is a shared-memory broadcast and nothing diverges); the lanes differ
-// only in which symbol's constants they hold: each lane fetches one symbol of the current
-// 32-symbol batch and its (m, packed) constants, and the unrolled step loop broadcasts them with
-// shuffles that do not depend on the state.  See ans_chain.cuh for the per-step critical path.
-// All other warps build tables before and pack bits after the chain.
+// (so the slot-table read is a shared-memory broadcast and nothing diverges); the other warps
+// only help build the tables and then retire.  Lane L fetches symbol (batch * 32 + L) one batch
+// ahead, looks up its constants and stages them in shared memory; the 32 steps of a batch are
+// straight-line code whose staged records are prefetched three steps ahead, so nothing but the
+// state itself sits on the dependent path.  See ans_chain.cuh for the per-step critical path.
 #include "ans_chain.cuh"
 #include "headers.cuh"
 #include "kernels.h"
@@ -25,18 +28,17 @@
 namespace hydb {
 
 constexpr int kAnsThreads = 256;
-constexpr int kDBitsWords = 384;
 
 struct AnsShared {
     uint16_t inv[kHfClusters * kAnsTotal];              // 73,728 B inverse alias table
-    AnsSymInfo info[kHfClusters * kHfTokens];           //  4,608 B
+    uint4 info4[kHfClusters * kHfTokens];               //  9,216 B per-symbol chain constants
+    uint4 stage[2][32];                                 //  1,024 B staged batch records
     AnsCluster cl[kHfClusters];                         //  5,256 B
     uint32_t hist[kHfClusters * kHfTokens];             //  2,304 B
     uint32_t dbits[kDBitsWords];                        //  1,536 B
-    uint32_t scan_a[kAnsThreads], scan_b[kAnsThreads];  //  2,048 B
     uint32_t alpha[kHfClusters];
     int log_alpha;
-    uint32_t dbitlen, nwords, final_state, err, ebits_total;
+    uint32_t dbitlen, err;
 };
 
 int ans_encode_smem_bytes() { return (int)sizeof(AnsShared); }
@@ -123,27 +125,32 @@ __device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *
     __syncthreads();
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __global__ void __launch_bounds__(kAnsThreads)
-k_ans_encode(Workspace ws, Templates tp) {
+k_ans_chain(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AnsShared &s = *reinterpret_cast<AnsShared *>(smem_raw);
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileDesc t = ws.tiles[tile];
     const uint32_t N = ws.nsyms[tile];
     const uint32_t *__restrict__ sy = ws.syms + (size_t)tile * kMaxHfSyms;
     uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
     uint16_t *__restrict__ fwords = ws.fwords + (size_t)tile * kMaxHfSyms;
-    uint8_t *slab = ws.slab + (size_t)tile * kSlabBytes;
-    uint32_t *payload = reinterpret_cast<uint32_t *>(slab + kSlabHeaderReserve);
-    constexpr uint32_t kPayloadCapBits = (uint32_t)(kSlabBytes - kSlabHeaderReserve) * 8u - 64u;
 
     // ---- 1. model ---------------------------------------------------------------------------
     for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kAnsThreads)
         s.hist[i] = ws.hist[(size_t)tile * kHfClusters * kHfTokens + i];
-    if (tid == 0) {
+    if (tid == 0)
         s.err = 0;
-        s.nwords = 0;
-    }
     __syncthreads();
     if (tid < (uint32_t)kHfClusters) {
         uint32_t a = 0;
@@ -178,7 +185,8 @@ k_ans_encode(Workspace ws, Templates tp) {
                 atomicOr(&s.err, (uint32_t)kErrAlias);
         }
         for (uint32_t k = 0; k < (uint32_t)kHfTokens; k++) {
-            s.info[c * kHfTokens + k] = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
+            const AnsSymInfo si = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
+            s.info4[c * kHfTokens + k] = make_uint4(si.m, si.w1, si.nf2, si.b2);
             if (ws.dbg_freqs)
                 ws.dbg_freqs[((size_t)tile * kHfClusters + c) * kHfTokens + k] = cl.freq[k];
         }
@@ -208,47 +216,55 @@ k_ans_encode(Workspace ws, Templates tp) {
             s.err |= kErrSlab;
     }
     __syncthreads();
-
-    // ---- 3. payload prefix A | L | B | D ---------------------------------------------------------
-    const uint32_t la = tp.bits[0], lb = tp.bits[1 + t.shape], ll = ws.lfbitlen[tile], ld = s.dbitlen;
-    const uint32_t e_start = la + ll + lb + ld;
-    const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !s.err && N > 0 && log_alpha <= 6;
-    for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kAnsThreads)
-        payload[w] = 0;
-    __syncthreads();
-    if (sane) {
-        append_bits(payload, 0, tp.words, la, tid, kAnsThreads);
-        append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kAnsThreads);
-        append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kAnsThreads);
-        append_bits(payload, (uint64_t)la + ll + lb, s.dbits, ld, tid, kAnsThreads);
+    const bool sane = !s.err && N > 0 && log_alpha <= 6;
+    {
+        const uint32_t words = (s.dbitlen + 31) >> 5;
+        for (uint32_t i = tid; i < words && i < (uint32_t)kDBitsWords; i += kAnsThreads)
+            ws.dbits[(size_t)tile * kDBitsWords + i] = s.dbits[i];
     }
-    __syncthreads();
+    if (warp != 0)
+        return;   // the remaining warps have nothing to do while the chain runs
+    if (!sane) {
+        if (lane == 0) {
+            ws.chain_out[tile * 4 + 0] = 0;
+            ws.chain_out[tile * 4 + 1] = 0;
+            ws.chain_out[tile * 4 + 2] = s.dbitlen;
+            ws.chain_out[tile * 4 + 3] = s.err ? s.err : (uint32_t)kErrAlphabet;
+        }
+        return;
+    }
 
-    // ---- 4. the chain ------------------------------------------------------------------------------
-    if (warp == 0 && sane) {
+    // ---- 3. the chain ------------------------------------------------------------------------------
+    {
         const uint32_t FULL = 0xFFFFFFFFu;
         const int nbatch = (int)((N + 31) >> 5);
-        auto fetch = [&](int bi, uint32_t &m, uint32_t &pk) {
-            m = 0;
-            pk = 0;
-            if (bi >= 0) {
-                const uint32_t p = (uint32_t)bi * 32u + lane;
-                if (p < N) {
-                    const uint32_t sym = sy[p];
-                    const AnsSymInfo inf = s.info[hf_cluster(sym) * kHfTokens + hf_token(sym)];
-                    m = inf.m;
-                    pk = inf.packed;
-                }
-            }
+        const uint32_t inv_base = (uint32_t)__cvta_generic_to_shared(s.inv);
+        const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(s.stage);
+        auto lookup = [](uint32_t addr) -> uint32_t { return lds16(addr); };
+        auto load_sym = [&](int bi) -> uint32_t {
+            const uint32_t p = (uint32_t)bi * 32u + lane;
+            return (bi >= 0 && p < N) ? sy[p] : 0xFFFFFFFFu;
         };
-        uint32_t cur_m, cur_pk, nxt_m, nxt_pk;
-        fetch(nbatch - 1, cur_m, cur_pk);
-        fetch(nbatch - 2, nxt_m, nxt_pk);
+        auto info_of = [&](uint32_t sym) -> uint4 {
+            if (sym == 0xFFFFFFFFu)
+                return make_uint4(0u, 32u | (1u << 8), 0u, 0u);
+            return s.info4[hf_cluster(sym) * kHfTokens + hf_token(sym)];
+        };
+        // stage a batch: `inf` = this lane's constants, `inf_lo` = constants of the next lower batch
+        auto stage = [&](int par, const uint4 &inf, const uint4 &inf_lo, bool lowest) {
+            const uint32_t f = inf.y >> 8;
+            const uint32_t f_up = __shfl_up_sync(FULL, f, 1);
+            const uint32_t f_lo31 = __shfl_sync(FULL, inf_lo.y >> 8, 31);
+            const uint32_t f_next = lane ? f_up : (lowest ? kAnsNoNext : f_lo31);
+            s.stage[par][lane] = make_uint4(inf.x, (inf.y & 0xFFu) | (f_next << 8), inf.z, inf.w + inv_base);
+        };
+        uint4 inf_cur = info_of(load_sym(nbatch - 1));
+        uint4 inf_nxt = info_of(load_sym(nbatch - 2));
+        stage(0, inf_cur, inf_nxt, nbatch == 1);
         // virtual step that "produced" the initial state 0x130000 = (0x130 << 12) | 0
-        uint32_t x;
-        uint32_t carry_flag, carry_word;
+        uint32_t x, carry_flag, carry_word;
         {
-            const uint32_t f_first = asi_freq(__shfl_sync(FULL, cur_pk, (N - 1) & 31));
+            const uint32_t f_first = __shfl_sync(FULL, inf_cur.y >> 8, (N - 1) & 31);
             carry_flag = ((kAnsInitState >> 20) >= f_first) ? 1u : 0u;
             carry_word = kAnsInitState & 0xFFFFu;
             x = carry_flag ? (kAnsInitState >> 16) : kAnsInitState;
@@ -256,31 +272,45 @@ k_ans_encode(Workspace ws, Templates tp) {
         uint32_t cnt = 0;
         uint32_t lowest_flag = 0xFFFFFFFFu;   // position of the most recent (lowest) flagged symbol
         uint32_t gap_err = 0;
+        int par = 0;
         for (int bi = nbatch - 1; bi >= 0; --bi) {
+            __syncwarp();
+            const uint32_t sym_nn = load_sym(bi - 2);   // in flight while this batch is coded
             const uint32_t base = (uint32_t)bi * 32u;
             const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
-            // frequency of the symbol coded after each lane's symbol (= previous in stream order)
-            const uint32_t f_cur = asi_freq(cur_pk);
-            const uint32_t f_up = __shfl_up_sync(FULL, f_cur, 1);
-            const uint32_t f_nx = asi_freq(__shfl_sync(FULL, nxt_pk, 31));
-            const uint32_t f_prev = lane ? f_up : (bi ? f_nx : 0x7FFFFFFFu);
+            const uint32_t stg = stage_base + (uint32_t)par * 32u * 16u;
             uint32_t mask = carry_flag << jtop;
             uint32_t myword = carry_word;
+            // a renormalisation found while coding symbol j belongs to symbol j - 1
+            if (jtop == 31) {
+                uint4 r0 = lds128(stg + 31 * 16), r1 = lds128(stg + 30 * 16), r2 = lds128(stg + 29 * 16);
 #pragma unroll
-            for (int j = 31; j >= 0; --j) {
-                if (j <= jtop) {   // warp-uniform
-                    const uint32_t m = __shfl_sync(FULL, cur_m, j);
-                    const uint32_t pk = __shfl_sync(FULL, cur_pk, j);
-                    const uint32_t fn = __shfl_sync(FULL, f_prev, j);
-                    bool fl;
-                    uint32_t word;
-                    ans_step(x, m, pk, s.inv, fn, fl, word);
+                for (int j = 31; j >= 0; --j) {
+                    const uint4 st = r0;
+                    r0 = r1;
+                    r1 = r2;
+                    if (j >= 3)
+                        r2 = lds128(stg + (uint32_t)(j - 3) * 16u);
+                    uint32_t p, word;
+                    ans_step(x, st.x, st.y, st.z, st.w, lookup, p, word);
                     if (j > 0) {
-                        mask |= (fl ? 1u : 0u) << (j > 0 ? j - 1 : 0);
-                        if (fl && lane == (uint32_t)(j - 1))
-                            myword = word;
+                        mask |= p << (j > 0 ? j - 1 : 0);
+                        myword = lane == (uint32_t)(j - 1) ? word : myword;
                     } else {
-                        carry_flag = fl ? 1u : 0u;
+                        carry_flag = p;
+                        carry_word = word;
+                    }
+                }
+            } else {
+                for (int j = jtop; j >= 0; --j) {
+                    const uint4 st = lds128(stg + (uint32_t)j * 16u);
+                    uint32_t p, word;
+                    ans_step(x, st.x, st.y, st.z, st.w, lookup, p, word);
+                    if (j > 0) {
+                        mask |= p << (j - 1);
+                        myword = lane == (uint32_t)(j - 1) ? word : myword;
+                    } else {
+                        carry_flag = p;
                         carry_word = word;
                     }
                 }
@@ -299,23 +329,63 @@ k_ans_encode(Workspace ws, Templates tp) {
                 lowest_flag = lo;
             }
             cnt += __popc(mask);
-            cur_m = nxt_m;
-            cur_pk = nxt_pk;
-            fetch(bi - 2, nxt_m, nxt_pk);
+            // stage the next batch into the other buffer
+            inf_cur = inf_nxt;
+            inf_nxt = info_of(sym_nn);
+            par ^= 1;
+            if (bi > 0)
+                stage(par, inf_cur, inf_nxt, bi == 1);
         }
         if (lowest_flag != 0xFFFFFFFFu && lowest_flag >= 65536u)
             gap_err = 1;   // the reference keeps this distance in a uint16_t (entropy.c:16, 1094, 1123)
         if (lane == 0) {
-            s.nwords = cnt;
-            s.final_state = x;
-            if (gap_err)
-                s.err |= kErrAnsGap;
+            ws.chain_out[tile * 4 + 0] = cnt;
+            ws.chain_out[tile * 4 + 1] = x;
+            ws.chain_out[tile * 4 + 2] = s.dbitlen;
+            ws.chain_out[tile * 4 + 3] = gap_err ? (uint32_t)kErrAnsGap : 0u;
         }
     }
+}
+
+struct PackShared {
+    uint32_t scan_a[kAnsThreads], scan_b[kAnsThreads];
+    uint32_t err, ebits_total;
+};
+
+__global__ void __launch_bounds__(kAnsThreads)
+k_ans_pack(Workspace ws, Templates tp) {
+    __shared__ PackShared s;
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+    const TileDesc t = ws.tiles[tile];
+    const uint32_t N = ws.nsyms[tile];
+    const uint32_t *__restrict__ sy = ws.syms + (size_t)tile * kMaxHfSyms;
+    const uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
+    const uint16_t *__restrict__ fwords = ws.fwords + (size_t)tile * kMaxHfSyms;
+    uint8_t *slab = ws.slab + (size_t)tile * kSlabBytes;
+    uint32_t *payload = reinterpret_cast<uint32_t *>(slab + kSlabHeaderReserve);
+    constexpr uint32_t kPayloadCapBits = (uint32_t)(kSlabBytes - kSlabHeaderReserve) * 8u - 64u;
+    const uint32_t W = ws.chain_out[tile * 4 + 0], final_state = ws.chain_out[tile * 4 + 1];
+    const uint32_t ld = ws.chain_out[tile * 4 + 2], chain_err = ws.chain_out[tile * 4 + 3];
+    if (tid == 0) {
+        s.err = chain_err;
+        s.ebits_total = 0;
+    }
+
+    // ---- 4. payload prefix A | L | B | D ---------------------------------------------------------
+    const uint32_t la = tp.bits[0], lb = tp.bits[1 + t.shape], ll = ws.lfbitlen[tile];
+    const uint32_t e_start = la + ll + lb + ld;
+    const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !chain_err && N > 0 && !ws.tile_err[tile];
+    for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kAnsThreads)
+        payload[w] = 0;
     __syncthreads();
+    if (sane) {
+        append_bits(payload, 0, tp.words, la, tid, kAnsThreads);
+        append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kAnsThreads);
+        append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kAnsThreads);
+        append_bits(payload, (uint64_t)la + ll + lb, ws.dbits + (size_t)tile * kDBitsWords, ld, tid, kAnsThreads);
+    }
 
     // ---- 5. forward packing of section E -------------------------------------------------------------
-    const uint32_t W = s.nwords;
     const uint64_t total_bits64 = (uint64_t)e_start + 32u + ws.resbits[tile] + 16ull * W;
     const bool fits = sane && total_bits64 <= kPayloadCapBits;
     if (tid == 0 && sane && !fits)
@@ -354,7 +424,7 @@ k_ans_encode(Workspace ws, Templates tp) {
                 if (tot_fl != W || (uint64_t)e_start + 32u + tot_bits != total_bits64)
                     s.err |= kErrSlab;   // internal consistency check
                 // final state, low half first (entropy.c:1127-1130)
-                const uint32_t st = s.final_state, sh = e_start & 31u, w0 = e_start >> 5;
+                const uint32_t st = final_state, sh = e_start & 31u, w0 = e_start >> 5;
                 atomicOr(&payload[w0], st << sh);
                 if (sh)
                     atomicOr(&payload[w0 + 1], st >> (32 - sh));
@@ -442,9 +512,13 @@ k_ans_encode(Workspace ws, Templates tp) {
     }
 }
 
-void launch_ans_encode(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st) {
-    cudaFuncSetAttribute(k_ans_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
-    k_ans_encode<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws, t);
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
+    cudaFuncSetAttribute(k_ans_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
+    k_ans_chain<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws);
+}
+
+void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st) {
+    k_ans_pack<<<ntiles, kAnsThreads, 0, st>>>(ws, t);
 }
 
 }  // namespace hydb

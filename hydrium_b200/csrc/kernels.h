@@ -29,6 +29,8 @@ struct Workspace {
     uint32_t *hist;           // [T][9][64] raw token counts
     uint32_t *lfbits;         // [T][kLfBitsWords] LF stream bit string (section L)
     uint32_t *lfbitlen;       // [T]
+    uint32_t *dbits;          // [T][kDBitsWords] section D bit string
+    uint32_t *chain_out;      // [T][4] renorm word count, final state, section D bits, error bits
     uint32_t *flags;          // [T][kMaxHfSyms / 32] renormalisation flag per symbol
     uint16_t *fwords;         // [T][kMaxHfSyms] renormalisation words in chain (reverse) order
     uint8_t *slab;            // [T][kSlabBytes] frames: header+TOC right-justified before byte 64
@@ -56,7 +58,8 @@ void launch_build_templates(const Templates &t, const uint32_t *d_shape_dims /*[
 void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st);
 void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
-void launch_ans_encode(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
+void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
 // compaction: out[prefix_len + out_off[i] ...] = frame i ; total written to ws.out_off[ntiles]
 void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
                    uint32_t *d_overflow, cudaStream_t st);

@@ -148,9 +148,9 @@ class Engine:
 
     def stage_ms(self) -> dict:
         """Device ms accumulated since the last call (CUDA events on the launching streams)."""
-        arr = (C.c_double * 6)()
+        arr = (C.c_double * 7)()
         self._check(self.lib.hydb_engine_stage_ms(self._h, C.byref(arr)))
-        keys = ("xyb_dct_quant", "hf_tokens", "ans_encode", "gather", "lf_group", "batches")
+        keys = ("xyb_dct_quant", "hf_tokens", "ans_chain", "ans_pack", "gather", "lf_group", "batches")
         return dict(zip(keys, list(arr)))
 
     # -- stage taps (parity tests) -----------------------------------------------------------

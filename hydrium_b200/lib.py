@@ -101,6 +101,6 @@ def load_library() -> C.CDLL:
     lib.hydb_engine_enable_timing.restype = C.c_int
     lib.hydb_engine_enable_timing.argtypes = [vp, C.c_int]
     lib.hydb_engine_stage_ms.restype = C.c_int
-    lib.hydb_engine_stage_ms.argtypes = [vp, C.POINTER(C.c_double * 6)]
+    lib.hydb_engine_stage_ms.argtypes = [vp, C.POINTER(C.c_double * 7)]
     _lib = lib
     return lib

@@ -164,9 +164,10 @@ HYDRIUM_EXPORT HYDStatusCode hydb_encode_image_host(HydbEngine *engine, const vo
 
 /* Per-kernel device time, measured with CUDA events on the launching streams.  stage_ms returns and
  * resets the milliseconds accumulated since the last call:
- * [0] xyb_dct_quant [1] hf_tokens [2] ans_encode [3] offsets+gather [4] lf_group (2nd stream) [5] #batches */
+ * [0] xyb_dct_quant [1] hf_tokens [2] ans_chain [3] ans_pack (incl. waiting for lf_group) [4] offsets+gather
+ * [5] lf_group (second stream, concurrent with [1]-[2]) [6] number of batches */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_enable_timing(HydbEngine *engine, int enable);
-HYDRIUM_EXPORT HYDStatusCode hydb_engine_stage_ms(HydbEngine *engine, double out[6]);
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_stage_ms(HydbEngine *engine, double out[7]);
 
 /* image header bytes (with the level-10 container prefix where the reference emits it) */
 HYDRIUM_EXPORT int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap);

@@ -149,7 +149,7 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
     {
         // virtual "previous step" holding the initial state: q = state >> 12, slot = 0
         const uint32_t q0 = kAnsInitState >> 12;
-        const uint32_t f_first = n ? asi_freq(info[hf_cluster(syms[n - 1])][hf_token(syms[n - 1])].packed) : 0x7FFFFFFFu;
+        const uint32_t f_first = n ? asi_freq(info[hf_cluster(syms[n - 1])][hf_token(syms[n - 1])]) : kAnsNoNext;
         const bool fl = (q0 >> 8) >= f_first;
         if (fl) {
             flag[n - 1] = 1;
@@ -162,10 +162,12 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
     for (uint32_t r = 0; r < n; r++) {
         const uint32_t p = n - 1 - r;
         const uint32_t c = hf_cluster(syms[p]), t = hf_token(syms[p]);
-        const uint32_t f_next = p ? asi_freq(info[hf_cluster(syms[p - 1])][hf_token(syms[p - 1])].packed) : 0x7FFFFFFFu;
-        bool fl;
-        uint32_t word;
-        ans_step(x, info[c][t].m, info[c][t].packed, &inv[0][0], f_next, fl, word);
+        const uint32_t f_next = p ? asi_freq(info[hf_cluster(syms[p - 1])][hf_token(syms[p - 1])]) : kAnsNoNext;
+        uint32_t fl, word;
+        const AnsSymInfo &si = info[c][t];
+        const uint8_t *inv_bytes = (const uint8_t *)&inv[0][0];
+        ans_step(x, si.m, (si.w1 & 0xFFu) | (f_next << 8), si.nf2, si.b2,
+                 [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; }, fl, word);
         if (fl) {
             flag[p - 1] = 1;
             words.push_back((uint16_t)word);
