@@ -22,7 +22,7 @@ constexpr uint32_t kAnsInitState = 0x130000u;   // reference: entropy.c:1083
 // per (cluster, token) constants for the chain (16 bytes, one LDS.128)
 struct AnsSymInfo {
     uint32_t m;     // reciprocal multiplier (ans_div_consts)
-    uint32_t w1;    // (32 + shift) in bits 0..7, frequency in bits 8..
+    uint32_t w1;    // shift (0..12) in bits 0..7, frequency in bits 8..
     uint32_t nf2;   // -2 * frequency (mod 2^32)
     uint32_t b2;    // byte offset of the symbol's first slot in the flat uint16 inverse table
 };
@@ -30,14 +30,14 @@ struct AnsSymInfo {
 HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t base) {
     AnsSymInfo s;
     s.m = 0;
-    s.w1 = 32u | (1u << 8);
+    s.w1 = 0u | (1u << 8);
     s.nf2 = 0;
     s.b2 = 0;
     if (!f)
         return s;
     uint32_t sh;
     ans_div_consts(f, s.m, sh);
-    s.w1 = (32u + sh) | (f << 8);
+    s.w1 = sh | (f << 8);
     s.nf2 = 0u - 2u * f;
     s.b2 = 2u * base;
     return s;
@@ -53,12 +53,31 @@ template <typename Lookup>
 HD void ans_step(uint32_t &x, uint32_t m, uint32_t w1n, uint32_t nf2, uint32_t b2, Lookup lookup,
                  uint32_t &p, uint32_t &word) {
     const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
-    const uint32_t q = (uint32_t)(t >> (w1n & 63u));
+    const uint32_t q = (uint32_t)(t >> 32) >> (w1n & 31u);   // total shift 32 + sh: only the high word matters
     const uint32_t slot = lookup(q * nf2 + (2u * x + b2));   // 2 * (base + x - q * f), mod 2^32
     p = (q >> 8) >= (w1n >> 8) ? 1u : 0u;
     const uint32_t a = p ? (q >> 4) : (q << 12);
     const uint32_t keep = p ? 0u : 0xFFFFu;
     word = ((q << 12) | slot) & 0xFFFFu;
+    x = a | (slot & keep);
+}
+
+
+// Leaner form used by the kernel: returns the state s' BEFORE the next renormalisation instead of
+// (flag, word).  Both are recovered later, off the dependent path, by whoever knows the next
+// symbol's frequency f:   flag = (s' >> 20) >= f,  word = s' & 0xFFFF   (entropy.c:1092-1100).
+// `thr` = (next symbol's frequency << 8) | shift: the renormalisation test
+// (q >> 8) >= f_next is evaluated as (q | 0xFF) >= thr, and the shifter uses the low five bits.
+template <typename Lookup>
+HD void ans_step_state(uint32_t &x, uint32_t m, uint32_t thr, uint32_t nf2, uint32_t b2, Lookup lookup,
+                       uint32_t &s_out) {
+    const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
+    const uint32_t q = (uint32_t)(t >> 32) >> (thr & 31u);   // total shift 32 + sh: only the high word matters
+    const uint32_t slot = lookup(q * nf2 + (2u * x + b2));
+    const bool p = (q | 0xFFu) >= thr;                       // renormalise for the next symbol?
+    const uint32_t a = p ? (q >> 4) : (q << 12);             // s' >> 16 == q >> 4 (slot < 4096)
+    const uint32_t keep = p ? 0u : 0xFFFFu;
+    s_out = (q << 12) | slot;
     x = a | (slot & keep);
 }
 

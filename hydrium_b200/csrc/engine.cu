@@ -131,6 +131,8 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(dalloc(&w.frame_len, T));
     A(dalloc(&w.out_off, T + 1));
     A(dalloc(&w.tile_err, T));
+    A(dalloc(&w.sm_ticket, 256));
+    A(cudaMemsetAsync(w.sm_ticket, 0, 256 * sizeof(uint32_t), eng->st));
     A(dalloc(&eng->lut8_srgb, 256));
     A(dalloc(&eng->lut8_lin, 256));
     A(dalloc(&eng->lut16_srgb, 65536));
@@ -173,8 +175,8 @@ void hydb_engine_destroy(HydbEngine *eng) {
     if (eng->st2) cudaStreamSynchronize(eng->st2);
     Workspace &w = eng->ws;
     void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags, w.dbits, w.chain_out,
-                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.dbg_xyb, w.dbg_dct,
-                   w.dbg_freqs, w.dbg_sect, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
+                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.sm_ticket, w.dbg_xyb, w.dbg_dct,
+                   w.dbg_freqs, w.dbg_sect, w.dbg_clk, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -207,14 +209,15 @@ HYDStatusCode hydb_engine_enable_taps(HydbEngine *eng, int enable) {
         CK(dalloc(&w.dbg_dct, T * 65536 * 3));
         CK(dalloc(&w.dbg_freqs, T * kHfClusters * kHfTokens));
         CK(dalloc(&w.dbg_sect, T * 4));
+        CK(dalloc(&w.dbg_clk, T * 4));
         CK(cudaMemset(w.dbg_xyb, 0, T * 65536 * 3 * sizeof(float)));
         CK(cudaMemset(w.dbg_dct, 0, T * 65536 * 3 * sizeof(float)));
         eng->taps = true;
     } else if (!enable && eng->taps) {
         CK(cudaStreamSynchronize(eng->st));
-        cudaFree(w.dbg_xyb); cudaFree(w.dbg_dct); cudaFree(w.dbg_freqs); cudaFree(w.dbg_sect);
+        cudaFree(w.dbg_xyb); cudaFree(w.dbg_dct); cudaFree(w.dbg_freqs); cudaFree(w.dbg_sect); cudaFree(w.dbg_clk);
         w.dbg_xyb = w.dbg_dct = nullptr;
-        w.dbg_freqs = w.dbg_sect = nullptr;
+        w.dbg_freqs = w.dbg_sect = w.dbg_clk = nullptr;
         eng->taps = false;
     }
     return HYD_OK;
@@ -569,6 +572,7 @@ int64_t hydb_engine_read_tap(HydbEngine *eng, int what, uint32_t tile, void *dst
     case HYDB_TAP_LFBITS:
         if (!read_u32(w.lfbitlen + tile)) return HYD_INTERNAL_ERROR;
         src = w.lfbits + (size_t)tile * kLfBitsWords; bytes = (((uint64_t)tmp + 31) / 32) * 4; break;
+    case HYDB_TAP_CLK: src = w.dbg_clk ? w.dbg_clk + (size_t)tile * 4 : nullptr; bytes = 16; break;
     case HYDB_TAP_SECT: src = w.dbg_sect ? w.dbg_sect + (size_t)tile * 4 : nullptr; bytes = 16; break;
     case HYDB_TAP_PAYLOAD: {
         uint32_t off = 0;

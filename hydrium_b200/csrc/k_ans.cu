@@ -28,11 +28,23 @@
 namespace hydb {
 
 constexpr int kAnsThreads = 256;
+constexpr int kRing = 4;                 // batches in flight between the helper and the chain warp
+constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;   // named barrier ids (0 is __syncthreads)
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 struct AnsShared {
     uint16_t inv[kHfClusters * kAnsTotal];              // 73,728 B inverse alias table
     uint4 info4[kHfClusters * kHfTokens];               //  9,216 B per-symbol chain constants
-    uint4 stage[2][32];                                 //  1,024 B staged batch records
+    uint4 stage[kRing][32];                             //  2,048 B ring of staged batch records
+    uint32_t cap[kRing][32];                            //  pre-renormalisation state left by each step
+    uint32_t fring[kRing][32];                          //  frequencies of the symbols of each ring slot
+    uint32_t chain_warp, ticket, f_first;
     AnsCluster cl[kHfClusters];                         //  5,256 B
     uint32_t hist[kHfClusters * kHfTokens];             //  2,304 B
     uint32_t dbits[kDBitsWords];                        //  1,536 B
@@ -130,9 +142,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));   // read-only table: free to be scheduled early
     return v;
 }
 
@@ -146,6 +166,7 @@ k_ans_chain(Workspace ws) {
     uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
     uint16_t *__restrict__ fwords = ws.fwords + (size_t)tile * kMaxHfSyms;
 
+    const long long clk0 = clock64();
     // ---- 1. model ---------------------------------------------------------------------------
     for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kAnsThreads)
         s.hist[i] = ws.hist[(size_t)tile * kHfClusters * kHfTokens + i];
@@ -222,10 +243,33 @@ k_ans_chain(Workspace ws) {
         for (uint32_t i = tid; i < words && i < (uint32_t)kDBitsWords; i += kAnsThreads)
             ws.dbits[(size_t)tile * kDBitsWords + i] = s.dbits[i];
     }
-    if (warp != 0)
+    // Two warps stay: the CHAIN warp runs nothing but the state recurrence; a HELPER warp feeds it
+    // staged per-symbol records through a small shared-memory ring and drains the states it leaves
+    // behind (renormalisation flags / words).  Co-resident CTAs put their chain warps on different
+    // SM sub-partitions: each CTA takes the next ticket of its SM and picks the warp whose hardware
+    // slot (%warpid) lives in sub-partition ticket % 4.
+    if (tid == 0) {
+        uint32_t smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        s.chain_warp = 0xFFFFFFFFu;
+        s.ticket = atomicAdd(&ws.sm_ticket[smid & 255u], 1u) & 3u;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        uint32_t hw;
+        asm("mov.u32 %0, %%warpid;" : "=r"(hw));
+        if ((hw & 3u) == s.ticket)
+            atomicMin(&s.chain_warp, warp);
+    }
+    __syncthreads();
+    if (s.chain_warp == 0xFFFFFFFFu && tid == 0)
+        s.chain_warp = 0;
+    __syncthreads();
+    const uint32_t chain_warp = s.chain_warp, helper_warp = chain_warp ^ 1u;
+    if (warp != chain_warp && warp != helper_warp)
         return;   // the remaining warps have nothing to do while the chain runs
     if (!sane) {
-        if (lane == 0) {
+        if (warp == chain_warp && lane == 0) {
             ws.chain_out[tile * 4 + 0] = 0;
             ws.chain_out[tile * 4 + 1] = 0;
             ws.chain_out[tile * 4 + 2] = s.dbitlen;
@@ -235,53 +279,98 @@ k_ans_chain(Workspace ws) {
     }
 
     // ---- 3. the chain ------------------------------------------------------------------------------
-    {
-        const uint32_t FULL = 0xFFFFFFFFu;
-        const int nbatch = (int)((N + 31) >> 5);
-        const uint32_t inv_base = (uint32_t)__cvta_generic_to_shared(s.inv);
-        const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(s.stage);
-        auto lookup = [](uint32_t addr) -> uint32_t { return lds16(addr); };
+    // Batches of 32 symbols, last batch first; batch number `seq` uses ring slot seq % kRing.
+    //   FULL[slot]  : helper arrives after staging a batch, chain waits before coding it
+    //   EMPTY[slot] : chain arrives after coding it, helper waits before draining / restaging it
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int nbatch = (int)((N + 31) >> 5);
+    const uint32_t inv_base = (uint32_t)__cvta_generic_to_shared(s.inv);
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(s.stage);
+    const uint32_t cap_base = (uint32_t)__cvta_generic_to_shared(s.cap);
+    const long long clk1 = clock64();
+    if (warp == helper_warp) {
         auto load_sym = [&](int bi) -> uint32_t {
             const uint32_t p = (uint32_t)bi * 32u + lane;
             return (bi >= 0 && p < N) ? sy[p] : 0xFFFFFFFFu;
         };
         auto info_of = [&](uint32_t sym) -> uint4 {
             if (sym == 0xFFFFFFFFu)
-                return make_uint4(0u, 32u | (1u << 8), 0u, 0u);
+                return make_uint4(0u, 1u << 8, 0u, 0u);
             return s.info4[hf_cluster(sym) * kHfTokens + hf_token(sym)];
         };
-        // stage a batch: `inf` = this lane's constants, `inf_lo` = constants of the next lower batch
-        auto stage = [&](int par, const uint4 &inf, const uint4 &inf_lo, bool lowest) {
-            const uint32_t f = inf.y >> 8;
-            const uint32_t f_up = __shfl_up_sync(FULL, f, 1);
-            const uint32_t f_lo31 = __shfl_sync(FULL, inf_lo.y >> 8, 31);
-            const uint32_t f_next = lane ? f_up : (lowest ? kAnsNoNext : f_lo31);
-            s.stage[par][lane] = make_uint4(inf.x, (inf.y & 0xFFu) | (f_next << 8), inf.z, inf.w + inv_base);
-        };
-        uint4 inf_cur = info_of(load_sym(nbatch - 1));
-        uint4 inf_nxt = info_of(load_sym(nbatch - 2));
-        stage(0, inf_cur, inf_nxt, nbatch == 1);
-        // virtual step that "produced" the initial state 0x130000 = (0x130 << 12) | 0
-        uint32_t x, carry_flag, carry_word;
-        {
-            const uint32_t f_first = __shfl_sync(FULL, inf_cur.y >> 8, (N - 1) & 31);
-            carry_flag = ((kAnsInitState >> 20) >= f_first) ? 1u : 0u;
-            carry_word = kAnsInitState & 0xFFFFu;
-            x = carry_flag ? (kAnsInitState >> 16) : kAnsInitState;
-        }
-        uint32_t cnt = 0;
-        uint32_t lowest_flag = 0xFFFFFFFFu;   // position of the most recent (lowest) flagged symbol
-        uint32_t gap_err = 0;
-        int par = 0;
-        for (int bi = nbatch - 1; bi >= 0; --bi) {
-            __syncwarp();
-            const uint32_t sym_nn = load_sym(bi - 2);   // in flight while this batch is coded
+        uint32_t cnt = 0, lowest_flag = 0xFFFFFFFFu, gap_err = 0;
+        uint32_t carry_s = kAnsInitState;   // the virtual step in front of the last symbol left 0x130000
+        // drain batch `seq`: lane L owns symbol base + L; its flag / word come from the state left
+        // by step L + 1, or by the previous batch's step 0 for the top lane
+        auto drain = [&](int seq) {
+            const int slot = seq % kRing, bi = nbatch - 1 - seq;
             const uint32_t base = (uint32_t)bi * 32u;
             const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
-            const uint32_t stg = stage_base + (uint32_t)par * 32u * 16u;
-            uint32_t mask = carry_flag << jtop;
-            uint32_t myword = carry_word;
-            // a renormalisation found while coding symbol j belongs to symbol j - 1
+            const uint32_t capb = cap_base + (uint32_t)slot * 32u * 4u;
+            const uint32_t sprev = (int)lane >= jtop ? carry_s : lds32(capb + (lane + 1u) * 4u);
+            const bool flagged = (int)lane <= jtop && (sprev >> 20) >= s.fring[slot][lane];
+            const uint32_t mask = __ballot_sync(FULL, flagged);
+            carry_s = lds32(capb);
+            if (lane == 0)
+                flags[bi] = mask;
+            if (flagged) {
+                const uint32_t above = __popc(mask & ~((2u << lane) - 1u));
+                fwords[cnt + above] = (uint16_t)(sprev & 0xFFFFu);   // chain order = descending position
+            }
+            if (mask) {
+                const uint32_t hi = base + 31u - (uint32_t)__clz(mask), lo = base + (uint32_t)__ffs(mask) - 1u;
+                if (lowest_flag != 0xFFFFFFFFu && lowest_flag - hi >= 65536u)
+                    gap_err = 1;
+                lowest_flag = lo;
+            }
+            cnt += __popc(mask);
+        };
+        uint4 inf_cur = info_of(load_sym(nbatch - 1));
+        uint32_t sym_nxt = load_sym(nbatch - 2);
+        for (int seq = 0; seq < nbatch; seq++) {
+            const int slot = seq % kRing, bi = nbatch - 1 - seq;
+            const uint32_t sym_nn = load_sym(bi - 2);   // consumed one iteration later
+            const uint4 inf_nxt = info_of(sym_nxt);
+            if (seq >= kRing) {
+                bar_sync(kBarEmpty + slot, 64);
+                drain(seq - kRing);
+            }
+            // staged .y = (frequency of the symbol coded next) << 8 | shift  (see ans_step)
+            const uint32_t f = inf_cur.y >> 8;
+            const uint32_t f_up = __shfl_up_sync(FULL, f, 1);
+            const uint32_t f_lo31 = __shfl_sync(FULL, inf_nxt.y >> 8, 31);
+            const uint32_t f_next = lane ? f_up : (bi == 0 ? kAnsNoNext : f_lo31);
+            s.stage[slot][lane] = make_uint4(inf_cur.x, (inf_cur.y & 0xFFu) | (f_next << 8), inf_cur.z, inf_cur.w + inv_base);
+            s.fring[slot][lane] = f;
+            if (seq == 0)
+                s.f_first = __shfl_sync(FULL, f, (N - 1) & 31);
+            bar_arrive(kBarFull + slot, 64);
+            inf_cur = inf_nxt;
+            sym_nxt = sym_nn;
+        }
+        for (int seq = nbatch > kRing ? nbatch - kRing : 0; seq < nbatch; seq++) {
+            bar_sync(kBarEmpty + seq % kRing, 64);
+            drain(seq);
+        }
+        if (lowest_flag != 0xFFFFFFFFu && lowest_flag >= 65536u)
+            gap_err = 1;   // the reference keeps this distance in a uint16_t (entropy.c:16, 1094, 1123)
+        if (lane == 0) {
+            ws.chain_out[tile * 4 + 0] = cnt;
+            ws.chain_out[tile * 4 + 2] = s.dbitlen;
+            ws.chain_out[tile * 4 + 3] = gap_err ? (uint32_t)kErrAnsGap : 0u;
+        }
+    } else {
+        auto lookup = [](uint32_t addr) -> uint32_t { return lds16(addr); };
+        uint32_t x = 0;
+        for (int seq = 0; seq < nbatch; seq++) {
+            const int slot = seq % kRing, bi = nbatch - 1 - seq;
+            const uint32_t base = (uint32_t)bi * 32u;
+            const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
+            const uint32_t stg = stage_base + (uint32_t)slot * 32u * 16u, capb = cap_base + (uint32_t)slot * 32u * 4u;
+            bar_sync(kBarFull + slot, 64);
+            if (seq == 0)   // renormalise the initial state for the last symbol (entropy.c:1083, 1092-1100)
+                x = ((kAnsInitState >> 20) >= s.f_first) ? (kAnsInitState >> 16) : kAnsInitState;
+            // step j codes symbol j and leaves the pre-renormalisation state s'_j in cap[j]
             if (jtop == 31) {
                 uint4 r0 = lds128(stg + 31 * 16), r1 = lds128(stg + 30 * 16), r2 = lds128(stg + 29 * 16);
 #pragma unroll
@@ -291,58 +380,30 @@ k_ans_chain(Workspace ws) {
                     r1 = r2;
                     if (j >= 3)
                         r2 = lds128(stg + (uint32_t)(j - 3) * 16u);
-                    uint32_t p, word;
-                    ans_step(x, st.x, st.y, st.z, st.w, lookup, p, word);
-                    if (j > 0) {
-                        mask |= p << (j > 0 ? j - 1 : 0);
-                        myword = lane == (uint32_t)(j - 1) ? word : myword;
-                    } else {
-                        carry_flag = p;
-                        carry_word = word;
-                    }
+                    uint32_t sp;
+                    ans_step_state(x, st.x, st.y, st.z, st.w, lookup, sp);
+                    sts32(capb + (uint32_t)j * 4u, sp);
                 }
             } else {
                 for (int j = jtop; j >= 0; --j) {
                     const uint4 st = lds128(stg + (uint32_t)j * 16u);
-                    uint32_t p, word;
-                    ans_step(x, st.x, st.y, st.z, st.w, lookup, p, word);
-                    if (j > 0) {
-                        mask |= p << (j - 1);
-                        myword = lane == (uint32_t)(j - 1) ? word : myword;
-                    } else {
-                        carry_flag = p;
-                        carry_word = word;
-                    }
+                    uint32_t sp;
+                    ans_step_state(x, st.x, st.y, st.z, st.w, lookup, sp);
+                    sts32(capb + (uint32_t)j * 4u, sp);
                 }
             }
-            // record this batch's flags and words (words in chain order = descending position)
-            if (lane == 0)
-                flags[bi] = mask;
-            if ((mask >> lane) & 1u) {
-                const uint32_t above = __popc(mask & ~((2u << lane) - 1u));
-                fwords[cnt + above] = (uint16_t)myword;
-            }
-            if (mask) {
-                const uint32_t hi = base + 31u - (uint32_t)__clz(mask), lo = base + (uint32_t)__ffs(mask) - 1u;
-                if (lowest_flag != 0xFFFFFFFFu && lowest_flag - hi >= 65536u)
-                    gap_err = 1;
-                lowest_flag = lo;
-            }
-            cnt += __popc(mask);
-            // stage the next batch into the other buffer
-            inf_cur = inf_nxt;
-            inf_nxt = info_of(sym_nn);
-            par ^= 1;
-            if (bi > 0)
-                stage(par, inf_cur, inf_nxt, bi == 1);
+            bar_arrive(kBarEmpty + slot, 64);
         }
-        if (lowest_flag != 0xFFFFFFFFu && lowest_flag >= 65536u)
-            gap_err = 1;   // the reference keeps this distance in a uint16_t (entropy.c:16, 1094, 1123)
         if (lane == 0) {
-            ws.chain_out[tile * 4 + 0] = cnt;
             ws.chain_out[tile * 4 + 1] = x;
-            ws.chain_out[tile * 4 + 2] = s.dbitlen;
-            ws.chain_out[tile * 4 + 3] = gap_err ? (uint32_t)kErrAnsGap : 0u;
+            if (ws.dbg_clk) {   // stage-tap builds only: cycles spent in the prologue and in the chain
+                uint32_t smid;
+                asm("mov.u32 %0, %%smid;" : "=r"(smid));
+                ws.dbg_clk[tile * 4 + 0] = (uint32_t)(clk1 - clk0);
+                ws.dbg_clk[tile * 4 + 1] = (uint32_t)(clock64() - clk1);
+                ws.dbg_clk[tile * 4 + 2] = smid;
+                ws.dbg_clk[tile * 4 + 3] = chain_warp;
+            }
         }
     }
 }

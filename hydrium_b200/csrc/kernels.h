@@ -38,10 +38,12 @@ struct Workspace {
     uint32_t *frame_len;      // [T]
     uint64_t *out_off;        // [T+1] exclusive scan of frame_len (compaction offsets)
     uint32_t *tile_err;       // [T] TileError bits
+    uint32_t *sm_ticket;      // [256] per-SM ticket counter (spreads chain warps over sub-partitions)
     // optional stage taps for the parity tests (NULL in production)
     float *dbg_xyb, *dbg_dct; // [T][256][256][3]
     uint32_t *dbg_freqs;      // [T][9][64] normalised frequencies
     uint32_t *dbg_sect;       // [T][4] bit lengths of sections prefix(A+L+B), D, E, total
+    uint32_t *dbg_clk;        // [T][4] k_ans_chain: prologue cycles, chain cycles, SM id, chain warp
 };
 
 // Shape-constant sections cached in HBM: entry 0 is section A, entry 1 + s is section B of shape s.

@@ -14,7 +14,7 @@ from .encoder import HydriumError
 from .lib import HydbTile, load_library
 
 TAP_XYB, TAP_DCT, TAP_COEF, TAP_NZINFO, TAP_LFQ, TAP_SYMS, TAP_FREQS, TAP_LFBITS, TAP_SECT, TAP_PAYLOAD, \
-    TAP_NSYMS, TAP_LFBITLEN = range(12)
+    TAP_NSYMS, TAP_LFBITLEN, TAP_CLK = range(13)
 
 
 class Engine:

@@ -200,7 +200,8 @@ enum {
     HYDB_TAP_SECT = 8,     /* uint32 [4] section bit lengths       */
     HYDB_TAP_PAYLOAD = 9,  /* bytes: payload of the frame          */
     HYDB_TAP_NSYMS = 10,   /* uint32 [1]                           */
-    HYDB_TAP_LFBITLEN = 11 /* uint32 [1]                           */
+    HYDB_TAP_LFBITLEN = 11,/* uint32 [1]                           */
+    HYDB_TAP_CLK = 12      /* uint32 [4] chain kernel: prologue cycles, chain cycles, SM id, chain warp */
 };
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_enable_taps(HydbEngine *engine, int enable);
 HYDRIUM_EXPORT int64_t hydb_engine_read_tap(HydbEngine *engine, int what, uint32_t tile, void *dst, uint64_t cap);

@@ -142,35 +142,30 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
         *d_bitlen = bw.bitlen();
         if (bw.overflow) err |= kErrSlab;
     }
-    // chain, last symbol first
+    // chain, last symbol first, the way k_ans_chain runs it: every step yields the pre-renormalisation
+    // state s'; the flag / word of symbol p are derived from the s' of step p + 1 and f(p)
     std::vector<uint8_t> flag(n + 1, 0);
     std::vector<uint16_t> words;
-    uint32_t x;
-    {
-        // virtual "previous step" holding the initial state: q = state >> 12, slot = 0
-        const uint32_t q0 = kAnsInitState >> 12;
-        const uint32_t f_first = n ? asi_freq(info[hf_cluster(syms[n - 1])][hf_token(syms[n - 1])]) : kAnsNoNext;
-        const bool fl = (q0 >> 8) >= f_first;
-        if (fl) {
-            flag[n - 1] = 1;
-            words.push_back((uint16_t)(kAnsInitState & 0xFFFF));
-            x = q0 >> 4;
-        } else {
-            x = kAnsInitState;
-        }
-    }
-    for (uint32_t r = 0; r < n; r++) {
-        const uint32_t p = n - 1 - r;
-        const uint32_t c = hf_cluster(syms[p]), t = hf_token(syms[p]);
-        const uint32_t f_next = p ? asi_freq(info[hf_cluster(syms[p - 1])][hf_token(syms[p - 1])]) : kAnsNoNext;
-        uint32_t fl, word;
-        const AnsSymInfo &si = info[c][t];
+    uint32_t x = 0;
+    if (n) {
+        std::vector<uint32_t> sprime(n + 1, 0);
+        sprime[n] = kAnsInitState;   // the virtual step before the last symbol
+        auto freq_of = [&](uint32_t p) { return asi_freq(info[hf_cluster(syms[p])][hf_token(syms[p])]); };
+        x = ((kAnsInitState >> 20) >= freq_of(n - 1)) ? (kAnsInitState >> 16) : kAnsInitState;
         const uint8_t *inv_bytes = (const uint8_t *)&inv[0][0];
-        ans_step(x, si.m, (si.w1 & 0xFFu) | (f_next << 8), si.nf2, si.b2,
-                 [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; }, fl, word);
-        if (fl) {
-            flag[p - 1] = 1;
-            words.push_back((uint16_t)word);
+        for (uint32_t r = 0; r < n; r++) {
+            const uint32_t p = n - 1 - r;
+            const AnsSymInfo &si = info[hf_cluster(syms[p])][hf_token(syms[p])];
+            const uint32_t f_next = p ? freq_of(p - 1) : kAnsNoNext;
+            ans_step_state(x, si.m, (si.w1 & 0xFFu) | (f_next << 8), si.nf2, si.b2,
+                           [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; },
+                           sprime[p]);
+        }
+        for (uint32_t p = n; p-- > 0;) {   // descending, like the chain emits them
+            if ((sprime[p + 1] >> 20) >= freq_of(p)) {
+                flag[p] = 1;
+                words.push_back((uint16_t)(sprime[p + 1] & 0xFFFF));
+            }
         }
     }
     // forward emission: final state, then per symbol [word][residue]
