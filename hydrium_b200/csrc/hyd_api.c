@@ -17,6 +17,7 @@
  *   - with hydb_encoder_set_batch(n > 1) tiles are encoded n at a time; hyd_flush then returns
  *     HYD_OK with nothing written until a batch completes.
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -58,6 +59,19 @@ struct HYDEncoder {
     char errbuf[256];
 };
 
+/* One engine + staging set is kept alive across encoders (creating the CUDA workspace and the
+ * page-locked staging costs far more than encoding an image): hyd_encoder_destroy parks it here,
+ * the next encoder with the same device / batch takes it back.  Distinct encoders may live on
+ * different threads, hence the mutex. */
+static struct {
+    pthread_mutex_t lock;
+    int valid, device;
+    uint32_t batch;
+    HydbEngine *engine;
+    uint8_t *stage_host, *stage_dev, *out_dev;
+    HydbTile *tiles;
+} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
+
 static uint32_t env_u32(const char *name, uint32_t fallback) {
     const char *v = getenv(name);
     if (!v || !*v)
@@ -80,6 +94,23 @@ HYDRIUM_EXPORT HYDEncoder *hyd_encoder_new(void) { /* libhydrium.c:16-19 */
 }
 
 static void release_gpu(HYDEncoder *enc) {
+    if (enc->engine && enc->stage_host && enc->stage_dev && enc->out_dev && enc->tiles) {
+        pthread_mutex_lock(&g_parked.lock);
+        if (!g_parked.valid) {
+            g_parked.valid = 1;
+            g_parked.device = enc->device;
+            g_parked.batch = enc->batch;
+            g_parked.engine = enc->engine;
+            g_parked.stage_host = enc->stage_host;
+            g_parked.stage_dev = enc->stage_dev;
+            g_parked.out_dev = enc->out_dev;
+            g_parked.tiles = enc->tiles;
+            enc->engine = NULL;
+            enc->stage_host = enc->stage_dev = enc->out_dev = NULL;
+            enc->tiles = NULL;
+        }
+        pthread_mutex_unlock(&g_parked.lock);
+    }
     if (enc->stage_host) hydb_host_free(enc->stage_host);
     if (enc->stage_dev) hydb_device_free(enc->stage_dev);
     if (enc->out_dev) hydb_device_free(enc->out_dev);
@@ -244,6 +275,18 @@ static HYDStatusCode gpu_error(HYDEncoder *enc, HYDStatusCode rc) {
 }
 
 static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
+    if (enc->engine)
+        return HYD_OK;
+    pthread_mutex_lock(&g_parked.lock);
+    if (g_parked.valid && g_parked.device == enc->device && g_parked.batch == enc->batch) {
+        g_parked.valid = 0;
+        enc->engine = g_parked.engine;
+        enc->stage_host = g_parked.stage_host;
+        enc->stage_dev = g_parked.stage_dev;
+        enc->out_dev = g_parked.out_dev;
+        enc->tiles = g_parked.tiles;
+    }
+    pthread_mutex_unlock(&g_parked.lock);
     if (enc->engine)
         return HYD_OK;
     HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->batch);

@@ -25,7 +25,19 @@ namespace hydb {
 
 __constant__ uint8_t c_freq_ctx[64] = {HYDB_FREQ_CTX};
 
-constexpr int kTokThreads = 1024;
+constexpr int kTokThreads = 512;
+
+// nnz_context(left) % 3 for left = 0..63, two bits each (see tables.cuh: 0,0,31,62,62,93 x4,123 x4,152 x8,180 x12,206...)
+__device__ __forceinline__ uint32_t nnz_ctx_mod3(uint32_t left) {
+    // values mod 3: 0->0, 31->1, 62->2, 93->0, 123->0, 152->2, 180->0, 206->2
+    if (left < 2) return 0;
+    if (left < 3) return 1;
+    if (left < 5) return 2;
+    if (left < 13) return 0;
+    if (left < 21) return 2;
+    if (left < 33) return 0;
+    return 2;
+}
 
 __global__ void __launch_bounds__(kTokThreads)
 k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef, const uint16_t *__restrict__ nzinfo,
@@ -55,11 +67,12 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
     }
     __syncthreads();
 
-    // ---- exclusive scan of symbol counts: 3 consecutive entries per thread --------------------
-    uint32_t cnt[3], local = 0;
+    // ---- exclusive scan of symbol counts: 6 consecutive entries per thread --------------------
+    constexpr int kPer = 3 * kMaxBlocks / kTokThreads;
+    uint32_t cnt[kPer], local = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const uint32_t e = tid * 3 + k;
+    for (int k = 0; k < kPer; k++) {
+        const uint32_t e = tid * kPer + k;
         uint32_t c = 0;
         if (e < ne) {
             const uint32_t info = s_info[e];
@@ -79,7 +92,7 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
         s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = s_warp[lane], wi = w;
+        uint32_t w = lane < kTokThreads / 32 ? s_warp[lane] : 0, wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
@@ -94,8 +107,8 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
     {
         uint32_t run = s_warp[warp] + incl - local;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const uint32_t e = tid * 3 + k;
+        for (int k = 0; k < kPer; k++) {
+            const uint32_t e = tid * kPer + k;
             if (e < ne)
                 s_off[e] = run;
             run += cnt[k];
@@ -105,6 +118,8 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
 
     // ---- one warp per (block, channel) ---------------------------------------------------------
     uint32_t *out = syms + (size_t)tile * kMaxHfSyms;
+    const int16_t *tile_coef = coef + (size_t)tile * kMaxBlocks * 3 * 64;
+    const uint32_t fc3_lo = c_freq_ctx[lane] % 3u, fc3_hi = c_freq_ctx[lane + 32] % 3u;   // per-lane constants
     uint32_t my_resbits = 0, my_err = 0;
     for (uint32_t e = warp; e < ne; e += kTokThreads / 32) {
         const uint32_t blk = e / 3, i = e - blk * 3, c = i < 2 ? 1 - i : i;
@@ -121,13 +136,16 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
         }
         if (!nz)
             continue;
-        const int16_t *q = coef + (((size_t)tile * kMaxBlocks + by * kBlocksPerRow + bx) * 3 + c) * 64;
-        const int q_lo = q[lane], q_hi = q[lane + 32];
+        const int16_t *q = tile_coef + ((by * kBlocksPerRow + bx) * 3 + c) * 64;
+        const int q_lo = q[lane];
+        const int q_hi = last >= 32 ? q[lane + 32] : 0;   // warp-uniform: nothing to code up there
         const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, q_lo != 0);
-        const uint32_t m_hi = __ballot_sync(0xFFFFFFFFu, q_hi != 0);
+        const uint32_t m_hi = last >= 32 ? __ballot_sync(0xFFFFFFFFu, q_hi != 0) : 0u;
         const uint64_t mask = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
 #pragma unroll
         for (int half = 0; half < 2; half++) {
+            if (half && last < 32)
+                break;
             const uint32_t j = lane + 32 * half;
             const int qv = half ? q_hi : q_lo;
             const bool valid = j >= 1 && j <= last;
@@ -136,7 +154,7 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
                 const uint32_t below = __popcll(mask & ((1ull << j) - 1ull));
                 const uint32_t left = nz - below;
                 const uint32_t prev = j == 1 ? (nz <= 4 ? 1u : 0u) : (uint32_t)((mask >> (j - 1)) & 1ull);
-                const uint32_t cluster = 3 + prev + 2 * ((i + nnz_context(left) + c_freq_ctx[j]) % 3);
+                const uint32_t cluster = 3 + prev + 2 * ((i + nnz_ctx_mod3(left) + (half ? fc3_hi : fc3_lo)) % 3);
                 uint32_t res, nbits;
                 uint32_t tok = hybrid_token(pack_signed(qv), 4, 1, 0, res, nbits);
                 if (tok >= (uint32_t)kHfTokens) {
