@@ -32,7 +32,7 @@ constexpr int kAnsTotal = 4096;          // 12-bit ANS precision, reference: ent
 // ---- per-tile workspace sizes (bytes / elements) ----------------------------------------
 constexpr int kLfBitsWords = 4096;       // LF stream scratch (u32 words) per tile
 constexpr int kSlabBytes = 768 * 1024;   // worst-case frame: header + TOC + payload
-constexpr int kSlabHeaderReserve = 64;   // frame header + TOC are right-justified before this
+constexpr int kSlabHeaderReserve = 128;  // [image header] + frame header + TOC are right-justified before this
 constexpr int kDBitsWords = 384;         // section D (ANS header tail) scratch per tile
 constexpr int kTemplWords = 256;         // per-shape constant bit strings (u32 words each)
 
@@ -58,12 +58,14 @@ struct TileDesc {
     uint32_t x0, y0;          // pixel origin inside the image (frame crop)
     uint32_t flags;           // kTile* below
     uint32_t shape;           // index of the (vbw, vbh) template set
+    uint32_t image_w, image_h;   // only read when kTileFirst is set
 };
 enum : uint32_t {
     kTileLast = 1u << 0,      // is_last frame (reference: encoder.c:482-485)
     kTileCrop = 1u << 1,      // image larger than the tile (reference: encoder.c:340-342)
     kTileFmt16 = 1u << 2,     // HYD_UINT16 samples, else HYD_UINT8
     kTileLinear = 1u << 3,    // linear-light input
+    kTileFirst = 1u << 4,     // first frame of a codestream: the image header goes in front of it
 };
 
 // ---- integer helpers (reference: math-functions.h:8-88) ----------------------------------

@@ -269,7 +269,9 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
         d.x0 = s.x0;
         d.y0 = s.y0;
         d.shape = (uint32_t)shape;
-        d.flags = (s.is_last ? kTileLast : 0u) |
+        d.image_w = s.image_width;
+        d.image_h = s.image_height;
+        d.flags = (s.is_last ? kTileLast : 0u) | (s.with_image_header ? kTileFirst : 0u) |
                   ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
                   (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.linear_light ? kTileLinear : 0u);
     }
@@ -352,20 +354,23 @@ HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     return HYD_OK;
 }
 
+// byte length of every frame of the last batch, in tile order (for callers that split a batch
+// into several codestreams, e.g. one per image)
+HYDStatusCode hydb_engine_frame_lengths(HydbEngine *eng, uint32_t *dst, uint32_t n) {
+    if (!eng || !dst || n > eng->last_n)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaStreamSynchronize(eng->st));
+    CK(cudaMemcpy(dst, eng->ws.frame_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return HYD_OK;
+}
+
 int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap) {
-    // reference: encoder.c:23-30 (level-10 container prefix), libhydrium.c:67-68 (when it applies)
-    static const uint8_t kLevel10[49] = {
-        0, 0, 0, 0x0c, 'J', 'X', 'L', ' ', 0x0d, 0x0a, 0x87, 0x0a, 0, 0, 0, 0x14, 'f', 't', 'y', 'p',
-        'j', 'x', 'l', ' ', 0, 0, 0, 0, 'j', 'x', 'l', ' ', 0, 0, 0, 9, 'j', 'x', 'l', 'l', 0x0a,
-        0, 0, 0, 0, 'j', 'x', 'l', 'c',
-    };
     uint64_t n = 0;
-    const uint64_t w64 = width, h64 = height;
-    if (w64 > (1u << 20) || h64 > (1u << 20) || w64 * h64 > (1u << 28)) {
-        if (cap < sizeof(kLevel10))
+    if (image_needs_level10(width, height)) {
+        if (cap < 49)
             return HYD_API_ERROR;
-        memcpy(dst, kLevel10, sizeof(kLevel10));
-        n = sizeof(kLevel10);
+        n = put_level10_prefix(dst);
     }
     uint32_t words[8] = {0};
     BitSink bw;
@@ -398,17 +403,6 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
     }
     CK(cudaSetDevice(eng->device));
     uint64_t pos = 0;
-    if (with_header) {
-        uint8_t hdr[64];
-        const int64_t hb = hydb_image_header(width, height, hdr, sizeof(hdr));
-        if (hb < 0 || (uint64_t)hb > d_out_cap) {
-            eng->error = "device output buffer too small";
-            return HYD_NEED_MORE_OUTPUT;
-        }
-        CK(cudaMemcpyAsync(d_out, hdr, (size_t)hb, cudaMemcpyHostToDevice, eng->st));
-        CK(cudaStreamSynchronize(eng->st));
-        pos = (uint64_t)hb;
-    }
     const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
     const uint64_t ntiles = (uint64_t)tiles_x * (tile_row_end - tile_row_begin);
     std::vector<HydbTile> batch;
@@ -437,6 +431,7 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
             t.is_last = (tx + 1 == tiles_x && ty + 1 == tiles_y) ? 1 : 0;   // encoder.c:482-485
             t.sample_fmt = sample_fmt;
             t.linear_light = linear_light;
+            t.with_image_header = (with_header && idx == 0) ? 1 : 0;
             batch.push_back(t);
         }
         HYDStatusCode rc = hydb_engine_encode_tiles(eng, batch.data(), n, d_out, d_out_cap, pos);

@@ -30,6 +30,19 @@ HDN inline void put_image_header(BitSink &bw, uint32_t width, uint32_t height) {
     bw.align_byte();
 }
 
+// level-10 container prefix (encoder.c:23-30), emitted when libhydrium.c:67-68 says so
+HD bool image_needs_level10(uint64_t w, uint64_t h) { return w > (1u << 20) || h > (1u << 20) || w * h > (1u << 28); }
+HDN inline uint32_t put_level10_prefix(uint8_t *dst) {
+    const uint8_t k[49] = {
+        0, 0, 0, 0x0c, 'J', 'X', 'L', ' ', 0x0d, 0x0a, 0x87, 0x0a, 0, 0, 0, 0x14, 'f', 't', 'y', 'p',
+        'j', 'x', 'l', ' ', 0, 0, 0, 0, 'j', 'x', 'l', ' ', 0, 0, 0, 9, 'j', 'x', 'l', 'l', 0x0a,
+        0, 0, 0, 0, 'j', 'x', 'l', 'c',
+    };
+    for (int i = 0; i < 49; i++)
+        dst[i] = k[i];
+    return 49;
+}
+
 // Frame header of one 256x256-group frame, byte aligned at both ends.
 HDN inline void put_frame_header(BitSink &bw, bool crop, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool last) {
     const U32Dist kFrameSize = {{0, 256, 2304, 18688}, {8, 11, 14, 30}};   // encoder.c:102-105

@@ -412,17 +412,6 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     /* encoder.c:482-485 */
     enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span >= W && ((uint64_t)tile_y + 1) * span >= H) : !!is_last;
 
-    if (!enc->wrote_header) { /* encoder.c:490-494: image header precedes the first frame */
-        rc = pend_reserve(enc, 64);
-        if (rc < HYD_ERROR_START)
-            return rc;
-        const int64_t hb = hydb_image_header((uint32_t)W, (uint32_t)H, enc->pend + enc->pend_len, 64);
-        if (hb < 0)
-            return HYD_INTERNAL_ERROR;
-        enc->pend_len += (size_t)hb;
-        enc->wrote_header = 1;
-    }
-
     HydbTile *t = &enc->tiles[enc->queued];
     memset(t, 0, sizeof(*t));
     t->width = tw;
@@ -434,6 +423,8 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     t->is_last = enc->one_frame || enc->last_tile; /* encoder.c:339 */
     t->sample_fmt = sample_fmt;
     t->linear_light = enc->metadata.linear_light != 0;
+    t->with_image_header = !enc->wrote_header; /* encoder.c:490-494: the image header precedes the first frame */
+    enc->wrote_header = 1;
     stage_tile(enc, t, buffer, row_stride, pixel_stride, sample_fmt == HYD_UINT8 ? 1 : 2);
     enc->queued++;
 

@@ -544,20 +544,33 @@ k_ans_pack(Workspace ws, Templates tp) {
         uint32_t flen = 0, foff = kSlabHeaderReserve;
         if (fits && !err) {
             const uint32_t payload_bytes = (total_bits + 7) >> 3;
+            uint8_t hb[kSlabHeaderReserve];
+            uint32_t n = 0;
             uint32_t hw[12];
             BitSink bw;
+            if (t.flags & kTileFirst) {   // image header in front of the codestream's first frame
+                if (image_needs_level10(t.image_w, t.image_h))
+                    n += put_level10_prefix(hb);
+                bw.init(hw, 12);
+                put_image_header(bw, t.image_w, t.image_h);
+                bw.flush_partial();
+                for (uint32_t i = 0; i < (bw.bitlen() >> 3); i++)
+                    hb[n++] = (uint8_t)(hw[i >> 2] >> (8 * (i & 3)));
+            }
             bw.init(hw, 12);
             put_frame_header(bw, (t.flags & kTileCrop) != 0, t.x0, t.y0, t.w, t.h, (t.flags & kTileLast) != 0);
             const bool ok = put_toc_entry(bw, payload_bytes);
             bw.flush_partial();
-            const uint32_t hb = bw.bitlen() >> 3;
-            if (!ok || bw.overflow || hb > (uint32_t)kSlabHeaderReserve) {
+            const uint32_t fb = bw.bitlen() >> 3;
+            if (!ok || bw.overflow || n + fb > (uint32_t)kSlabHeaderReserve) {
                 err |= kErrSlab;
             } else {
-                foff = kSlabHeaderReserve - hb;
-                for (uint32_t i = 0; i < hb; i++)
-                    slab[foff + i] = (uint8_t)(hw[i >> 2] >> (8 * (i & 3)));
-                flen = hb + payload_bytes;
+                for (uint32_t i = 0; i < fb; i++)
+                    hb[n++] = (uint8_t)(hw[i >> 2] >> (8 * (i & 3)));
+                foff = kSlabHeaderReserve - n;
+                for (uint32_t i = 0; i < n; i++)
+                    slab[foff + i] = hb[i];
+                flen = n + payload_bytes;
             }
         }
         ws.frame_off[tile] = foff;

@@ -135,6 +135,50 @@ class Engine:
         self._check(self.lib.hydb_engine_finish(self._h, C.byref(n)))
         return int(n.value)
 
+    def encode_image_batch(self, d_images: int, count: int, width: int, height: int, channels: int = 3, *,
+                           sample_fmt: int = HYD_UINT8, linear_light: int = 0, d_out: int, d_out_cap: int):
+        """`count` independent images of the same size, stored back to back in device memory, each
+        its own codestream (BASELINE config 4: a batch of frames).  Tiles of different images share
+        GPU launches.  Returns a list of (offset, length) into d_out, one complete codestream each
+        (image header + frames)."""
+        item = 1 if sample_fmt == HYD_UINT8 else 2
+        ntx, nty = (width + 255) // 256, (height + 255) // 256
+        per_image = ntx * nty
+        spans, pos = [], 0
+        img_bytes = width * height * channels * item
+        imgs_per_launch = max(1, self.max_batch // per_image)
+        if per_image > self.max_batch:
+            raise ValueError("image has more tiles than the engine batch; use encode_image_device per image")
+        for first in range(0, count, imgs_per_launch):
+            group = range(first, min(count, first + imgs_per_launch))
+            tiles = []
+            for k in group:
+                base = d_images + k * img_bytes
+                for ty in range(nty):
+                    for tx in range(ntx):
+                        t = HydbTile()
+                        p = base + (ty * 256 * width + tx * 256) * channels * item
+                        t.plane = (C.c_void_p * 3)(p, p + item, p + 2 * item)
+                        t.row_stride, t.pixel_stride = width * channels, channels
+                        t.x0, t.y0 = tx * 256, ty * 256
+                        t.width, t.height = min(256, width - tx * 256), min(256, height - ty * 256)
+                        t.image_width, t.image_height = width, height
+                        t.is_last = int(tx == ntx - 1 and ty == nty - 1)
+                        t.sample_fmt, t.linear_light = sample_fmt, linear_light
+                        t.with_image_header = int(tx == 0 and ty == 0)
+                        tiles.append(t)
+            arr = (HydbTile * len(tiles))(*tiles)
+            self._check(self.lib.hydb_engine_encode_tiles(self._h, arr, len(tiles), d_out, d_out_cap, pos))
+            n = C.c_uint64(0)
+            self._check(self.lib.hydb_engine_finish(self._h, C.byref(n)))
+            lens = np.zeros(len(tiles), np.uint32)
+            self._check(self.lib.hydb_engine_frame_lengths(self._h, lens.ctypes.data, len(tiles)))
+            for gi, _ in enumerate(group):
+                size = int(lens[gi * per_image:(gi + 1) * per_image].sum())
+                spans.append((pos, size))
+                pos += size
+        return spans
+
     def synth_fill(self, d_dst: int, width: int, height: int, *, bits: int = 8, seed: int = 0, smooth: bool = False,
                    x0: int = 0, y0: int = 0, full_width: int | None = None, full_height: int | None = None) -> None:
         self._check(self.lib.hydb_synth_fill(self._h, d_dst, width, height, x0, y0,

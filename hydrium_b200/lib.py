@@ -21,7 +21,7 @@ HYDB_SYMBOLS = (
     "hydb_engine_encode_tiles", "hydb_engine_finish", "hydb_encode_image_device", "hydb_encode_image_host",
     "hydb_image_header", "hydb_host_alloc", "hydb_host_free", "hydb_device_alloc", "hydb_device_free",
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
-    "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms",
+    "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
 )
 
 
@@ -30,7 +30,7 @@ class HydbTile(C.Structure):
         ("plane", C.c_void_p * 3), ("row_stride", C.c_int64), ("pixel_stride", C.c_int64),
         ("width", C.c_uint32), ("height", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32),
         ("image_width", C.c_uint32), ("image_height", C.c_uint32), ("is_last", C.c_int32),
-        ("sample_fmt", C.c_int32), ("linear_light", C.c_int32), ("reserved", C.c_int32),
+        ("sample_fmt", C.c_int32), ("linear_light", C.c_int32), ("with_image_header", C.c_int32),
     ]
 
 
@@ -98,6 +98,8 @@ def load_library() -> C.CDLL:
     lib.hydb_engine_enable_taps.argtypes = [vp, C.c_int]
     lib.hydb_engine_read_tap.restype = i64
     lib.hydb_engine_read_tap.argtypes = [vp, C.c_int, u32, vp, u64]
+    lib.hydb_engine_frame_lengths.restype = C.c_int
+    lib.hydb_engine_frame_lengths.argtypes = [vp, vp, u32]
     lib.hydb_engine_enable_timing.restype = C.c_int
     lib.hydb_engine_enable_timing.argtypes = [vp, C.c_int]
     lib.hydb_engine_stage_ms.restype = C.c_int

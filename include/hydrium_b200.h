@@ -125,7 +125,7 @@ typedef struct HydbTile {
     int32_t is_last;         /* 0 / 1 */
     int32_t sample_fmt;      /* HYD_UINT8 / HYD_UINT16 */
     int32_t linear_light;
-    int32_t reserved;
+    int32_t with_image_header; /* 1: this tile starts a codestream, emit the image header before its frame */
 } HydbTile;
 
 /* max_batch_tiles bounds the tiles per hydb_engine_encode_tiles call (workspace ~2.4 MB / tile). */
@@ -145,6 +145,10 @@ HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_tiles(HydbEngine *engine, const 
                                                       uint8_t *d_out, uint64_t d_out_cap, uint64_t d_out_pos);
 /* Synchronise, check per-tile error flags of the last batch, return total bytes appended by it. */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_finish(HydbEngine *engine, uint64_t *batch_bytes);
+
+/* Byte length of each frame of the last batch, in tile order (to split one batch into several
+ * codestreams, e.g. one per image of a batch of frames). */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_frame_lengths(HydbEngine *engine, uint32_t *dst, uint32_t n);
 
 /* Whole image, tile mode shift 0/0, raster tile order restricted to tile rows
  * [tile_row_begin, tile_row_end): d_pixels points at the first sample of tile row tile_row_begin

@@ -288,3 +288,126 @@ def test_config2_full_size(product_lib, oracle):
         assert b"".join(parts) == full
         eng.device_free(d_in)
         eng.device_free(d_out)
+
+
+def test_lf_stream_stress(engine, oracle):
+    """Blocky images (constant 8x8 blocks) drive the LF path hard: long runs, many distinct
+    residual tokens, skewed histograms that hit the depth limiter of the code-length builder."""
+    rng = np.random.default_rng(17)
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    cases = []
+    for kind in range(8):
+        bw_, bh_ = int(rng.integers(1, 33)), int(rng.integers(1, 33))
+        if kind == 0:
+            lv = rng.integers(0, 256, (bh_, bw_, 3))
+        elif kind == 1:
+            lv = np.repeat(rng.integers(0, 256, (bh_, 1, 3)), bw_, axis=1)          # constant rows: long runs
+        elif kind == 2:
+            lv = rng.choice([0, 255], (bh_, bw_, 3))
+        elif kind == 3:
+            lv = (rng.geometric(0.08, (bh_, bw_, 3)) - 1).clip(0, 255)
+        elif kind == 4:   # Fibonacci-distributed levels
+            pool = np.concatenate([np.full(min(f, 300), (i * 11) % 256) for i, f in enumerate(fib)])
+            lv = rng.choice(pool, (32, 32, 3))
+        elif kind == 5:
+            lv = np.zeros((32, 32, 3), np.int64)
+            lv[::5, ::3] = 200
+        elif kind == 6:
+            lv = np.cumsum(rng.integers(-3, 4, (32, 32, 3)), axis=1).clip(0, 255) + 100
+        else:
+            lv = np.tile(np.arange(32)[None, :, None] * 8, (32, 1, 3))
+        img = np.repeat(np.repeat(lv.astype(np.uint8 if kind != 6 else np.uint16), 8, axis=0), 8, axis=1)
+        if img.dtype == np.uint16:
+            img = (img.astype(np.uint32) * 200).clip(0, 65535).astype(np.uint16)
+        cases.append(np.ascontiguousarray(img))
+    for i, img in enumerate(cases):
+        lin = int(img.dtype == np.uint16)
+        assert engine.encode_image(img, linear_light=lin) == oracle.encode_image(img, linear_light=lin), i
+
+
+def test_config3_slice_16bit_linear(product_lib, oracle):
+    """BASELINE configs[2] in miniature: 16-bit linear RGB, packed (stride 3) and RGBA (stride 4,
+    the CLI's layout), several tile rows, sharded into bands like the 8-GPU run."""
+    w, h = 1024, 768
+    img = synth_image(w, h, 16, seed=4)
+    want = oracle.encode_image(img, linear_light=1)
+    with E.Engine(device=0, max_batch_tiles=5) as eng:
+        assert eng.encode_image(img, linear_light=1) == want
+        rgba = np.zeros((h, w, 4), np.uint16)
+        rgba[:, :, :3] = img
+        assert eng.encode_image(rgba, linear_light=1) == want
+        d_in = eng.upload(img)
+        cap = E.output_bound(w, h)
+        d_out = eng.device_alloc(cap)
+        parts = []
+        for r in range(3):
+            band = d_in + r * 256 * w * 3 * 2
+            n = eng.encode_image_device(band, w, h, 3, sample_fmt=HYD_UINT16, linear_light=1, tile_rows=(r, r + 1),
+                                        with_header=(r == 0), d_out=d_out, d_out_cap=cap)
+            parts.append(eng.download(d_out, n))
+        assert b"".join(parts) == want
+        eng.device_free(d_in)
+        eng.device_free(d_out)
+
+
+def test_config4_batch_of_frames(product_lib, oracle):
+    """BASELINE configs[3] in miniature: independent 1920x1080 frames (8 x 5 tiles, partial right
+    column and bottom row), each its own codestream, tiles of different frames sharing launches."""
+    w, h, count = 1920, 1080, 5
+    frames = [synth_image(w, h, 8, seed=100 + k) for k in range(count)]
+    want = [oracle.encode_image(f) for f in frames]
+    with E.Engine(device=0, max_batch_tiles=96) as eng:
+        d_in = eng.upload(np.stack(frames))
+        cap = count * E.output_bound(w, h)
+        d_out = eng.device_alloc(cap)
+        spans = eng.encode_image_batch(d_in, count, w, h, 3, d_out=d_out, d_out_cap=cap)
+        assert len(spans) == count
+        for k, (off, n) in enumerate(spans):
+            assert eng.download(d_out + off, n) == want[k], k
+        eng.device_free(d_in)
+        eng.device_free(d_out)
+    # the same through one nine-symbol encoder per frame (engine is parked and reused between them)
+    import os
+    os.environ["HYDRIUM_B200_BATCH"] = "40"
+    try:
+        for k in range(2):
+            assert encode_cli_loop(product_lib, frames[k]) == want[k]
+    finally:
+        del os.environ["HYDRIUM_B200_BATCH"]
+
+
+def test_config5_streaming_window(product_lib, oracle):
+    """BASELINE configs[4] in miniature: a band of the 65536x65536 image generated on the device and
+    streamed through the engine in several launches; level-10 container header on the first tile."""
+    iw = ih = 65536
+    ntx = 6
+    with E.Engine(device=0, max_batch_tiles=4) as eng:
+        band_w = ntx * 256
+        d_in = eng.device_alloc(band_w * 256 * 3)
+        eng.synth_fill(d_in, band_w, 256, bits=8, x0=0, y0=0, full_width=iw, full_height=ih)
+        tiles = []
+        for tx in range(ntx):
+            t = HydbTile()
+            p = d_in + tx * 256 * 3
+            t.plane = (C.c_void_p * 3)(p, p + 1, p + 2)
+            t.row_stride, t.pixel_stride = band_w * 3, 3
+            t.x0, t.y0, t.width, t.height = tx * 256, 0, 256, 256
+            t.image_width, t.image_height = iw, ih
+            t.sample_fmt, t.linear_light, t.is_last = HYD_UINT8, 0, 0
+            t.with_image_header = int(tx == 0)
+            tiles.append(t)
+        cap = 8 << 20
+        d_out = eng.device_alloc(cap)
+        pos = 0
+        for i in range(0, ntx, 4):
+            pos += eng.encode_tiles(tiles[i:i + 4], d_out, cap, pos)
+        got = eng.download(d_out, pos)
+        win = synth_image(band_w, 256, 8, full_width=iw, full_height=ih)
+        want = oracle.image_header(iw, ih)
+        for tx in range(ntx):
+            want += oracle.encode_tile(np.ascontiguousarray(win[:, tx * 256:(tx + 1) * 256]), tx, 0, image_size=(iw, ih), window=True)
+        assert got == want
+        eng.device_free(d_in)
+        eng.device_free(d_out)
