@@ -45,6 +45,12 @@ struct HydbEngine {
     uint64_t launches = 0;
     std::string error;
     std::vector<TileDesc> h_tiles;
+    // band pipeline of the host path: H2D of band k+1 overlaps the kernels of band k
+    static constexpr int kBands = 4;
+    cudaStream_t band_st[kBands] = {nullptr, nullptr, nullptr, nullptr}, band_st2[kBands] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t band_front[kBands] = {nullptr, nullptr, nullptr, nullptr}, band_lf[kBands] = {nullptr, nullptr, nullptr, nullptr},
+                band_done[kBands] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_desc = nullptr;
     // grow-only device buffers behind hydb_encode_image_host
     void *host_in = nullptr;
     uint8_t *host_out = nullptr;
@@ -112,6 +118,14 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(cudaStreamCreateWithFlags(&eng->st2, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&eng->ev_front, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&eng->ev_lf, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&eng->ev_desc, cudaEventDisableTiming));
+    for (int b = 0; b < HydbEngine::kBands; b++) {
+        A(cudaStreamCreateWithFlags(&eng->band_st[b], cudaStreamNonBlocking));
+        A(cudaStreamCreateWithFlags(&eng->band_st2[b], cudaStreamNonBlocking));
+        A(cudaEventCreateWithFlags(&eng->band_front[b], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&eng->band_lf[b], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&eng->band_done[b], cudaEventDisableTiming));
+    }
     A(dalloc(&w.tiles, T));
     A(dalloc(&w.coef, T * kMaxBlocks * 3 * 64));
     A(dalloc(&w.nzinfo, T * kMaxBlocks * 3));
@@ -180,6 +194,14 @@ void hydb_engine_destroy(HydbEngine *eng) {
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
     for (void *p : dev)
         if (p) cudaFree(p);
+    for (int b = 0; b < HydbEngine::kBands; b++) {
+        if (eng->band_st[b]) cudaStreamDestroy(eng->band_st[b]);
+        if (eng->band_st2[b]) cudaStreamDestroy(eng->band_st2[b]);
+        if (eng->band_front[b]) cudaEventDestroy(eng->band_front[b]);
+        if (eng->band_lf[b]) cudaEventDestroy(eng->band_lf[b]);
+        if (eng->band_done[b]) cudaEventDestroy(eng->band_done[b]);
+    }
+    if (eng->ev_desc) cudaEventDestroy(eng->ev_desc);
     if (eng->host_in) cudaFree(eng->host_in);
     if (eng->host_out) cudaFree(eng->host_out);
     for (cudaEvent_t ev : eng->tev) if (ev) cudaEventDestroy(ev);
@@ -236,13 +258,38 @@ static int shape_of(HydbEngine *eng, uint32_t vbw, uint32_t vbh, std::vector<uin
     return (int)eng->shapes.size() - 1;
 }
 
-HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, uint8_t *d_out,
-                                       uint64_t d_out_cap, uint64_t d_out_pos) {
-    if (!eng || !tiles || !n || n > eng->max_batch || !d_out) {
-        if (eng) eng->error = "invalid arguments to hydb_engine_encode_tiles";
-        return HYD_API_ERROR;
-    }
-    CK(cudaSetDevice(eng->device));
+// workspace seen by a sub-range of the batch starting at tile `first` (all arrays are [tile][...])
+static Workspace ws_view(const Workspace &w, uint32_t first) {
+    Workspace v = w;
+    const size_t f = first;
+    v.tiles += f;
+    v.coef += f * kMaxBlocks * 3 * 64;
+    v.nzinfo += f * kMaxBlocks * 3;
+    v.lfq += f * 3 * kMaxBlocks;
+    v.syms += f * kMaxHfSyms;
+    v.nsyms += f;
+    v.resbits += f;
+    v.hist += f * kHfClusters * kHfTokens;
+    v.lfbits += f * kLfBitsWords;
+    v.lfbitlen += f;
+    v.dbits += f * kDBitsWords;
+    v.chain_out += f * 4;
+    v.flags += f * (kMaxHfSyms / 32);
+    v.fwords += f * kMaxHfSyms;
+    v.slab += f * kSlabBytes;
+    v.frame_off += f;
+    v.frame_len += f;
+    v.tile_err += f;
+    if (v.dbg_xyb) v.dbg_xyb += f * 65536 * 3;
+    if (v.dbg_dct) v.dbg_dct += f * 65536 * 3;
+    if (v.dbg_freqs) v.dbg_freqs += f * kHfClusters * kHfTokens;
+    if (v.dbg_sect) v.dbg_sect += f * 4;
+    if (v.dbg_clk) v.dbg_clk += f * 4;
+    return v;
+}
+
+// validate + translate the caller's tiles, build templates for new shapes, upload the descriptors
+static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, cudaStream_t st) {
     std::vector<uint32_t> fresh;
     const uint32_t first_fresh = (uint32_t)eng->shapes.size();
     eng->h_tiles.resize(n);
@@ -275,7 +322,6 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
                   ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
                   (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.linear_light ? kTileLinear : 0u);
     }
-    cudaStream_t st = eng->st;
     if (!fresh.empty()) {
         std::vector<uint32_t> dims;
         for (uint32_t k : fresh) {
@@ -291,6 +337,34 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     CK(cudaMemcpyAsync(eng->ws.tiles, eng->h_tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(eng->ws.tile_err, 0, n * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(eng->d_overflow, 0, sizeof(uint32_t), st));
+    return HYD_OK;
+}
+
+// queue the result read-back of a batch of n tiles whose frames were gathered at d_out_pos
+static HYDStatusCode queue_readback(HydbEngine *eng, uint32_t n, uint64_t d_out_pos) {
+    cudaStream_t st = eng->st;
+    CK(cudaMemcpyAsync(eng->h_err, eng->ws.tile_err, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(eng->h_err + eng->max_batch, eng->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(eng->h_total, eng->ws.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    eng->last_n = n;
+    eng->last_base = d_out_pos;
+    return HYD_OK;
+}
+
+HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, uint8_t *d_out,
+                                       uint64_t d_out_cap, uint64_t d_out_pos) {
+    if (!eng || !tiles || !n || n > eng->max_batch || !d_out) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_encode_tiles";
+        return HYD_API_ERROR;
+    }
+    CK(cudaSetDevice(eng->device));
+    cudaStream_t st = eng->st;
+    {
+        const HYDStatusCode rc = prepare_tiles(eng, tiles, n, st);
+        if (rc != HYD_OK)
+            return rc;
+    }
     const bool tm = eng->timing;
     if (tm) CK(cudaEventRecord(eng->tev[0], st));
     launch_xyb_dct_quant(eng->ws, eng->luts, n, st);
@@ -312,13 +386,7 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     if (tm) CK(cudaEventRecord(eng->tev[5], st));
     eng->timed_pending = tm;
     eng->launches += 7;
-    CK(cudaMemcpyAsync(eng->h_err, eng->ws.tile_err, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(eng->h_err + eng->max_batch, eng->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(eng->h_total, eng->ws.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaGetLastError());
-    eng->last_n = n;
-    eng->last_base = d_out_pos;
-    return HYD_OK;
+    return queue_readback(eng, n, d_out_pos);
 }
 
 HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
@@ -385,6 +453,74 @@ int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_
     return (int64_t)(n + bytes);
 }
 
+// Whole-image tile list (raster order) for pixels at `base` (device memory).
+static void image_tiles(std::vector<HydbTile> &tiles, const void *base, uint32_t width, uint32_t height, uint32_t channels,
+                        int64_t row_stride, int sample_fmt, int linear_light, uint32_t row_begin, uint32_t row_end,
+                        int with_header) {
+    const uint32_t tiles_x = (width + 255) >> 8, tiles_y = (height + 255) >> 8;
+    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+    tiles.resize((size_t)tiles_x * (row_end - row_begin));
+    for (size_t idx = 0; idx < tiles.size(); idx++) {
+        const uint32_t tx = (uint32_t)(idx % tiles_x), ty = row_begin + (uint32_t)(idx / tiles_x);
+        HydbTile &t = tiles[idx];
+        memset(&t, 0, sizeof(t));
+        const uint8_t *p = (const uint8_t *)base +
+                           ((int64_t)(ty - row_begin) * 256 * row_stride + (int64_t)tx * 256 * channels) * (int64_t)item;
+        t.plane[0] = p;
+        t.plane[1] = p + item;
+        t.plane[2] = p + 2 * item;
+        t.row_stride = row_stride;
+        t.pixel_stride = channels;
+        t.x0 = tx * 256;
+        t.y0 = ty * 256;
+        t.width = width - t.x0 < 256 ? width - t.x0 : 256;
+        t.height = height - t.y0 < 256 ? height - t.y0 : 256;
+        t.image_width = width;
+        t.image_height = height;
+        t.is_last = (tx + 1 == tiles_x && ty + 1 == tiles_y) ? 1 : 0;   // encoder.c:482-485
+        t.sample_fmt = sample_fmt;
+        t.linear_light = linear_light;
+        t.with_image_header = (with_header && idx == 0) ? 1 : 0;
+    }
+}
+
+// Band pipeline for a batch that holds `rows` tile rows of `tiles_x` tiles (descriptors already
+// uploaded): the rows are cut into up to kBands bands, each with its own stream pair, so that the
+// rANS chains of early bands start while later bands are still in their front-end kernels (and,
+// on the host path, while their pixels are still crossing PCIe: `h_src` != NULL copies each
+// band's rows to `d_dst` on the band's stream first).  Frames are position- but not
+// order-dependent; the caller gathers all tiles afterwards on eng->st, which waits for every band.
+static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t rows, const void *h_src, void *d_dst,
+                                  size_t row_bytes, uint32_t pixel_rows) {
+    CK(cudaEventRecord(eng->ev_desc, eng->st));
+    const uint32_t nbands = rows < (uint32_t)HydbEngine::kBands ? rows : (uint32_t)HydbEngine::kBands;
+    for (uint32_t b = 0; b < nbands; b++) {
+        const uint32_t r0 = (uint32_t)((uint64_t)rows * b / nbands), r1 = (uint32_t)((uint64_t)rows * (b + 1) / nbands);
+        const uint32_t first = r0 * tiles_x, n = (r1 - r0) * tiles_x;
+        cudaStream_t sb = eng->band_st[b], sb2 = eng->band_st2[b];
+        CK(cudaStreamWaitEvent(sb, eng->ev_desc, 0));
+        if (h_src) {
+            const size_t y0 = (size_t)r0 * 256, y1 = (size_t)r1 * 256 < pixel_rows ? (size_t)r1 * 256 : pixel_rows;
+            CK(cudaMemcpyAsync((uint8_t *)d_dst + y0 * row_bytes, (const uint8_t *)h_src + y0 * row_bytes,
+                               (y1 - y0) * row_bytes, cudaMemcpyHostToDevice, sb));
+        }
+        const Workspace v = ws_view(eng->ws, first);
+        launch_xyb_dct_quant(v, eng->luts, n, sb);
+        CK(cudaEventRecord(eng->band_front[b], sb));
+        CK(cudaStreamWaitEvent(sb2, eng->band_front[b], 0));
+        launch_lf_group(v, n, sb2);
+        CK(cudaEventRecord(eng->band_lf[b], sb2));
+        launch_hf_tokens(v, n, sb);
+        launch_ans_chain(v, n, sb);
+        CK(cudaStreamWaitEvent(sb, eng->band_lf[b], 0));
+        launch_ans_pack(v, eng->templ, n, sb);
+        CK(cudaEventRecord(eng->band_done[b], sb));
+        CK(cudaStreamWaitEvent(eng->st, eng->band_done[b], 0));
+        eng->launches += 5;
+    }
+    return HYD_OK;
+}
+
 HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, uint32_t width, uint32_t height,
                                        uint32_t channels, int64_t row_stride, int sample_fmt, int linear_light,
                                        uint32_t tile_row_begin, uint32_t tile_row_end, int with_header, uint8_t *d_out,
@@ -403,38 +539,42 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
     }
     CK(cudaSetDevice(eng->device));
     uint64_t pos = 0;
-    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
     const uint64_t ntiles = (uint64_t)tiles_x * (tile_row_end - tile_row_begin);
-    std::vector<HydbTile> batch;
-    batch.reserve(eng->max_batch);
+    std::vector<HydbTile> tiles;
+    if (ntiles <= eng->max_batch && tile_row_end - tile_row_begin >= 2 && !eng->timing) {
+        // one batch: band-pipelined (see launch_bands); with per-kernel timing on, the plain
+        // single-stream sequence below is used so that the events bracket whole kernels
+        image_tiles(tiles, d_pixels, width, height, channels, row_stride, sample_fmt, linear_light, tile_row_begin,
+                    tile_row_end, with_header);
+        HYDStatusCode rc = prepare_tiles(eng, tiles.data(), (uint32_t)ntiles, eng->st);
+        if (rc == HYD_OK)
+            rc = launch_bands(eng, tiles_x, tile_row_end - tile_row_begin, nullptr, nullptr, 0, 0);
+        if (rc != HYD_OK)
+            return rc;
+        launch_gather(eng->ws, (uint32_t)ntiles, d_out, d_out_cap, 0, eng->d_overflow, eng->st);
+        eng->launches += 2;
+        rc = queue_readback(eng, (uint32_t)ntiles, 0);
+        if (rc != HYD_OK)
+            return rc;
+        uint64_t total = 0;
+        rc = hydb_engine_finish(eng, &total);
+        if (rc != HYD_OK)
+            return rc;
+        *out_len = total;
+        return HYD_OK;
+    }
     for (uint64_t first = 0; first < ntiles; first += eng->max_batch) {
         const uint32_t n = (uint32_t)((ntiles - first) < eng->max_batch ? (ntiles - first) : eng->max_batch);
-        batch.clear();
-        for (uint32_t k = 0; k < n; k++) {
-            const uint64_t idx = first + k;
-            const uint32_t tx = (uint32_t)(idx % tiles_x), ty = tile_row_begin + (uint32_t)(idx / tiles_x);
-            HydbTile t;
-            memset(&t, 0, sizeof(t));
-            const uint8_t *p = (const uint8_t *)d_pixels +
-                               ((int64_t)(ty - tile_row_begin) * 256 * row_stride + (int64_t)tx * 256 * channels) * (int64_t)item;
-            t.plane[0] = p;
-            t.plane[1] = p + item;
-            t.plane[2] = p + 2 * item;
-            t.row_stride = row_stride;
-            t.pixel_stride = channels;
-            t.x0 = tx * 256;
-            t.y0 = ty * 256;
-            t.width = width - t.x0 < 256 ? width - t.x0 : 256;
-            t.height = height - t.y0 < 256 ? height - t.y0 : 256;
-            t.image_width = width;
-            t.image_height = height;
-            t.is_last = (tx + 1 == tiles_x && ty + 1 == tiles_y) ? 1 : 0;   // encoder.c:482-485
-            t.sample_fmt = sample_fmt;
-            t.linear_light = linear_light;
-            t.with_image_header = (with_header && idx == 0) ? 1 : 0;
-            batch.push_back(t);
-        }
-        HYDStatusCode rc = hydb_engine_encode_tiles(eng, batch.data(), n, d_out, d_out_cap, pos);
+        const uint32_t r0 = tile_row_begin + (uint32_t)(first / tiles_x);
+        // batches are cut at arbitrary tiles: build the descriptors of whole rows and slice
+        const uint32_t r1 = tile_row_begin + (uint32_t)((first + n + tiles_x - 1) / tiles_x);
+        const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+        image_tiles(tiles, (const uint8_t *)d_pixels + (int64_t)(r0 - tile_row_begin) * 256 * row_stride * (int64_t)item, width,
+                    height, channels, row_stride, sample_fmt, linear_light, r0, r1, 0);
+        const size_t skip = (size_t)(first - (uint64_t)(r0 - tile_row_begin) * tiles_x);
+        if (with_header && first == 0)
+            tiles[0].with_image_header = 1;
+        HYDStatusCode rc = hydb_engine_encode_tiles(eng, tiles.data() + skip, n, d_out, d_out_cap, pos);
         if (rc < HYD_ERROR_START)
             return rc;
         uint64_t total = 0;
@@ -495,12 +635,39 @@ HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint
         rc = grow_device(eng, (void **)&eng->host_out, &eng->host_out_cap, (size_t)h_out_cap);
     if (rc != HYD_OK)
         return rc;
-    CK(cudaMemcpyAsync(eng->host_in, h_pixels, in_bytes, cudaMemcpyHostToDevice, eng->st));
-    rc = hydb_encode_image_device(eng, eng->host_in, width, height, channels, (int64_t)width * channels, sample_fmt,
-                                  linear_light, 0, (height + 255) >> 8, 1, eng->host_out, h_out_cap, out_len);
+    const uint32_t tiles_x = (width + 255) >> 8, tiles_y = (height + 255) >> 8;
+    const uint64_t ntiles = (uint64_t)tiles_x * tiles_y;
+    if (ntiles > eng->max_batch || tiles_y < 2) {
+        // several launches anyway: plain copy, then the device path
+        CK(cudaMemcpyAsync(eng->host_in, h_pixels, in_bytes, cudaMemcpyHostToDevice, eng->st));
+        rc = hydb_encode_image_device(eng, eng->host_in, width, height, channels, (int64_t)width * channels, sample_fmt,
+                                      linear_light, 0, tiles_y, 1, eng->host_out, h_out_cap, out_len);
+        if (rc != HYD_OK)
+            return rc;
+        CK(cudaMemcpyAsync(h_out, eng->host_out, *out_len, cudaMemcpyDeviceToHost, eng->st));
+        CK(cudaStreamSynchronize(eng->st));
+        return HYD_OK;
+    }
+    std::vector<HydbTile> tiles;
+    image_tiles(tiles, eng->host_in, width, height, channels, (int64_t)width * channels, sample_fmt, linear_light, 0,
+                tiles_y, 1);
+    rc = prepare_tiles(eng, tiles.data(), (uint32_t)ntiles, eng->st);
     if (rc != HYD_OK)
         return rc;
-    CK(cudaMemcpyAsync(h_out, eng->host_out, *out_len, cudaMemcpyDeviceToHost, eng->st));
+    rc = launch_bands(eng, tiles_x, tiles_y, h_pixels, eng->host_in, (size_t)width * channels * item, height);
+    if (rc != HYD_OK)
+        return rc;
+    launch_gather(eng->ws, (uint32_t)ntiles, eng->host_out, h_out_cap, 0, eng->d_overflow, eng->st);
+    eng->launches += 2;
+    rc = queue_readback(eng, (uint32_t)ntiles, 0);
+    if (rc != HYD_OK)
+        return rc;
+    uint64_t total = 0;
+    rc = hydb_engine_finish(eng, &total);
+    if (rc != HYD_OK)
+        return rc;
+    *out_len = total;
+    CK(cudaMemcpyAsync(h_out, eng->host_out, total, cudaMemcpyDeviceToHost, eng->st));
     CK(cudaStreamSynchronize(eng->st));
     return HYD_OK;
 }
