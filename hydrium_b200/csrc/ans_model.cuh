@@ -37,10 +37,12 @@ HDN inline int ans_normalise(uint32_t *f, uint32_t n) {
     if (!total)
         return -1;
     uint32_t sum = 0;
+    const bool narrow = total < (1ull << 20);   // then f << 12 fits 32 bits: avoid the slow 64-bit divide
     for (uint32_t k = 0; k < n; k++) {
         if (!f[k])
             continue;
-        uint32_t v = (uint32_t)((((uint64_t)f[k] << 12) / total) & 0xFFFFu);
+        uint32_t v = narrow ? (((f[k] << 12) / (uint32_t)total) & 0xFFFFu)
+                            : (uint32_t)((((uint64_t)f[k] << 12) / total) & 0xFFFFu);
         if (!v)
             v = 1;
         f[k] = v;

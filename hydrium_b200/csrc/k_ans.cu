@@ -205,14 +205,17 @@ k_ans_chain(Workspace ws) {
             if (single < 0 || !ans_build_alias(cl, &s.hist[c * kHfTokens], a, log_alpha, single > 0))
                 atomicOr(&s.err, (uint32_t)kErrAlias);
         }
-        for (uint32_t k = 0; k < (uint32_t)kHfTokens; k++) {
-            const AnsSymInfo si = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
-            s.info4[c * kHfTokens + k] = make_uint4(si.m, si.w1, si.nf2, si.b2);
-            if (ws.dbg_freqs)
-                ws.dbg_freqs[((size_t)tile * kHfClusters + c) * kHfTokens + k] = cl.freq[k];
-        }
     }
     __syncthreads();
+    // per-symbol chain constants (one 64-bit division each): all threads
+    for (uint32_t idx = tid; idx < kHfClusters * kHfTokens; idx += kAnsThreads) {
+        const uint32_t c = idx / kHfTokens, k = idx - c * kHfTokens;
+        const AnsCluster &cl = s.cl[c];
+        const AnsSymInfo si = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
+        s.info4[idx] = make_uint4(si.m, si.w1, si.nf2, si.b2);
+        if (ws.dbg_freqs)
+            ws.dbg_freqs[(size_t)tile * kHfClusters * kHfTokens + idx] = cl.freq[k];
+    }
     for (uint32_t idx = tid; idx < kHfClusters * kAnsTotal; idx += kAnsThreads) {
         const uint32_t c = idx >> 12, slot = idx & (kAnsTotal - 1);
         if (s.alpha[c]) {

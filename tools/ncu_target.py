@@ -13,6 +13,7 @@ with Engine(device=0, max_batch_tiles=256) as eng:
     cap = output_bound(W, H)
     d_out = eng.device_alloc(cap)
     eng.synth_fill(d_in, W, H, bits=8, seed=0)
+    eng.enable_timing(True)   # plain single-stream sequence: one launch of every kernel per image, as bench.py times them
     for _ in range(it):
         n = eng.encode_image_device(d_in, W, H, 3, d_out=d_out, d_out_cap=cap)
     print("bytes", n)
