@@ -1,16 +1,39 @@
 // hydrium_b200/csrc/ans_chain.cuh
 //
-// One step of the reverse rANS state chain (reference: entropy.c:1087-1120), arranged so that
-// the dependent path per symbol is  multiply-high -> shift -> multiply-subtract -> one shared
-// load -> one logic op:
+// One step of the reverse rANS state chain (reference: entropy.c:1087-1120), arranged so that the
+// only operations between two consecutive slot-table loads are ONE multiply-high and ONE
+// multiply-add.  The reference's step for a symbol with frequency f is
 //
-//   x        state after renormalisation for this symbol            (x < f * 2^20)
-//   q        = floor(x / f)                 (exact reciprocal, ans_model.cuh)
-//   slot     = inv[cum + (x - q*f)]         (inverse alias table)
-//   s'       = (q << 12) | slot             state after coding the symbol
-//   renormalise for the NEXT symbol iff (s' >> 20) >= f_next  <=>  (q >> 8) >= f_next,
-//   which does not wait for the table load; the emitted word is s' & 0xFFFF and the carried
-//   state is then s' >> 16 = q >> 4.
+//     x   state after renormalisation for this symbol                       (2^16 <= x < f * 2^20)
+//     q = x / f,  r = x % f,  slot = inv[base + r],  s' = (q << 12) | slot
+//     renormalise for the NEXT symbol iff (s' >> 20) >= f_next  <=>  q >= f_next << 8:
+//     the 16-bit word s' & 0xFFFF is emitted and the state becomes s' >> 16 = q >> 4.
+//
+// The state entering a step is x = a + v with
+//     a = q_prev << 12 (no renormalisation) or q_prev >> 4 (renormalised)    known BEFORE the previous
+//                                                                            step's table load returns
+//     v = slot_prev (no renormalisation) or 0                                the load result.
+// With mc = ceil(2^32 / f) and e = f * mc - 2^32 (0 <= e < f), x * mc / 2^32 over-estimates x / f by
+// x * e / (f * 2^32), which can reach 1.  Subtracting qa * e for ANY qa with 0 <= x - qa * f < 2^14
+// shrinks that error to (x - qa * f) * e / (f * 2^32) < 2^26 / (f * 2^32) < 1 / f, so
+//     q = hi32( x * mc - qa * e )        is exact.
+// While the previous load is in flight the "shadow" computes, for the coming symbol,
+//     w  = a * mc (64 bit),  qa = hi32(w) - 1        qa in {a/f - 1, a/f}, so x - qa * f < 2f + 4096
+//     R  = w - qa * e,       C0 = base2 + 2 * a
+// and once v arrives the dependent path is
+//     q    = hi32(v * mc + R)                                               multiply-high, 64-bit addend
+//     addr = C0 + 2 * v - 2 * f * q  = base2 + 2 * (x - q * f)              multiply-add -> next load
+// When the previous step renormalised, v must not count: the shadow replaces mc by 0 and the factor
+// 2 by 0, so the two path instructions are the same in both cases.
+// f = 1 has no 32-bit reciprocal: mc = 2^32 - 1 with e = -2 gives R = a * 2^32 + (a - 4) and
+// t = x * 2^32 + (a - 4 - v) with 0 <= a - 4 - v < 2^32, i.e. q = x exactly.  Power-of-two f >= 2
+// use mc = 2^32 / f, e = 0.  tests/test_host_logic.py checks the identity exhaustively at the range
+// boundaries and the whole formulation against the oracle.
+//
+// Why this shape: measured on B200 (tools/ubench), a single warp pays ~8 issue cycles per IMAD.WIDE,
+// ~6 per IMAD.HI, ~8 per LDS.128 and ~2.6 per IMAD, so the step is bound by instruction issue as
+// much as by latency; this form needs two wide multiplies, one multiply-high, two multiply-adds and
+// one 16-byte record per symbol.
 #pragma once
 
 #include "ans_model.cuh"
@@ -18,67 +41,91 @@
 namespace hydb {
 
 constexpr uint32_t kAnsInitState = 0x130000u;   // reference: entropy.c:1083
-
-// per (cluster, token) constants for the chain (16 bytes, one LDS.128)
+// per (cluster, token) constants for the chain: also the 16-byte record staged per symbol
 struct AnsSymInfo {
-    uint32_t m;     // reciprocal multiplier (ans_div_consts)
-    uint32_t w1;    // shift (0..12) in bits 0..7, frequency in bits 8..
-    uint32_t nf2;   // -2 * frequency (mod 2^32)
+    uint32_t mc;    // ceil(2^32 / f)   (2^32 - 1 for f = 1); 0 for an unused symbol
+    uint32_t ne;    // -e = 2^32 - f * mc (mod 2^32), a small non-positive signed value (+2 for f = 1)
+    uint32_t nf2;   // -2f (mod 2^32)
     uint32_t b2;    // byte offset of the symbol's first slot in the flat uint16 inverse table
 };
 // `base` = cluster * 4096 + cumulative frequency
 HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t base) {
     AnsSymInfo s;
-    s.m = 0;
-    s.w1 = 0u | (1u << 8);
-    s.nf2 = 0;
-    s.b2 = 0;
+    s.mc = s.ne = s.nf2 = s.b2 = 0;
     if (!f)
         return s;
-    uint32_t sh;
-    ans_div_consts(f, s.m, sh);
-    s.w1 = sh | (f << 8);
+    if (f == 1) {
+        s.mc = 0xFFFFFFFFu;
+        s.ne = 2u;
+    } else {
+        s.mc = (uint32_t)((1ull << 32) / f) + ((f & (f - 1)) ? 1u : 0u);
+        s.ne = (0u - f) * s.mc;
+    }
     s.nf2 = 0u - 2u * f;
     s.b2 = 2u * base;
     return s;
 }
-HD uint32_t asi_freq(const AnsSymInfo &s) { return s.w1 >> 8; }
-constexpr uint32_t kAnsNoNext = 0xFFFFFFu;   // "no further symbol": never triggers a renormalisation
+HD uint32_t asi_freq(const AnsSymInfo &s) { return (0u - s.nf2) >> 1; }
+// renormalisation threshold f << 8 of the symbol coded NEXT
+HD uint32_t asi_threshold(const AnsSymInfo &s) { return (0u - s.nf2) << 7; }
+constexpr uint32_t kAnsNoNext = 0xFFFFFFFFu;   // threshold for "no further symbol": never renormalises
 
-// Code one symbol.  `w1n` = this symbol's shift in bits 0..7 and, in bits 8.., the frequency of
-// the symbol that will be coded NEXT (the previous one in stream order; kAnsNoNext for none).
-// `lookup(byte_offset)` reads the uint16 slot table.  Out: x for the next step, whether that
-// step's renormalisation fires (p), and the 16-bit word it would emit.
-template <typename Lookup>
-HD void ans_step(uint32_t &x, uint32_t m, uint32_t w1n, uint32_t nf2, uint32_t b2, Lookup lookup,
-                 uint32_t &p, uint32_t &word) {
-    const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
-    const uint32_t q = (uint32_t)(t >> 32) >> (w1n & 31u);   // total shift 32 + sh: only the high word matters
-    const uint32_t slot = lookup(q * nf2 + (2u * x + b2));   // 2 * (base + x - q * f), mod 2^32
-    p = (q >> 8) >= (w1n >> 8) ? 1u : 0u;
-    const uint32_t a = p ? (q >> 4) : (q << 12);
-    const uint32_t keep = p ? 0u : 0xFFFFu;
-    word = ((q << 12) | slot) & 0xFFFFu;
-    x = a | (slot & keep);
+// The live values carried from step to step.
+struct AnsCarry {
+    uint32_t v;        // previous table load result
+    uint32_t meff;     // mc of the symbol being coded, or 0 when v must not count
+    uint32_t k;        // 2, or 0 when v must not count
+    uint32_t c0;       // table byte address of "remainder" a
+    uint64_t R;        // a * mc - qa * e
+};
+
+HD uint32_t ans_hi32(uint64_t w) {
+#if defined(__CUDA_ARCH__)
+    uint32_t h;   // taken as a 32-bit value so the signed multiply below stays a single IMAD.WIDE
+    asm("{ .reg .b32 lo; mov.b64 {lo, %0}, %1; }" : "=r"(h) : "l"(w));
+    return h;
+#else
+    return (uint32_t)(w >> 32);
+#endif
 }
 
+// shadow part: given the state's known part `a` and the record of the symbol to code
+HD void ans_prepare(AnsCarry &c, uint32_t a, bool v_counts, uint32_t mc, uint32_t ne, uint32_t b2) {
+    c.meff = v_counts ? mc : 0u;
+    c.k = v_counts ? 2u : 0u;
+    const uint64_t w = (uint64_t)a * mc;
+    const uint32_t qa = ans_hi32(w) - 1u;
+    c.c0 = 2u * a + b2;
+    c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)ne);
+}
 
-// Leaner form used by the kernel: returns the state s' BEFORE the next renormalisation instead of
-// (flag, word).  Both are recovered later, off the dependent path, by whoever knows the next
-// symbol's frequency f:   flag = (s' >> 20) >= f,  word = s' & 0xFFFF   (entropy.c:1092-1100).
-// `thr` = (next symbol's frequency << 8) | shift: the renormalisation test
-// (q >> 8) >= f_next is evaluated as (q | 0xFF) >= thr, and the shifter uses the low five bits.
+// set-up before the first step: the initial state renormalised for the first coded symbol
+// (reference: entropy.c:1083, 1092-1100).  `table_addr` is added to every table offset.
+HD void ans_chain_begin(AnsCarry &c, const AnsSymInfo &first, uint32_t table_addr) {
+    const uint32_t f = asi_freq(first);
+    const uint32_t x = ((kAnsInitState >> 20) >= f) ? (kAnsInitState >> 16) : kAnsInitState;
+    c.v = 0;
+    ans_prepare(c, x, false, first.mc, first.ne, first.b2 + table_addr);
+}
+
+// Code one symbol (`own`); `next` is the symbol coded in the following step (the previous one in
+// stream order) or NULL.  `lookup(byte_address)` reads the uint16 slot table.  Leaves in `s_out`
+// the state s' BEFORE the next renormalisation; flag and word are recovered later, off the
+// dependent path, by whoever knows the next symbol's frequency f:  flag = (s' >> 20) >= f,
+// word = s' & 0xFFFF  (entropy.c:1092-1100).  After the last step s_out is the final state.
+// (k_ans_chain spells the same sequence out by hand to control the instruction order.)
 template <typename Lookup>
-HD void ans_step_state(uint32_t &x, uint32_t m, uint32_t thr, uint32_t nf2, uint32_t b2, Lookup lookup,
-                       uint32_t &s_out) {
-    const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
-    const uint32_t q = (uint32_t)(t >> 32) >> (thr & 31u);   // total shift 32 + sh: only the high word matters
-    const uint32_t slot = lookup(q * nf2 + (2u * x + b2));
-    const bool p = (q | 0xFFu) >= thr;                       // renormalise for the next symbol?
-    const uint32_t a = p ? (q >> 4) : (q << 12);             // s' >> 16 == q >> 4 (slot < 4096)
-    const uint32_t keep = p ? 0u : 0xFFFFu;
-    s_out = (q << 12) | slot;
-    x = a | (slot & keep);
+HD void ans_step(AnsCarry &c, const AnsSymInfo &own, const AnsSymInfo *next, uint32_t table_addr, Lookup lookup,
+                 uint32_t &s_out) {
+    const uint32_t q = ans_hi32((uint64_t)c.v * c.meff + c.R);
+    const uint32_t slot = lookup(q * own.nf2 + (c.v * c.k + c.c0));
+    const bool p = next && q >= asi_threshold(*next);   // renormalise for the next symbol?
+    const uint32_t q12 = q << 12;
+    const uint32_t a = p ? (q >> 4) : q12;              // s' >> 16 == q >> 4 (slot < 4096)
+    if (next)
+        ans_prepare(c, a, !p, next->mc, next->ne, next->b2 + table_addr);
+    c.v = slot;
+    s_out = q12 | slot;
 }
 
 }  // namespace hydb

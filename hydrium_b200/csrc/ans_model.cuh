@@ -10,7 +10,7 @@
 //     direct slot table  inv[cum[sym] + offset] = (bucket << log_bucket) | pos  -- the alias map
 //     is a bijection on [0, 4096), so the reference's per-symbol entry search (entropy.c:1106-1113)
 //     becomes one shared-memory load in the serial chain;
-//   * state / freq uses an exact multiply-high reciprocal instead of a hardware divide.
+//   * state / freq is split into two exact multiply-high divisions (ans_chain.cuh).
 #pragma once
 
 #include "bitio.cuh"
@@ -142,32 +142,6 @@ HD void ans_slot_symbol(const AnsCluster &c, uint32_t s, int log_alpha, uint32_t
         sym = c.owner[i];
         offset = (uint32_t)((int32_t)c.off[i] + (int32_t)pos);
     }
-}
-
-// Exact floor(x / f) for 1 <= f <= 4096 and x < f * 2^20 (the rANS state invariant after
-// renormalisation, entropy.c:1092-1102):
-//     q = ((x * m) + (x << 32)) >> (32 + sh)        (64-bit arithmetic, no overflow)
-// f = 2^l:  m = 0, sh = l.   otherwise: l = floor(log2 f), m = ceil(2^(33+l) / f) - 2^32, sh = l + 1.
-// Proof sketch: with M = 2^32 + m = ceil(2^k / f), k = 33 + l, the error x*(M*f - 2^k) < f^2 * 2^20
-// <= 2^k, so the floor is unchanged; x*M < 2^64.  tests/test_host_logic.py checks it exhaustively
-// at the range boundaries.
-HD void ans_div_consts(uint32_t f, uint32_t &m, uint32_t &sh) {
-    const int l = floor_log2_u32(f);
-    if ((f & (f - 1)) == 0) {
-        m = 0;
-        sh = (uint32_t)l;
-        return;
-    }
-    const unsigned k = 33u + (unsigned)l;
-    // 2^k / f with k <= 44 fits 64 bits
-    const uint64_t num = 1ull << k;
-    const uint64_t M = (num + f - 1) / f;
-    m = (uint32_t)(M - (1ull << 32));
-    sh = (uint32_t)l + 1u;
-}
-HD uint32_t ans_div(uint32_t x, uint32_t m, uint32_t sh) {
-    const uint64_t t = (uint64_t)x * m + ((uint64_t)x << 32);
-    return (uint32_t)(t >> (32u + sh));
 }
 
 HD void ans_put_u8(BitSink &bw, uint32_t b) {   // reference: entropy.c:71-78

@@ -14,12 +14,17 @@
 //   6. frame header + TOC entry                            (encoder.c:327-435, 992-1005)
 //
 // The chain (3) is the one inherently serial part of the codec: one 32-bit state threads
-// through every symbol of the group.  It runs in warp 0 with every lane carrying the same state
-// (so the slot-table read is a shared-memory broadcast and nothing diverges); the other warps
-// only help build the tables and then retire.  Lane L fetches symbol (batch * 32 + L) one batch
-// ahead, looks up its constants and stages them in shared memory; the 32 steps of a batch are
-// straight-line code whose staged records are prefetched three steps ahead, so nothing but the
-// state itself sits on the dependent path.  See ans_chain.cuh for the per-step critical path.
+// through every symbol of the group.  A CHAIN warp runs nothing but the recurrence, every lane
+// carrying the same state (the slot-table read is a shared-memory broadcast, nothing diverges);
+// a HELPER warp looks up each symbol's 16-byte record {reciprocal, correction, -2f, table address}
+// one to four batches ahead, stages it in a shared-memory ring and later turns the states the chain
+// leaves behind into renormalisation flags and words; the other warps only build the tables and
+// retire.  The 32 steps of a batch are straight-line code whose records roll through registers
+// four steps ahead.  ans_chain.cuh has the per-step maths: between two table loads there is one
+// multiply-high and one multiply-add; the rest of the step (about fifteen instructions) executes
+// in the load's shadow.  Measured with ncu source-level sampling (profiles/r01_chain_source_*.txt),
+// the step is bound by in-order issue of those instructions -- wide integer multiplies occupy the
+// multiply pipe for ~8 cycles each -- rather than by the load latency.
 #include "ans_chain.cuh"
 #include "headers.cuh"
 #include "kernels.h"
@@ -40,11 +45,11 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 
 struct AnsShared {
     uint16_t inv[kHfClusters * kAnsTotal];              // 73,728 B inverse alias table
-    uint4 info4[kHfClusters * kHfTokens];               //  9,216 B per-symbol chain constants
-    uint4 stage[kRing][32];                             //  2,048 B ring of staged batch records
+    uint4 info4[kHfClusters * kHfTokens];               //  9,216 B per-symbol chain constants (AnsSymInfo)
+    uint4 stage[kRing][32];                             //  2,048 B ring of staged batch records (AnsSymInfo + table address)
     uint32_t cap[kRing][32];                            //  pre-renormalisation state left by each step
     uint32_t fring[kRing][32];                          //  frequencies of the symbols of each ring slot
-    uint32_t chain_warp, ticket, f_first;
+    uint32_t chain_warp, ticket;
     AnsCluster cl[kHfClusters];                         //  5,256 B
     uint32_t hist[kHfClusters * kHfTokens];             //  2,304 B
     uint32_t dbits[kDBitsWords];                        //  1,536 B
@@ -152,7 +157,9 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
     uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));   // read-only table: free to be scheduled early
+    // volatile: keeps the table load of a chain step ahead of that step's record prefetch and state
+    // store in program order, so nothing queues in front of it in the shared-memory pipe
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
@@ -212,7 +219,7 @@ k_ans_chain(Workspace ws) {
         const uint32_t c = idx / kHfTokens, k = idx - c * kHfTokens;
         const AnsCluster &cl = s.cl[c];
         const AnsSymInfo si = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
-        s.info4[idx] = make_uint4(si.m, si.w1, si.nf2, si.b2);
+        s.info4[idx] = make_uint4(si.mc, si.ne, si.nf2, si.b2);
         if (ws.dbg_freqs)
             ws.dbg_freqs[(size_t)tile * kHfClusters * kHfTokens + idx] = cl.freq[k];
     }
@@ -296,9 +303,9 @@ k_ans_chain(Workspace ws) {
             const uint32_t p = (uint32_t)bi * 32u + lane;
             return (bi >= 0 && p < N) ? sy[p] : 0xFFFFFFFFu;
         };
-        auto info_of = [&](uint32_t sym) -> uint4 {
+        auto info_of = [&](uint32_t sym) -> uint4 {   // unused lanes: frequency 0 (never flags)
             if (sym == 0xFFFFFFFFu)
-                return make_uint4(0u, 1u << 8, 0u, 0u);
+                return make_uint4(0u, 0u, 0u, 0u);
             return s.info4[hf_cluster(sym) * kHfTokens + hf_token(sym)];
         };
         uint32_t cnt = 0, lowest_flag = 0xFFFFFFFFu, gap_err = 0;
@@ -338,15 +345,10 @@ k_ans_chain(Workspace ws) {
                 bar_sync(kBarEmpty + slot, 64);
                 drain(seq - kRing);
             }
-            // staged .y = (frequency of the symbol coded next) << 8 | shift  (see ans_step)
-            const uint32_t f = inf_cur.y >> 8;
-            const uint32_t f_up = __shfl_up_sync(FULL, f, 1);
-            const uint32_t f_lo31 = __shfl_sync(FULL, inf_nxt.y >> 8, 31);
-            const uint32_t f_next = lane ? f_up : (bi == 0 ? kAnsNoNext : f_lo31);
-            s.stage[slot][lane] = make_uint4(inf_cur.x, (inf_cur.y & 0xFFu) | (f_next << 8), inf_cur.z, inf_cur.w + inv_base);
-            s.fring[slot][lane] = f;
-            if (seq == 0)
-                s.f_first = __shfl_sync(FULL, f, (N - 1) & 31);
+            // record of lane L = the chain constants of symbol base + L, table address folded in;
+            // unused lanes of the last batch carry frequency 0 and are never read by the chain
+            s.stage[slot][lane] = make_uint4(inf_cur.x, inf_cur.y, inf_cur.z, inf_cur.w + inv_base);
+            s.fring[slot][lane] = (0u - inf_cur.z) >> 1;
             bar_arrive(kBarFull + slot, 64);
             inf_cur = inf_nxt;
             sym_nxt = sym_nn;
@@ -363,40 +365,99 @@ k_ans_chain(Workspace ws) {
             ws.chain_out[tile * 4 + 3] = gap_err ? (uint32_t)kErrAnsGap : 0u;
         }
     } else {
-        auto lookup = [](uint32_t addr) -> uint32_t { return lds16(addr); };
-        uint32_t x = 0;
+        // Steps run in chain order n = 0 .. N-1 (symbol N-1-n); a step needs the record of its own
+        // symbol and, in the table load's shadow, that of the next one.  Only the first batch can be
+        // partial; it runs through a plain loop.  Full batches are 32 straight-line steps whose records
+        // roll through four registers sets loaded four steps ahead -- across the batch boundary too,
+        // which is why the FULL barrier of batch seq + 1 is taken before batch seq starts.
+        AnsCarry c;
+        uint32_t x = 0, q12_prev = 0;
+        auto rec_at = [&](int bi, int j) -> uint32_t {   // shared address of the record of symbol bi * 32 + j
+            return stage_base + (uint32_t)((((nbatch - 1 - bi) % kRing) * 32 + j) * 16);
+        };
+        // One step, spelled out in the order the instructions should issue (ans_chain.cuh has the
+        // maths).  `own` / `nxt` = {mc, -e, -2f, table address}.  The state a step leaves is stored by
+        // the following step, once the table load has returned.
+#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr)                                                   \
+        {                                                                                                      \
+            const uint32_t vprev = c.v;                                                                        \
+            const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
+            const uint32_t cv = vprev * c.k + c.c0;                                                            \
+            const uint32_t sp = q12_prev | vprev;                                                              \
+            if (store_prev)                                                                                    \
+                sts32((cap_addr), sp);                                                                         \
+            const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
+            const bool p = q >= (thr_n);                                                                       \
+            const uint32_t q4 = q >> 4;                                                                        \
+            q12_prev = q << 12;                                                                                \
+            const uint32_t a = p ? q4 : q12_prev;                                                              \
+            c.meff = p ? 0u : (nxt).x;                                                                         \
+            c.k = p ? 0u : 2u;                                                                                 \
+            const uint64_t w = (uint64_t)a * (nxt).x;                                                          \
+            const uint32_t qa = ans_hi32(w) - 1u;                                                              \
+            c.c0 = 2u * a + (nxt).w;                                                                           \
+            c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)(nxt).y);                            \
+            c.v = slotv;                                                                                       \
+        }
+        bar_sync(kBarFull + 0, 64);
+        {
+            const uint4 fr = lds128(rec_at(nbatch - 1, (int)((N - 1) & 31u)));
+            AnsSymInfo first;
+            first.mc = fr.x; first.ne = fr.y; first.nf2 = fr.z; first.b2 = fr.w;
+            ans_chain_begin(c, first, 0u);
+        }
+        uint4 r0, r1, r2, r3;
+        r0 = r1 = r2 = r3 = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t prev_cap0 = 0;   // where the state left by the previous batch's last step goes
+        int prev_slot = -1;
         for (int seq = 0; seq < nbatch; seq++) {
             const int slot = seq % kRing, bi = nbatch - 1 - seq;
             const uint32_t base = (uint32_t)bi * 32u;
             const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
             const uint32_t stg = stage_base + (uint32_t)slot * 32u * 16u, capb = cap_base + (uint32_t)slot * 32u * 4u;
-            bar_sync(kBarFull + slot, 64);
-            if (seq == 0)   // renormalise the initial state for the last symbol (entropy.c:1083, 1092-1100)
-                x = ((kAnsInitState >> 20) >= s.f_first) ? (kAnsInitState >> 16) : kAnsInitState;
-            // step j codes symbol j and leaves the pre-renormalisation state s'_j in cap[j]
+            const uint32_t nstg = stage_base + (uint32_t)((seq + 1) % kRing) * 32u * 16u;
             if (jtop == 31) {
-                uint4 r0 = lds128(stg + 31 * 16), r1 = lds128(stg + 30 * 16), r2 = lds128(stg + 29 * 16);
+                if (seq == 0 || (seq == 1 && ((N - 1) & 31u) != 31u)) {   // first straight-line batch: fill the pipeline
+                    r0 = lds128(stg + 31 * 16);
+                    r1 = lds128(stg + 30 * 16);
+                    r2 = lds128(stg + 29 * 16);
+                    r3 = lds128(stg + 28 * 16);
+                }
 #pragma unroll
                 for (int j = 31; j >= 0; --j) {
-                    const uint4 st = r0;
+                    const uint4 own = r0, nxt = r1;
                     r0 = r1;
                     r1 = r2;
-                    if (j >= 3)
-                        r2 = lds128(stg + (uint32_t)(j - 3) * 16u);
-                    uint32_t sp;
-                    ans_step_state(x, st.x, st.y, st.z, st.w, lookup, sp);
-                    sts32(capb + (uint32_t)j * 4u, sp);
+                    r2 = r3;
+                    if (j == 8 && seq + 1 < nbatch)   // the next batch's records are read from step 3 on
+                        bar_sync(kBarFull + (seq + 1) % kRing, 64);
+                    r3 = j >= 4 ? lds128(stg + (uint32_t)(j - 4) * 16u) : lds128(nstg + (uint32_t)(28 + j) * 16u);
+                    const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
+                    if (j == 31) {   // the previous batch's last state is complete now: store it and release the batch
+                        HYDB_ANS_STEP(own, nxt, thr_n, prev_slot >= 0, prev_cap0);
+                        if (prev_slot >= 0)
+                            bar_arrive(kBarEmpty + prev_slot, 64);
+                    } else {
+                        HYDB_ANS_STEP(own, nxt, thr_n, true, capb + (uint32_t)(j + 1) * 4u);
+                    }
                 }
             } else {
+                if (seq + 1 < nbatch)
+                    bar_sync(kBarFull + (seq + 1) % kRing, 64);
                 for (int j = jtop; j >= 0; --j) {
-                    const uint4 st = lds128(stg + (uint32_t)j * 16u);
-                    uint32_t sp;
-                    ans_step_state(x, st.x, st.y, st.z, st.w, lookup, sp);
-                    sts32(capb + (uint32_t)j * 4u, sp);
+                    const uint4 own = lds128(stg + (uint32_t)j * 16u);
+                    const uint4 nxt = j ? lds128(stg + (uint32_t)(j - 1) * 16u) : lds128(nstg + 31u * 16u);
+                    const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
+                    HYDB_ANS_STEP(own, nxt, thr_n, j < jtop, capb + (uint32_t)(j + 1) * 4u);
                 }
             }
-            bar_arrive(kBarEmpty + slot, 64);
+            prev_cap0 = capb;
+            prev_slot = slot;
         }
+        x = q12_prev | c.v;   // final state: what the last step leaves (no renormalisation follows)
+        sts32(prev_cap0, x);
+        bar_arrive(kBarEmpty + prev_slot, 64);
+#undef HYDB_ANS_STEP
         if (lane == 0) {
             ws.chain_out[tile * 4 + 1] = x;
             if (ws.dbg_clk) {   // stage-tap builds only: cycles spent in the prologue and in the chain

@@ -151,16 +151,17 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
         std::vector<uint32_t> sprime(n + 1, 0);
         sprime[n] = kAnsInitState;   // the virtual step before the last symbol
         auto freq_of = [&](uint32_t p) { return asi_freq(info[hf_cluster(syms[p])][hf_token(syms[p])]); };
-        x = ((kAnsInitState >> 20) >= freq_of(n - 1)) ? (kAnsInitState >> 16) : kAnsInitState;
         const uint8_t *inv_bytes = (const uint8_t *)&inv[0][0];
+        auto info_of = [&](uint32_t p) -> const AnsSymInfo & { return info[hf_cluster(syms[p])][hf_token(syms[p])]; };
+        AnsCarry carry;
+        ans_chain_begin(carry, info_of(n - 1), 0u);
         for (uint32_t r = 0; r < n; r++) {
             const uint32_t p = n - 1 - r;
-            const AnsSymInfo &si = info[hf_cluster(syms[p])][hf_token(syms[p])];
-            const uint32_t f_next = p ? freq_of(p - 1) : kAnsNoNext;
-            ans_step_state(x, si.m, (si.w1 & 0xFFu) | (f_next << 8), si.nf2, si.b2,
-                           [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; },
-                           sprime[p]);
+            ans_step(carry, info_of(p), p ? &info_of(p - 1) : nullptr, 0u,
+                     [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; },
+                     sprime[p]);
         }
+        x = sprime[0];   // the state left by the last step is final (no renormalisation follows)
         for (uint32_t p = n; p-- > 0;) {   // descending, like the chain emits them
             if ((sprime[p + 1] >> 20) >= freq_of(p)) {
                 flag[p] = 1;
@@ -213,17 +214,32 @@ uint32_t hh_frame_header(int crop, uint32_t x0, uint32_t y0, uint32_t w, uint32_
     return bw.bitlen();
 }
 
-// exact-division check: returns the number of mismatches over boundary and pseudo-random states
+// Exactness of the corrected-reciprocal division of ans_chain.cuh: for every frequency, states
+// x = a + v at the range boundaries and pseudo-random ones must give q = x / f and the table index
+// x % f.  Returns the number of mismatches.
 uint64_t hh_div_check(uint32_t f_lo, uint32_t f_hi, uint32_t samples) {
     uint64_t bad = 0;
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     for (uint32_t f = f_lo; f <= f_hi; f++) {
-        uint32_t m, sh;
-        ans_div_consts(f, m, sh);
+        const AnsSymInfo si = ans_sym_info(f, 0);
         const uint64_t lim = (uint64_t)f << 20;   // x < f * 2^20
+        auto check1 = [&](uint32_t a, uint32_t v, bool counts) {
+            AnsCarry c;
+            c.v = v;
+            ans_prepare(c, a, counts, si.mc, si.ne, 0x12340u);
+            const uint32_t q = ans_hi32((uint64_t)c.v * c.meff + c.R);
+            const uint32_t addr = q * si.nf2 + (c.v * c.k + c.c0);
+            const uint32_t x = a + (counts ? v : 0u);
+            if (q != x / f || addr != 0x12340u + 2u * (x % f)) bad++;
+        };
         auto check = [&](uint64_t x) {
-            if (x >= lim || x > 0xFFFFFFFFull) return;
-            if (ans_div((uint32_t)x, m, sh) != (uint32_t)(x / f)) bad++;
+            if (x >= lim || x > 0xFFFFFFFFull || x < 65536) return;
+            const uint32_t xx = (uint32_t)x;
+            check1(xx & ~0xFFFu, xx & 0xFFFu, true);   // not renormalised: a = q_prev << 12, v = slot
+            if (xx < 65536u * 16u) {                   // renormalised: a is the whole state, v is ignored
+                check1(xx, 0xFFFu, false);
+                check1(xx, (uint32_t)(rng >> 52), false);
+            }
         };
         for (uint64_t q = 0; q < 64; q++) {
             check(q * f); check(q * f + f - 1); if (q) check(q * f - 1);
@@ -235,11 +251,13 @@ uint64_t hh_div_check(uint32_t f_lo, uint32_t f_hi, uint32_t samples) {
             check(x); check(x - 1); check(x + 1);
             const uint64_t qv = x / f;
             check(qv * f); check(qv * f + f - 1); if (qv) check(qv * f - 1);
+            for (uint64_t d = 0; d < 4096; d += 37) { check((x & ~0xFFFull) + d); check((qv * f & ~0xFFFull) + d); }
         }
         for (uint32_t i = 0; i < samples; i++) {
             rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
             const uint64_t qv = rng % (1ull << 20);
             check(qv * f); check(qv * f + f - 1); if (qv) check(qv * f - 1); check(qv * f + (rng >> 40) % f);
+            check(65536 + (rng >> 44));   // small states, as after a renormalisation
         }
     }
     return bad;
