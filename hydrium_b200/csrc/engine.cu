@@ -119,9 +119,14 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(cudaEventCreateWithFlags(&eng->ev_front, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&eng->ev_lf, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&eng->ev_desc, cudaEventDisableTiming));
+    // earlier bands get higher stream priority: when an SM frees a slot, the tokeniser / chain CTAs of
+    // band 0 go before the front-end CTAs of later bands, so the first (3 ms long) chains start early
+    int prio_least = 0, prio_greatest = 0;
+    A(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     for (int b = 0; b < HydbEngine::kBands; b++) {
-        A(cudaStreamCreateWithFlags(&eng->band_st[b], cudaStreamNonBlocking));
-        A(cudaStreamCreateWithFlags(&eng->band_st2[b], cudaStreamNonBlocking));
+        const int prio = prio_greatest + b < prio_least ? prio_greatest + b : prio_least;
+        A(cudaStreamCreateWithPriority(&eng->band_st[b], cudaStreamNonBlocking, prio));
+        A(cudaStreamCreateWithPriority(&eng->band_st2[b], cudaStreamNonBlocking, prio_least));
         A(cudaEventCreateWithFlags(&eng->band_front[b], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&eng->band_lf[b], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&eng->band_done[b], cudaEventDisableTiming));
@@ -492,6 +497,12 @@ static void image_tiles(std::vector<HydbTile> &tiles, const void *base, uint32_t
 // order-dependent; the caller gathers all tiles afterwards on eng->st, which waits for every band.
 static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t rows, const void *h_src, void *d_dst,
                                   size_t row_bytes, uint32_t pixel_rows) {
+    // HYDRIUM_B200_BANDTRACE=1: print when each band's stages started / ended (development aid; synchronises)
+    static const bool trace = [] { const char *e = getenv("HYDRIUM_B200_BANDTRACE"); return e && e[0] == '1'; }();
+    static cudaEvent_t tr[1 + HydbEngine::kBands * 5];
+    if (trace && !tr[0])
+        for (cudaEvent_t &e : tr) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(tr[0], eng->st);
     CK(cudaEventRecord(eng->ev_desc, eng->st));
     const uint32_t nbands = rows < (uint32_t)HydbEngine::kBands ? rows : (uint32_t)HydbEngine::kBands;
     for (uint32_t b = 0; b < nbands; b++) {
@@ -505,18 +516,32 @@ static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t ro
                                (y1 - y0) * row_bytes, cudaMemcpyHostToDevice, sb));
         }
         const Workspace v = ws_view(eng->ws, first);
+        if (trace) cudaEventRecord(tr[1 + b * 5 + 0], sb);
         launch_xyb_dct_quant(v, eng->luts, n, sb);
+        if (trace) cudaEventRecord(tr[1 + b * 5 + 1], sb);
         CK(cudaEventRecord(eng->band_front[b], sb));
         CK(cudaStreamWaitEvent(sb2, eng->band_front[b], 0));
         launch_lf_group(v, n, sb2);
         CK(cudaEventRecord(eng->band_lf[b], sb2));
         launch_hf_tokens(v, n, sb);
+        if (trace) cudaEventRecord(tr[1 + b * 5 + 2], sb);
         launch_ans_chain(v, n, sb);
+        if (trace) cudaEventRecord(tr[1 + b * 5 + 3], sb);
         CK(cudaStreamWaitEvent(sb, eng->band_lf[b], 0));
         launch_ans_pack(v, eng->templ, n, sb);
+        if (trace) cudaEventRecord(tr[1 + b * 5 + 4], sb);
         CK(cudaEventRecord(eng->band_done[b], sb));
         CK(cudaStreamWaitEvent(eng->st, eng->band_done[b], 0));
         eng->launches += 5;
+    }
+    if (trace) {
+        cudaDeviceSynchronize();
+        for (uint32_t b = 0; b < nbands; b++) {
+            float t[5];
+            for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t[k], tr[0], tr[1 + b * 5 + k]);
+            fprintf(stderr, "[bandtrace] band %u: start %.3f  xyb done %.3f  tokens done %.3f  chain done %.3f  pack done %.3f ms\n",
+                    b, t[0], t[1], t[2], t[3], t[4]);
+        }
     }
     return HYD_OK;
 }

@@ -32,7 +32,8 @@
 
 namespace hydb {
 
-constexpr int kAnsThreads = 256;
+constexpr int kAnsThreads = 256;    // k_ans_chain
+constexpr int kPackThreads = 1024;  // k_ans_pack: one thread per ~3 chunks of 32 symbols, so its global loads overlap
 constexpr int kRing = 4;                 // batches in flight between the helper and the chain warp
 constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;   // named barrier ids (0 is __syncthreads)
 
@@ -95,7 +96,7 @@ __device__ __forceinline__ void append_bits(uint32_t *__restrict__ dst, uint64_t
     }
 }
 
-// block-wide exclusive scan of two values per thread (256 threads)
+// block-wide exclusive scan of two values per thread (kPackThreads threads)
 __device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *sa, uint32_t *sb, uint32_t tid,
                                             uint32_t &total_a, uint32_t &total_b) {
     const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *
     }
     __syncthreads();
     if (warp == 0) {
-        uint32_t wa = lane < kAnsThreads / 32 ? sa[lane] : 0, wb = lane < kAnsThreads / 32 ? sb[lane] : 0;
+        uint32_t wa = lane < kPackThreads / 32 ? sa[lane] : 0, wb = lane < kPackThreads / 32 ? sb[lane] : 0;
         uint32_t xa = wa, xb = wb;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -124,11 +125,11 @@ __device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *
                 xb += vb;
             }
         }
-        if (lane < kAnsThreads / 32) {
+        if (lane < kPackThreads / 32) {
             sa[lane] = xa - wa;
             sb[lane] = xb - wb;
         }
-        if (lane == kAnsThreads / 32 - 1) {
+        if (lane == kPackThreads / 32 - 1) {
             sa[32] = xa;
             sb[32] = xb;
         }
@@ -473,11 +474,11 @@ k_ans_chain(Workspace ws) {
 }
 
 struct PackShared {
-    uint32_t scan_a[kAnsThreads], scan_b[kAnsThreads];
+    uint32_t scan_a[kPackThreads], scan_b[kPackThreads];
     uint32_t err, ebits_total;
 };
 
-__global__ void __launch_bounds__(kAnsThreads)
+__global__ void __launch_bounds__(kPackThreads)
 k_ans_pack(Workspace ws, Templates tp) {
     __shared__ PackShared s;
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
@@ -500,14 +501,14 @@ k_ans_pack(Workspace ws, Templates tp) {
     const uint32_t la = tp.bits[0], lb = tp.bits[1 + t.shape], ll = ws.lfbitlen[tile];
     const uint32_t e_start = la + ll + lb + ld;
     const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !chain_err && N > 0 && !ws.tile_err[tile];
-    for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kAnsThreads)
+    for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kPackThreads)
         payload[w] = 0;
     __syncthreads();
     if (sane) {
-        append_bits(payload, 0, tp.words, la, tid, kAnsThreads);
-        append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kAnsThreads);
-        append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kAnsThreads);
-        append_bits(payload, (uint64_t)la + ll + lb, ws.dbits + (size_t)tile * kDBitsWords, ld, tid, kAnsThreads);
+        append_bits(payload, 0, tp.words, la, tid, kPackThreads);
+        append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kPackThreads);
+        append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kPackThreads);
+        append_bits(payload, (uint64_t)la + ll + lb, ws.dbits + (size_t)tile * kDBitsWords, ld, tid, kPackThreads);
     }
 
     // ---- 5. forward packing of section E -------------------------------------------------------------
@@ -517,12 +518,12 @@ k_ans_pack(Workspace ws, Templates tp) {
         s.err |= kErrSlab;
     const uint32_t total_bits = fits ? (uint32_t)total_bits64 : 0;
     if (fits) {
-        for (uint32_t w = (e_start >> 5) + 3 + tid; w <= (total_bits >> 5) + 1; w += kAnsThreads)
+        for (uint32_t w = (e_start >> 5) + 3 + tid; w <= (total_bits >> 5) + 1; w += kPackThreads)
             payload[w] = 0;
     }
     __syncthreads();
     {
-        const uint32_t nchunks = (N + 31) >> 5, cpt = (nchunks + kAnsThreads - 1) / kAnsThreads;
+        const uint32_t nchunks = (N + 31) >> 5, cpt = (nchunks + kPackThreads - 1) / kPackThreads;
         const uint32_t c0 = tid * cpt < nchunks ? tid * cpt : nchunks;
         const uint32_t c1 = c0 + cpt < nchunks ? c0 + cpt : nchunks;
         uint32_t bits = 0, nfl = 0;
@@ -531,9 +532,13 @@ k_ans_pack(Workspace ws, Templates tp) {
                 const uint32_t fl = flags[c];
                 nfl += __popc(fl);
                 const uint4 *q = reinterpret_cast<const uint4 *>(sy + (size_t)c * 32);
+                uint4 vv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    vv[k] = q[k];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint4 v = q[k];
+                    const uint4 v = vv[k];
                     const uint32_t p = c * 32 + k * 4;
                     bits += (p + 0 < N ? hf_nbits(v.x) : 0) + (p + 1 < N ? hf_nbits(v.y) : 0) +
                             (p + 2 < N ? hf_nbits(v.z) : 0) + (p + 3 < N ? hf_nbits(v.w) : 0);
@@ -577,22 +582,34 @@ k_ans_pack(Workspace ws, Templates tp) {
             for (uint32_t c = c0; c < c1; c++) {
                 const uint32_t fl = flags[c];
                 const uint4 *q = reinterpret_cast<const uint4 *>(sy + (size_t)c * 32);
+                uint4 vv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    vv[k] = q[k];
+                // this chunk's renormalisation words, fetched together (forward order = descending index)
+                const int nw = __popc(fl);
+                uint16_t wbuf[32];
+#pragma unroll
+                for (int k = 0; k < 32; k++)
+                    wbuf[k] = k < nw ? fwords[widx - k] : (uint16_t)0;
+                int wk = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint4 v = q[k];
+                    const uint4 v = vv[k];
                     const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const uint32_t p = c * 32 + k * 4 + u;
                         if (p < N) {
                             if ((fl >> (k * 4 + u)) & 1u)
-                                put(fwords[widx--], 16);
+                                put(wbuf[wk++], 16);
                             const uint32_t nb = hf_nbits(sv[u]);
                             if (nb)
                                 put(hf_residue(sv[u]), nb);
                         }
                     }
                 }
+                widx -= nw;
             }
             if (nacc && (uint32_t)acc)
                 atomicOr(&payload[wpos], (uint32_t)acc);
@@ -652,11 +669,13 @@ k_ans_pack(Workspace ws, Templates tp) {
 
 void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
     cudaFuncSetAttribute(k_ans_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
+    prefer_max_shared(k_ans_chain);
     k_ans_chain<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws);
 }
 
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st) {
-    k_ans_pack<<<ntiles, kAnsThreads, 0, st>>>(ws, t);
+    prefer_max_shared(k_ans_pack);
+    k_ans_pack<<<ntiles, kPackThreads, 0, st>>>(ws, t);
 }
 
 }  // namespace hydb

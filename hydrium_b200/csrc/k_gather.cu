@@ -98,6 +98,8 @@ k_gather_frames(const uint8_t *__restrict__ slab, const uint32_t *__restrict__ f
 
 void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
                    uint32_t *d_overflow, cudaStream_t st) {
+    prefer_max_shared(k_frame_offsets);
+    prefer_max_shared(k_gather_frames);
     k_frame_offsets<<<1, 1024, 0, st>>>(ws.frame_len, ws.out_off, ntiles);
     k_gather_frames<<<ntiles, 256, 0, st>>>(ws.slab, ws.frame_off, ws.frame_len, ws.out_off, out, out_cap, base, d_overflow);
 }

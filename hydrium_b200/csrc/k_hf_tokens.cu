@@ -25,7 +25,7 @@ namespace hydb {
 
 __constant__ uint8_t c_freq_ctx[64] = {HYDB_FREQ_CTX};
 
-constexpr int kTokThreads = 512;
+constexpr int kTokThreads = 1024;
 
 // nnz_context(left) % 3 for left = 0..63, two bits each (see tables.cuh: 0,0,31,62,62,93 x4,123 x4,152 x8,180 x12,206...)
 __device__ __forceinline__ uint32_t nnz_ctx_mod3(uint32_t left) {
@@ -121,54 +121,80 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
     const int16_t *tile_coef = coef + (size_t)tile * kMaxBlocks * 3 * 64;
     const uint32_t fc3_lo = c_freq_ctx[lane] % 3u, fc3_hi = c_freq_ctx[lane + 32] % 3u;   // per-lane constants
     uint32_t my_resbits = 0, my_err = 0;
-    for (uint32_t e = warp; e < ne; e += kTokThreads / 32) {
-        const uint32_t blk = e / 3, i = e - blk * 3, c = i < 2 ? 1 - i : i;
-        const uint32_t by = blk / vbw, bx = blk - by * vbw;
-        const uint32_t info = s_info[e], nz = info & 0xFF, last = info >> 8;
-        const uint32_t base = s_off[e];
-        if (lane == 0) {
-            // non-zero count on cluster i, hybrid config (4, 1, 0) (encoder.c:908)
-            uint32_t res, nbits;
-            uint32_t tok = hybrid_token(nz, 4, 1, 0, res, nbits);
-            out[base] = hf_pack(tok, i, nbits, res);
-            atomicAdd(&s_hist[i * kHfTokens + tok], 1u);
-            my_resbits += nbits;
-        }
-        if (!nz)
-            continue;
-        const int16_t *q = tile_coef + ((by * kBlocksPerRow + bx) * 3 + c) * 64;
-        const int q_lo = q[lane];
-        const int q_hi = last >= 32 ? q[lane + 32] : 0;   // warp-uniform: nothing to code up there
-        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, q_lo != 0);
-        const uint32_t m_hi = last >= 32 ? __ballot_sync(0xFFFFFFFFu, q_hi != 0) : 0u;
-        const uint64_t mask = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            if (half && last < 32)
-                break;
-            const uint32_t j = lane + 32 * half;
-            const int qv = half ? q_hi : q_lo;
-            const bool valid = j >= 1 && j <= last;
-            uint32_t key = 0xFFFFFFFFu;
-            if (valid) {
-                const uint32_t below = __popcll(mask & ((1ull << j) - 1ull));
-                const uint32_t left = nz - below;
-                const uint32_t prev = j == 1 ? (nz <= 4 ? 1u : 0u) : (uint32_t)((mask >> (j - 1)) & 1ull);
-                const uint32_t cluster = 3 + prev + 2 * ((i + nnz_ctx_mod3(left) + (half ? fc3_hi : fc3_lo)) % 3);
-                uint32_t res, nbits;
-                uint32_t tok = hybrid_token(pack_signed(qv), 4, 1, 0, res, nbits);
-                if (tok >= (uint32_t)kHfTokens) {
-                    my_err |= kErrAlphabet;
-                    tok = kHfTokens - 1;
-                }
-                out[base + j] = hf_pack(tok, cluster, nbits, res);
-                my_resbits += nbits;
-                key = cluster * kHfTokens + tok;
+    // The coefficients come from HBM / L2 (hundreds of cycles away) and each warp walks its entries one
+    // after the other, so they are fetched kAhead entries ahead into registers.
+    constexpr int kAhead = 4;
+    constexpr uint32_t kStep = kTokThreads / 32;
+    auto fetch = [&](uint32_t e, int &lo, int &hi) {
+        lo = hi = 0;
+        if (e < ne) {
+            const uint32_t info = s_info[e];
+            if (info & 0xFF) {
+                const uint32_t blk = e / 3, i = e - blk * 3, c = i < 2 ? 1 - i : i;
+                const uint32_t by = blk / vbw, bx = blk - by * vbw;
+                const int16_t *q = tile_coef + ((by * kBlocksPerRow + bx) * 3 + c) * 64;
+                lo = q[lane];
+                if ((info >> 8) >= 32)   // warp-uniform: nothing to code in the upper half otherwise
+                    hi = q[lane + 32];
             }
-            // warp-aggregated histogram update
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-            if (valid && lane == (uint32_t)(__ffs(peers) - 1))
-                atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+        }
+    };
+    int buf_lo[kAhead], buf_hi[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; k++)
+        fetch(warp + (uint32_t)k * kStep, buf_lo[k], buf_hi[k]);
+    for (uint32_t e0 = warp; e0 < ne; e0 += kStep * kAhead) {
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            const uint32_t e = e0 + (uint32_t)k * kStep;
+            const int q_lo = buf_lo[k], q_hi = buf_hi[k];
+            fetch(e + kStep * kAhead, buf_lo[k], buf_hi[k]);
+            if (e >= ne)
+                continue;
+            const uint32_t blk = e / 3, i = e - blk * 3;
+            const uint32_t info = s_info[e], nz = info & 0xFF, last = info >> 8;
+            const uint32_t base = s_off[e];
+            if (lane == 0) {
+                // non-zero count on cluster i, hybrid config (4, 1, 0) (encoder.c:908)
+                uint32_t res, nbits;
+                uint32_t tok = hybrid_token(nz, 4, 1, 0, res, nbits);
+                out[base] = hf_pack(tok, i, nbits, res);
+                atomicAdd(&s_hist[i * kHfTokens + tok], 1u);
+                my_resbits += nbits;
+            }
+            if (!nz)
+                continue;
+            const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, q_lo != 0);
+            const uint32_t m_hi = last >= 32 ? __ballot_sync(0xFFFFFFFFu, q_hi != 0) : 0u;
+            const uint64_t mask = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                if (half && last < 32)
+                    break;
+                const uint32_t j = lane + 32 * half;
+                const int qv = half ? q_hi : q_lo;
+                const bool valid = j >= 1 && j <= last;
+                uint32_t key = 0xFFFFFFFFu;
+                if (valid) {
+                    const uint32_t below = __popcll(mask & ((1ull << j) - 1ull));
+                    const uint32_t left = nz - below;
+                    const uint32_t prev = j == 1 ? (nz <= 4 ? 1u : 0u) : (uint32_t)((mask >> (j - 1)) & 1ull);
+                    const uint32_t cluster = 3 + prev + 2 * ((i + nnz_ctx_mod3(left) + (half ? fc3_hi : fc3_lo)) % 3);
+                    uint32_t res, nbits;
+                    uint32_t tok = hybrid_token(pack_signed(qv), 4, 1, 0, res, nbits);
+                    if (tok >= (uint32_t)kHfTokens) {
+                        my_err |= kErrAlphabet;
+                        tok = kHfTokens - 1;
+                    }
+                    out[base + j] = hf_pack(tok, cluster, nbits, res);
+                    my_resbits += nbits;
+                    key = cluster * kHfTokens + tok;
+                }
+                // warp-aggregated histogram update
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+                if (valid && lane == (uint32_t)(__ffs(peers) - 1))
+                    atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+            }
         }
     }
 #pragma unroll
@@ -192,6 +218,7 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
 }
 
 void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
+    prefer_max_shared(k_hf_tokens);
     k_hf_tokens<<<ntiles, kTokThreads, 0, st>>>(ws.tiles, ws.coef, ws.nzinfo, ws.syms, ws.nsyms, ws.resbits, ws.hist,
                                                 ws.tile_err);
 }

@@ -515,6 +515,7 @@ k_build_templates(Templates t, const uint32_t *__restrict__ shape_dims, uint32_t
 
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
     cudaFuncSetAttribute(k_lf_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LfShared));
+    prefer_max_shared(k_lf_group);
     k_lf_group<<<ntiles, 32, sizeof(LfShared), st>>>(ws.tiles, ws.lfq, ws.lfbits, ws.lfbitlen, ws.tile_err);
 }
 

@@ -246,6 +246,7 @@ void launch_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_
 }
 
 void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st) {
+    prefer_max_shared(k_xyb_dct_quant);
     k_xyb_dct_quant<<<dim3(kBlocksPerRow, ntiles), 256, 0, st>>>(ws.tiles, luts, ws.coef, ws.nzinfo, ws.lfq, ws.dbg_xyb,
                                                                  ws.dbg_dct);
 }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -68,5 +69,16 @@ void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t 
 void launch_synth_fill(void *dst, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t full_w,
                        uint32_t full_h, int bits, uint32_t seed, int smooth, cudaStream_t st);
 int ans_encode_smem_bytes();
+
+// Every kernel of the pipeline asks for the same (largest) shared-memory carve-out: an SM only
+// changes its L1 / shared split when it is idle, so kernels with different preferences cannot share
+// an SM and the rANS chain CTAs of an early band (95 KB each) would otherwise wait for the front-end
+// kernels of all later bands to drain.  HYDRIUM_B200_CARVEOUT=0 leaves the driver's default.
+template <typename K>
+inline void prefer_max_shared(K kernel) {
+    static const bool on = [] { const char *e = getenv("HYDRIUM_B200_CARVEOUT"); return !(e && e[0] == '0'); }();
+    if (on)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
 
 }  // namespace hydb
