@@ -363,9 +363,18 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to
+    # file descriptor 1 behind Python's back, so everything but our line is sent to stderr.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_ours(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -46,6 +46,7 @@ enum TileError : uint32_t {
     kErrSlab = 1u << 4,           // frame larger than the slab
     kErrAlias = 1u << 5,          // reference would fail: "empty underfull during alias table gen"
     kErrLfAlphabet = 1u << 6,     // more distinct LF tokens than the sparse coder holds
+    kErrNonFinite = 1u << 7,      // NaN / Inf float sample (reference: format.c:123-126 "Invalid NaN Float")
 };
 
 // Device-visible tile descriptor (mirrors what hyd_send_tile is given,
@@ -63,9 +64,10 @@ struct TileDesc {
 enum : uint32_t {
     kTileLast = 1u << 0,      // is_last frame (reference: encoder.c:482-485)
     kTileCrop = 1u << 1,      // image larger than the tile (reference: encoder.c:340-342)
-    kTileFmt16 = 1u << 2,     // HYD_UINT16 samples, else HYD_UINT8
+    kTileFmt16 = 1u << 2,     // HYD_UINT16 samples, else HYD_UINT8 (or float, see kTileFmtF32)
     kTileLinear = 1u << 3,    // linear-light input
     kTileFirst = 1u << 4,     // first frame of a codestream: the image header goes in front of it
+    kTileFmtF32 = 1u << 5,    // HYD_FLOAT32 samples (reference: format.c:111-140)
 };
 
 // ---- integer helpers (reference: math-functions.h:8-88) ----------------------------------

@@ -73,7 +73,12 @@ struct HydbEngine {
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
+static size_t sample_item_bytes(int sample_fmt) {
+    return sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4);
+}
+
 static const char *tile_error_text(uint32_t bits) {
+    if (bits & kErrNonFinite) return "Invalid NaN Float";                 // reference: format.c:124
     if (bits & kErrAlphabet) return "HF token alphabet exceeds 64 symbols";
     if (bits & kErrHuffman) return "couldn't find target";               // reference: entropy.c:635
     if (bits & kErrAlias) return "empty underfull during alias table gen";   // reference: entropy.c:219
@@ -301,7 +306,7 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
     for (uint32_t i = 0; i < n; i++) {
         const HydbTile &s = tiles[i];
         if (!s.width || !s.height || s.width > 256 || s.height > 256 || (s.x0 & 255) || (s.y0 & 255) ||
-            (s.sample_fmt != HYD_UINT8 && s.sample_fmt != HYD_UINT16) || !s.plane[0] || !s.plane[1] || !s.plane[2]) {
+            (s.sample_fmt != HYD_UINT8 && s.sample_fmt != HYD_UINT16 && s.sample_fmt != HYD_FLOAT32) || !s.plane[0] || !s.plane[1] || !s.plane[2]) {
             eng->error = "invalid tile descriptor";
             return HYD_API_ERROR;
         }
@@ -325,7 +330,8 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
         d.image_h = s.image_height;
         d.flags = (s.is_last ? kTileLast : 0u) | (s.with_image_header ? kTileFirst : 0u) |
                   ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
-                  (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.linear_light ? kTileLinear : 0u);
+                  (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.sample_fmt == HYD_FLOAT32 ? kTileFmtF32 : 0u) |
+                  (s.linear_light ? kTileLinear : 0u);
     }
     if (!fresh.empty()) {
         std::vector<uint32_t> dims;
@@ -415,7 +421,7 @@ HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     for (uint32_t i = 0; i < eng->last_n; i++) {
         if (eng->h_err[i]) {
             eng->error = tile_error_text(eng->h_err[i]);
-            return HYD_INTERNAL_ERROR;
+            return (eng->h_err[i] & kErrNonFinite) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
         }
     }
     if (eng->last_n && eng->h_err[eng->max_batch]) {
@@ -463,7 +469,7 @@ static void image_tiles(std::vector<HydbTile> &tiles, const void *base, uint32_t
                         int64_t row_stride, int sample_fmt, int linear_light, uint32_t row_begin, uint32_t row_end,
                         int with_header) {
     const uint32_t tiles_x = (width + 255) >> 8, tiles_y = (height + 255) >> 8;
-    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+    const size_t item = sample_item_bytes(sample_fmt);
     tiles.resize((size_t)tiles_x * (row_end - row_begin));
     for (size_t idx = 0; idx < tiles.size(); idx++) {
         const uint32_t tx = (uint32_t)(idx % tiles_x), ty = row_begin + (uint32_t)(idx / tiles_x);
@@ -551,7 +557,7 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
                                        uint32_t tile_row_begin, uint32_t tile_row_end, int with_header, uint8_t *d_out,
                                        uint64_t d_out_cap, uint64_t *out_len) {
     if (!eng || !d_pixels || !d_out || !out_len || !width || !height || channels < 3 ||
-        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16)) {
+        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16 && sample_fmt != HYD_FLOAT32)) {
         if (eng) eng->error = "invalid arguments to hydb_encode_image_device";
         return HYD_API_ERROR;
     }
@@ -593,7 +599,7 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
         const uint32_t r0 = tile_row_begin + (uint32_t)(first / tiles_x);
         // batches are cut at arbitrary tiles: build the descriptors of whole rows and slice
         const uint32_t r1 = tile_row_begin + (uint32_t)((first + n + tiles_x - 1) / tiles_x);
-        const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+        const size_t item = sample_item_bytes(sample_fmt);
         image_tiles(tiles, (const uint8_t *)d_pixels + (int64_t)(r0 - tile_row_begin) * 256 * row_stride * (int64_t)item, width,
                     height, channels, row_stride, sample_fmt, linear_light, r0, r1, 0);
         const size_t skip = (size_t)(first - (uint64_t)(r0 - tile_row_begin) * tiles_x);
@@ -650,10 +656,11 @@ static HYDStatusCode grow_device(HydbEngine *eng, void **p, size_t *cap, size_t 
 HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint32_t width, uint32_t height,
                                      uint32_t channels, int sample_fmt, int linear_light, uint8_t *h_out,
                                      uint64_t h_out_cap, uint64_t *out_len) {
-    if (!eng || !h_pixels || !h_out || !out_len || (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16))
+    if (!eng || !h_pixels || !h_out || !out_len ||
+        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16 && sample_fmt != HYD_FLOAT32))
         return HYD_API_ERROR;
     CK(cudaSetDevice(eng->device));
-    const size_t item = sample_fmt == HYD_UINT8 ? 1 : 2;
+    const size_t item = sample_item_bytes(sample_fmt);
     const size_t in_bytes = (size_t)width * height * channels * item;
     HYDStatusCode rc = grow_device(eng, &eng->host_in, &eng->host_in_cap, in_bytes);
     if (rc == HYD_OK)

@@ -25,7 +25,7 @@
 
 #define TILE 256u
 /* worst-case staged bytes of one tile: 256 rows x 256 px x 4 samples x 2 bytes */
-#define TILE_STAGE_BYTES (256u * 256u * 4u * 2u)
+#define TILE_STAGE_BYTES (256u * 256u * 4u * 4u) /* worst case: RGBA float */
 /* device output bytes reserved per queued tile (the engine reports overflow, never overruns) */
 #define TILE_OUT_BYTES (768u * 1024u)
 
@@ -400,10 +400,6 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
         enc->error = "tile out of bounds";
         return HYD_API_ERROR;
     }
-    if (sample_fmt == HYD_FLOAT32) {
-        enc->error = "HYD_FLOAT32 input is not supported by the B200 encoder";
-        return HYD_API_ERROR;
-    }
     HYDStatusCode rc = ensure_gpu(enc);
     if (rc < HYD_ERROR_START)
         return rc;
@@ -425,7 +421,8 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     t->linear_light = enc->metadata.linear_light != 0;
     t->with_image_header = !enc->wrote_header; /* encoder.c:490-494: the image header precedes the first frame */
     enc->wrote_header = 1;
-    stage_tile(enc, t, buffer, row_stride, pixel_stride, sample_fmt == HYD_UINT8 ? 1 : 2);
+    stage_tile(enc, t, buffer, row_stride, pixel_stride,
+               sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4));
     enc->queued++;
 
     if (enc->queued == enc->batch || enc->last_tile) {

@@ -41,6 +41,11 @@ __device__ __forceinline__ float fast_cbrt(float x) {
     return __fdiv_rn(1.0f, z);
 }
 
+// reference: format.c:29-31
+__device__ __forceinline__ float opsin_bias(float x) {
+    return __fsub_rn(fast_cbrt(__fadd_rn(x, 0.0037930732552754493f)), 0.155954f);
+}
+
 __global__ void k_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_srgb, uint16_t *lut16_lin,
                              float *bias) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,8 +54,7 @@ __global__ void k_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *
     const float step16 = __fdiv_rn(1.0f, __fsub_rn(65536.0f, 1.0f));
     const float f16 = __fmul_rn((float)i, step16);
     {
-        const float b = __fsub_rn(fast_cbrt(__fadd_rn(f16, 0.0037930732552754493f)), 0.155954f);
-        bias[i] = b;
+        bias[i] = opsin_bias(f16);
     }
     auto to_u16 = [](float x) -> uint16_t {
         int v = __float2int_rz(__fadd_rn(__fmul_rn(x, 65535.f), 0.5f));
@@ -117,10 +121,49 @@ __device__ __forceinline__ void load_xyb(const TileDesc &t, const uint16_t *in_l
     }
 }
 
+// HYD_FLOAT32 samples: no tables, the transfer curve and the opsin mix are evaluated per pixel in the
+// reference's operation order (format.c:38-46, 111-140).  Returns false for a NaN / Inf sample.
+__device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uint32_t px0, uint32_t y, float (&X)[8],
+                                             float (&Y)[8], float (&B)[8]) {
+    const float *p0 = (const float *)t.plane[0];
+    const float *p1 = (const float *)t.plane[1];
+    const float *p2 = (const float *)t.plane[2];
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t px = px0 + i;
+        float x = 0.0f, yy = 0.0f, b = 0.0f;
+        if (px < t.w && y < t.h) {
+            const int64_t o = (int64_t)y * t.row_stride + (int64_t)px * t.pixel_stride;
+            float r = __ldg(p0 + o), g = __ldg(p1 + o), bl = __ldg(p2 + o);
+            finite = finite && isfinite(r) && isfinite(g) && isfinite(bl);
+            if (!linear) {
+                r = srgb_to_linear(r);
+                g = srgb_to_linear(g);
+                bl = srgb_to_linear(bl);
+            }
+            // (c0 * r + c1 * g) + c2 * b, every product and sum rounded separately
+            auto mix = [&](float c0, float c1, float c2) {
+                return __fadd_rn(__fadd_rn(__fmul_rn(c0, r), __fmul_rn(c1, g)), __fmul_rn(c2, bl));
+            };
+            const float l = opsin_bias(mix(0.3f, 0.622f, 0.078f));
+            const float m = opsin_bias(mix(0.23f, 0.692f, 0.078f));
+            const float s = opsin_bias(mix(0.243423f, 0.204767f, 0.55181f));
+            yy = __fmul_rn(__fadd_rn(l, m), 0.5f);
+            x = __fsub_rn(yy, m);
+            b = __fsub_rn(s, yy);
+        }
+        X[i] = x;
+        Y[i] = yy;
+        B[i] = b;
+    }
+    return finite;
+}
+
 __global__ void __launch_bounds__(256)
 k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__restrict__ coef,
-                uint16_t *__restrict__ nzinfo, int32_t *__restrict__ lfq, float *__restrict__ dbg_xyb,
-                float *__restrict__ dbg_dct) {
+                uint16_t *__restrict__ nzinfo, int32_t *__restrict__ lfq, uint32_t *__restrict__ tile_err,
+                float *__restrict__ dbg_xyb, float *__restrict__ dbg_dct) {
     __shared__ float s_rows[3 * 32 * kBlkPad];            // 27,648 B
     __shared__ __align__(16) int16_t s_q[32 * 3 * 64];    // 12,288 B
     __shared__ uint16_t s_lut8[256];
@@ -133,9 +176,10 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     if (by >= vbh)
         return;
     const uint32_t tid = threadIdx.x, b = tid >> 3, r = tid & 7;
-    const bool fmt16 = (t.flags & kTileFmt16) != 0, linear = (t.flags & kTileLinear) != 0;
+    const bool fmt16 = (t.flags & kTileFmt16) != 0, fmt32 = (t.flags & kTileFmtF32) != 0;
+    const bool linear = (t.flags & kTileLinear) != 0;
 
-    if (!fmt16)
+    if (!fmt16 && !fmt32)
         s_lut8[tid] = (linear ? luts.lut8_lin : luts.lut8_srgb)[tid];
     if (tid < 192)
         s_w[tid] = (float)c_hf_weights[tid >> 6][tid & 63];
@@ -146,7 +190,10 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     // ---- colour transform + row pass --------------------------------------------------------
     if (b < vbw) {
         float v[3][8];
-        if (fmt16)
+        if (fmt32) {
+            if (!load_xyb_f32(t, linear, b * 8, by * 8 + r, v[0], v[1], v[2]))
+                atomicOr(&tile_err[tile], (uint32_t)kErrNonFinite);
+        } else if (fmt16)
             load_xyb<uint16_t>(t, linear ? luts.lut16_lin : luts.lut16_srgb, luts.bias, b * 8, by * 8 + r, v[0], v[1], v[2]);
         else
             load_xyb<uint8_t>(t, s_lut8, luts.bias, b * 8, by * 8 + r, v[0], v[1], v[2]);
@@ -247,8 +294,8 @@ void launch_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_
 
 void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st) {
     prefer_max_shared(k_xyb_dct_quant);
-    k_xyb_dct_quant<<<dim3(kBlocksPerRow, ntiles), 256, 0, st>>>(ws.tiles, luts, ws.coef, ws.nzinfo, ws.lfq, ws.dbg_xyb,
-                                                                 ws.dbg_dct);
+    k_xyb_dct_quant<<<dim3(kBlocksPerRow, ntiles), 256, 0, st>>>(ws.tiles, luts, ws.coef, ws.nzinfo, ws.lfq, ws.tile_err,
+                                                                 ws.dbg_xyb, ws.dbg_dct);
 }
 
 }  // namespace hydb

@@ -9,9 +9,18 @@ import ctypes as C
 
 import numpy as np
 
-from .abi import HYD_ERROR_START, HYD_OK, HYD_UINT8, HYD_UINT16
+from .abi import HYD_ERROR_START, HYD_FLOAT32, HYD_OK, HYD_UINT8, HYD_UINT16
 from .encoder import HydriumError
 from .lib import HydbTile, load_library
+
+
+def _fmt_of(image: np.ndarray) -> int:
+    """HYDSampleFormat of a numpy image (reference: libhydrium.h:101-107)."""
+    try:
+        return {np.dtype(np.uint8): HYD_UINT8, np.dtype(np.uint16): HYD_UINT16,
+                np.dtype(np.float32): HYD_FLOAT32}[image.dtype]
+    except KeyError:
+        raise ValueError(f"unsupported sample type {image.dtype}") from None
 
 TAP_XYB, TAP_DCT, TAP_COEF, TAP_NZINFO, TAP_LFQ, TAP_SYMS, TAP_FREQS, TAP_LFBITS, TAP_SECT, TAP_PAYLOAD, \
     TAP_NSYMS, TAP_LFBITLEN, TAP_CLK = range(13)
@@ -104,7 +113,7 @@ class Engine:
         """Convenience: numpy image (H, W, C) -> complete codestream bytes (tile mode, shift 0/0)."""
         image = np.ascontiguousarray(image)
         h, w, ch = image.shape
-        fmt = HYD_UINT8 if image.dtype == np.uint8 else HYD_UINT16
+        fmt = _fmt_of(image)
         cap = output_bound(w, h)
         d_in = self.upload(image)
         d_out = self.device_alloc(cap)
@@ -120,7 +129,7 @@ class Engine:
         """hydb_encode_image_host: host pixels in, host codestream out (H2D + D2H inside)."""
         image = np.ascontiguousarray(image)
         h, w, ch = image.shape
-        fmt = HYD_UINT8 if image.dtype == np.uint8 else HYD_UINT16
+        fmt = _fmt_of(image)
         if out is None:
             out = np.empty(output_bound(w, h), np.uint8)
         n = C.c_uint64(0)
@@ -141,7 +150,7 @@ class Engine:
         its own codestream (BASELINE config 4: a batch of frames).  Tiles of different images share
         GPU launches.  Returns a list of (offset, length) into d_out, one complete codestream each
         (image header + frames)."""
-        item = 1 if sample_fmt == HYD_UINT8 else 2
+        item = {HYD_UINT8: 1, HYD_UINT16: 2}.get(sample_fmt, 4)
         ntx, nty = (width + 255) // 256, (height + 255) // 256
         per_image = ntx * nty
         spans, pos = [], 0

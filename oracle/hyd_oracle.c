@@ -12,6 +12,7 @@
 #include "hyd_oracle.h"
 
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 static const char *g_err = NULL;
@@ -973,13 +974,36 @@ void orc_build_luts(int sample_fmt, int linear_light, uint16_t *input_lut, float
         bias_lut[i] = opsin_bias(i * step16);
 }
 
-/* pixel -> XYB with zero padding of partial blocks (format.c:48-56, 85-109, 182-191) */
-static void stage_xyb(const OrcTile *t, uint32_t w, uint32_t h, uint32_t stride, uint32_t rows,
-                      const uint16_t *in_lut, const float *bias_lut, float *xyb) {
+/* pixel -> XYB with zero padding of partial blocks (format.c:48-56, 85-109, 182-191);
+ * float samples skip both tables (format.c:38-46, 111-140).  Returns 0, or -1 for a non-finite sample. */
+static int stage_xyb(const OrcTile *t, uint32_t w, uint32_t h, uint32_t stride, uint32_t rows,
+                     const uint16_t *in_lut, const float *bias_lut, float *xyb) {
     memset(xyb, 0, (size_t)stride * rows * 3 * sizeof(float));
     for (uint32_t y = 0; y < h; y++) {
         for (uint32_t x = 0; x < w; x++) {
             ptrdiff_t o = (ptrdiff_t)y * t->row_stride + (ptrdiff_t)x * t->pixel_stride;
+            if (t->sample_fmt == ORC_FLOAT32) {
+                float fr = ((const float *)t->plane[0])[o], fg = ((const float *)t->plane[1])[o],
+                      fb = ((const float *)t->plane[2])[o];
+                /* the reference sets "Invalid NaN Float" but drops the status (format.c:123-126, 168-172)
+                 * and goes on with a partly stale buffer; both the oracle and the product refuse instead */
+                if (!isfinite(fr) || !isfinite(fg) || !isfinite(fb))
+                    return -1;
+                if (!t->linear_light) {
+                    fr = srgb_to_linear(fr);
+                    fg = srgb_to_linear(fg);
+                    fb = srgb_to_linear(fb);
+                }
+                const float l = opsin_bias(0.3f * fr + 0.622f * fg + 0.078f * fb);
+                const float m = opsin_bias(0.23f * fr + 0.692f * fg + 0.078f * fb);
+                const float s = opsin_bias(0.243423f * fr + 0.204767f * fg + 0.55181f * fb);
+                const float Y = (l + m) * 0.5f;
+                float *px = xyb + ((size_t)y * stride + x) * 3;
+                px[0] = Y - m;
+                px[1] = Y;
+                px[2] = s - Y;
+                continue;
+            }
             uint32_t r, g, b;
             if (t->sample_fmt == ORC_UINT8) {
                 r = in_lut[((const uint8_t *)t->plane[0])[o]];
@@ -1000,6 +1024,7 @@ static void stage_xyb(const OrcTile *t, uint32_t w, uint32_t h, uint32_t stride,
             px[2] = s - Y;
         }
     }
+    return 0;
 }
 
 /* 8-point transform in the reference's summation order (encoder.c:641-648) */
@@ -1267,7 +1292,7 @@ static void snapshot(const Bits *bw, uint8_t *dst, uint64_t cap, uint64_t *bitle
 
 int64_t orc_encode_tile(const OrcTile *t, uint8_t *dst, uint64_t cap, OrcStages *stages) {
     g_err = NULL;
-    if (t->sample_fmt != ORC_UINT8 && t->sample_fmt != ORC_UINT16)
+    if (t->sample_fmt != ORC_UINT8 && t->sample_fmt != ORC_UINT16 && t->sample_fmt != ORC_FLOAT32)
         FAIL(ORC_API_ERROR, "Invalid Sample Format");
     const uint64_t tiles_x = (t->image_width + 255) / 256, tiles_y = (t->image_height + 255) / 256;
     if (t->tile_x >= tiles_x || t->tile_y >= tiles_y)                                     /* encoder.c:448-451 */
@@ -1294,9 +1319,14 @@ int64_t orc_encode_tile(const OrcTile *t, uint8_t *dst, uint64_t cap, OrcStages 
         g_err = "out of memory";
         goto done;
     }
-    orc_build_luts(t->sample_fmt, t->linear_light, in_lut, bias_lut);
+    if (t->sample_fmt != ORC_FLOAT32)
+        orc_build_luts(t->sample_fmt, t->linear_light, in_lut, bias_lut);
 
-    stage_xyb(t, w, h, stride, rows, in_lut, bias_lut, xyb);
+    if (stage_xyb(t, w, h, stride, rows, in_lut, bias_lut, xyb) < 0) {
+        g_err = "Invalid NaN Float";
+        result = ORC_API_ERROR;
+        goto done;
+    }
     if (stages) {
         stages->vbw = vbw;
         stages->vbh = vbh;
@@ -1407,7 +1437,7 @@ int64_t orc_encode_image(const void *pixels, uint64_t width, uint64_t height, in
     int64_t n = orc_image_header(width, height, dst, cap);
     if (n < 0)
         return n;
-    const size_t item = sample_fmt == ORC_UINT8 ? 1 : 2;
+    const size_t item = sample_fmt == ORC_UINT8 ? 1 : (sample_fmt == ORC_UINT16 ? 2 : 4);
     const uint64_t tiles_x = (width + 255) / 256, tiles_y = (height + 255) / 256;
     for (uint64_t ty = 0; ty < tiles_y; ty++)
         for (uint64_t tx = 0; tx < tiles_x; tx++) {

@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 enum { ORC_OK = 0, ORC_NOMEM = -13, ORC_API_ERROR = -14, ORC_INTERNAL_ERROR = -15 };
-enum { ORC_UINT8 = 0, ORC_UINT16 = 1 };
+enum { ORC_UINT8 = 0, ORC_UINT16 = 1, ORC_FLOAT32 = 2 };
 
 /* One hybrid-uint coded symbol (reference: entropy.h:9-14). */
 typedef struct OrcSymbol {
@@ -61,7 +61,7 @@ typedef struct OrcTile {
     int      linear_light;
     uint32_t tile_x, tile_y;      /* in units of 256 px                                   */
     int      is_last;             /* <0: lower-right tile is last; else explicit           */
-    int      sample_fmt;          /* ORC_UINT8 / ORC_UINT16                               */
+    int      sample_fmt;          /* ORC_UINT8 / ORC_UINT16 / ORC_FLOAT32                 */
     const void *plane[3];         /* first R, G, B sample of the tile                      */
     ptrdiff_t row_stride, pixel_stride; /* in samples                                     */
 } OrcTile;

@@ -131,6 +131,14 @@ class Stages:
         return arr[:(n + 7) // 8].tobytes()
 
 
+def _sample_fmt(image: np.ndarray) -> int:
+    """HYDSampleFormat of a numpy image: uint8 -> 0, uint16 -> 1, float32 -> 2 (libhydrium.h:101-107)."""
+    try:
+        return {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[image.dtype]
+    except KeyError:
+        raise ValueError(f"unsupported sample type {image.dtype}") from None
+
+
 def _tile_args(image: np.ndarray, tx: int, ty: int, pixel_stride=None):
     h, w, ch = image.shape
     item = image.dtype.itemsize
@@ -179,7 +187,7 @@ class Oracle:
         t.image_width, t.image_height = (w, h) if image_size is None else image_size
         t.linear_light = linear_light
         t.tile_x, t.tile_y, t.is_last = tx, ty, is_last
-        t.sample_fmt = 0 if image.dtype == np.uint8 else 1
+        t.sample_fmt = _sample_fmt(image)
         t.plane = (C.c_void_p * 3)(*planes)
         t.row_stride, t.pixel_stride = rs, ps
         st = None
@@ -198,7 +206,7 @@ class Oracle:
         h, w, ch = image.shape
         cap = 64 + ((w + 255) // 256) * ((h + 255) // 256) * (1 << 20)
         out = np.zeros(min(cap, max(1 << 20, w * h * ch * 3 + (1 << 16))), np.uint8)
-        n = self.lib.orc_encode_image(image.ctypes.data, w, h, ch, 0 if image.dtype == np.uint8 else 1,
+        n = self.lib.orc_encode_image(image.ctypes.data, w, h, ch, _sample_fmt(image),
                                       linear_light, out.ctypes.data, out.nbytes)
         if n < 0:
             raise RuntimeError(f"oracle error {n}: {self.error()}")
@@ -272,7 +280,7 @@ class RefTap:
         n = C.c_uint64(0)
         arr = (C.c_void_p * 3)(*planes)
         ret = self.lib.hyd_tap_encode_tile(C.byref(md), arr, tx, ty, rs, ps, is_last,
-                                           0 if image.dtype == np.uint8 else 1, C.byref(st),
+                                           _sample_fmt(image), C.byref(st),
                                            out.ctypes.data, out.nbytes, C.byref(n))
         if ret < -10:
             raise RuntimeError(f"reference error {ret}")

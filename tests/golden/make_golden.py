@@ -19,6 +19,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from hydrium_b200.encoder import encode_cli_loop  # noqa: E402
 from hydrium_b200.synth import synth_image  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(HERE))
+from util import kat_image  # noqa: E402
 from oracle.pyoracle import ref_library  # noqa: E402
 
 # name, width, height, bits, linear, shift, smooth, seed
@@ -34,6 +37,9 @@ CASES = [
     ("L_260x300_u8_linear", 260, 300, 8, 1, 0, False, 2),
     ("T_40x24", 40, 24, 8, 0, 0, False, 0),
     ("Q_300x260", 300, 260, 8, 0, 0, False, 1),
+    # bits = 32: HYD_FLOAT32 samples, the 16-bit synthetic divided by 65535 in float32 (tests/util.py kat_image)
+    ("P_300x260_f32_srgb", 300, 260, 32, 0, 0, False, 5),
+    ("R_270x130_f32_linear", 270, 130, 32, 1, 0, False, 6),
     ("G_2304x2100_oneframe_ref_only", 2304, 2100, 8, 0, -1, False, 0),
     ("H_1024_tile512_ref_only", 1024, 1024, 8, 0, 1, False, 0),
 ]
@@ -54,7 +60,7 @@ def main():
     lib = ref_library("Os")
     table = {}
     for name, w, h, bits, lin, shift, smooth, seed in CASES:
-        img = synth_image(w, h, bits, seed=seed, smooth=smooth)
+        img = kat_image({"width": w, "height": h, "bits": bits, "seed": seed, "smooth": smooth})
         out = encode_cli_loop(lib, img, linear_light=lin, shift_x=shift, shift_y=shift)
         table[name] = {"width": w, "height": h, "bits": bits, "linear_light": lin, "shift": shift,
                        "smooth": smooth, "seed": seed,

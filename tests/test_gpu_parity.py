@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 from hydrium_b200 import engine as E
-from hydrium_b200.abi import HYD_UINT8, HYD_UINT16
-from hydrium_b200.encoder import HYDEncoder, encode_cli_loop, tile_grid
+from hydrium_b200.abi import HYD_API_ERROR, HYD_FLOAT32, HYD_NEED_MORE_OUTPUT, HYD_UINT8, HYD_UINT16
+from hydrium_b200.encoder import HYDEncoder, HydriumError, encode_cli_loop, tile_grid
 from hydrium_b200.lib import HydbTile
 from hydrium_b200.synth import synth_image
 from oracle.pyoracle import Stages
@@ -40,7 +40,7 @@ def _tile_desc(d_img, img, tx, ty, linear, image_size=None, origin=None):
     iw, ih = (w, h) if image_size is None else image_size
     t.image_width, t.image_height = iw, ih
     t.is_last = int((tx + 1) * 256 >= iw and (ty + 1) * 256 >= ih)
-    t.sample_fmt = HYD_UINT8 if img.dtype == np.uint8 else HYD_UINT16
+    t.sample_fmt = E._fmt_of(img)
     t.linear_light = linear
     return t
 
@@ -224,6 +224,51 @@ def test_sample_layouts(product_lib, oracle):
     b16 = rgba16.ctypes.data
     got = run(lambda tx, ty: tuple(b16 + ((ty * 256 * w + tx * 256) * 4 + c) * 2 for c in range(3)), w * 4, 4, HYD_UINT16)
     assert got == oracle.encode_image(img16), "rgba16 (the CLI's 16-bit layout, hydrium.c:445-449)"
+
+
+def test_float32_samples(product_lib, engine, oracle):
+    """HYD_FLOAT32 input (reference: format.c:111-140): golden known answers, the nine-symbol API in
+    packed-RGB and planar layouts, and the rejection of non-finite samples."""
+    t = kat_table()
+    for key in ("P_300x260_f32_srgb", "R_270x130_f32_linear"):
+        img = kat_image(t[key])
+        assert img.dtype == np.float32
+        out = engine.encode_image(img, linear_light=t[key]["linear_light"])
+        assert len(out) == t[key]["length"] and sha256(out) == t[key]["sha256"], key
+        assert encode_cli_loop(product_lib, img, linear_light=t[key]["linear_light"]) == out, key
+    img = kat_image(t["P_300x260_f32_srgb"])
+    want = oracle.encode_image(img)
+    planar = np.ascontiguousarray(img.transpose(2, 0, 1))            # three float planes
+    h, w, _ = img.shape
+    enc = HYDEncoder(product_lib)
+    out = bytearray()
+    obuf = np.empty(1 << 20, np.uint8)
+    enc.check(enc.set_metadata(w, h, 0, 0, 0))
+    enc.check(enc.provide_output_buffer(obuf))
+    for ty in range((h + 255) // 256):
+        for tx in range((w + 255) // 256):
+            base = planar.ctypes.data + (ty * 256 * w + tx * 256) * 4
+            enc.check(enc.send_tile(tuple(base + c * h * w * 4 for c in range(3)), tx, ty, w, 1, -1, HYD_FLOAT32))
+            while True:
+                ret = enc.flush()
+                _, written = enc.release_output_buffer()
+                out += obuf[:written].tobytes()
+                enc.check(enc.provide_output_buffer(obuf))
+                if ret != HYD_NEED_MORE_OUTPUT:
+                    break
+    enc.destroy()
+    assert bytes(out) == want
+    # a NaN or an infinity anywhere in a tile is refused with the reference's message
+    for poison in (np.nan, np.inf, -np.inf):
+        bad = img.copy()
+        bad[200, 17, 2] = poison
+        with pytest.raises(HydriumError) as ei:
+            encode_cli_loop(product_lib, bad)
+        assert ei.value.code == HYD_API_ERROR and ei.value.message == "Invalid NaN Float"
+        with pytest.raises(HydriumError) as ei:
+            engine.encode_image(bad)
+        assert ei.value.message == "Invalid NaN Float"
+    assert engine.encode_image(img) == want   # the engine is still usable afterwards
 
 
 def test_far_tiles_of_huge_images(engine, oracle):

@@ -15,7 +15,14 @@ def kat_table():
         return json.load(f)
 
 
+def float_image(width, height, seed=0, smooth=False):
+    """HYD_FLOAT32 test image: the 16-bit synthetic scaled to [0, 1] with one float32 division."""
+    return synth_image(width, height, 16, seed=seed, smooth=smooth).astype(np.float32) / np.float32(65535)
+
+
 def kat_image(entry):
+    if entry["bits"] == 32:
+        return float_image(entry["width"], entry["height"], seed=entry["seed"], smooth=entry["smooth"])
     return synth_image(entry["width"], entry["height"], entry["bits"], seed=entry["seed"], smooth=entry["smooth"])
 
 
@@ -44,4 +51,7 @@ def image_set(rng):
         ("smooth1000x300", synth_image(1000, 300, 8, smooth=True), 0),
         ("tiny1x1", synth_image(1, 1, 8), 0),
         ("thin257x3", synth_image(257, 3, 8, seed=4), 0),
+        ("float_srgb300x200", float_image(300, 200, seed=9), 0),
+        ("float_linear_noise", rng.random((90, 260, 3), dtype=np.float32), 1),
+        ("float_over_range", rng.random((40, 70, 3), dtype=np.float32) * np.float32(3.5), 1),
     ]
