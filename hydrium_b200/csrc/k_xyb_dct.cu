@@ -46,6 +46,12 @@ __device__ __forceinline__ float opsin_bias(float x) {
     return __fsub_rn(fast_cbrt(__fadd_rn(x, 0.0037930732552754493f)), 0.155954f);
 }
 
+// entry `idx` of the reference's bias table, computed instead of looked up (format.c:73-83)
+__device__ __forceinline__ float bias_entry(uint32_t idx) {
+    const float step16 = __fdiv_rn(1.0f, __fsub_rn(65536.0f, 1.0f));   // folded at compile time
+    return opsin_bias(__fmul_rn((float)idx, step16));
+}
+
 __global__ void k_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_srgb, uint16_t *lut16_lin,
                              float *bias) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,7 +60,7 @@ __global__ void k_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *
     const float step16 = __fdiv_rn(1.0f, __fsub_rn(65536.0f, 1.0f));
     const float f16 = __fmul_rn((float)i, step16);
     {
-        bias[i] = opsin_bias(f16);
+        bias[i] = bias_entry(i);   // kept for the table tap of the parity tests
     }
     auto to_u16 = [](float x) -> uint16_t {
         int v = __float2int_rz(__fadd_rn(__fmul_rn(x, 65535.f), 0.5f));
@@ -98,19 +104,46 @@ __device__ __forceinline__ void load_xyb(const TileDesc &t, const uint16_t *in_l
     const Sample *p0 = (const Sample *)t.plane[0];
     const Sample *p1 = (const Sample *)t.plane[1];
     const Sample *p2 = (const Sample *)t.plane[2];
+    // packed 8-bit RGB whose 24-byte block rows are word aligned (the usual case): six 32-bit loads
+    // per thread instead of twenty-four byte loads
+    uint32_t pk[6];
+    bool packed = false;
+    if (sizeof(Sample) == 1) {
+        packed = t.pixel_stride == 3 && p1 == p0 + 1 && p2 == p0 + 2 && px0 + 8 <= t.w && y < t.h &&
+                 (((uintptr_t)p0 | (uintptr_t)t.row_stride) & 3u) == 0;
+        if (packed) {
+            const uint32_t *q = (const uint32_t *)(p0 + (int64_t)y * t.row_stride + (int64_t)px0 * 3);
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                pk[k] = __ldg(q + k);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t px = px0 + i;
         float x = 0.0f, yy = 0.0f, b = 0.0f;   // zero padding of partial blocks (format.c:182-191)
         if (px < t.w && y < t.h) {
-            const int64_t o = (int64_t)y * t.row_stride + (int64_t)px * t.pixel_stride;
-            const uint32_t r = in_lut[__ldg(p0 + o)];
-            const uint32_t g = in_lut[__ldg(p1 + o)];
-            const uint32_t bl = in_lut[__ldg(p2 + o)];
-            // format.c:48-56
-            const float l = __ldg(bias + (((19661u * r + 40761u * g + 5112u * bl) >> 16) & 0xFFFFu));
-            const float m = __ldg(bias + (((15073u * r + 45350u * g + 5112u * bl) >> 16) & 0xFFFFu));
-            const float s = __ldg(bias + (((15953u * r + 13419u * g + 36163u * bl) >> 16) & 0xFFFFu));
+            uint32_t sr, sg, sb;
+            if (sizeof(Sample) == 1 && packed) {
+                sr = (pk[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 0xFFu;
+                sg = (pk[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 0xFFu;
+                sb = (pk[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 0xFFu;
+            } else {
+                const int64_t o = (int64_t)y * t.row_stride + (int64_t)px * t.pixel_stride;
+                sr = __ldg(p0 + o);
+                sg = __ldg(p1 + o);
+                sb = __ldg(p2 + o);
+            }
+            const uint32_t r = in_lut[sr];
+            const uint32_t g = in_lut[sg];
+            const uint32_t bl = in_lut[sb];
+            // format.c:48-56.  The reference reads bias_lut[idx]; entry idx of that table is
+            // opsin_bias((float)idx * (1 / 65535)) (format.c:73-83), which is recomputed here in
+            // registers: about thirty FP32 instructions instead of a 32-way scattered gather from a
+            // 256 KB table, which was half of this kernel's time (L1 wavefronts).
+            const float l = bias_entry(((19661u * r + 40761u * g + 5112u * bl) >> 16) & 0xFFFFu);
+            const float m = bias_entry(((15073u * r + 45350u * g + 5112u * bl) >> 16) & 0xFFFFu);
+            const float s = bias_entry(((15953u * r + 13419u * g + 36163u * bl) >> 16) & 0xFFFFu);
             yy = __fmul_rn(__fadd_rn(l, m), 0.5f);
             x = __fsub_rn(yy, m);
             b = __fsub_rn(s, yy);
