@@ -317,11 +317,13 @@ def run_ours(args) -> int:
         ans_ms = stages["ans_chain"] / nb
         b_in, b_out = float(n_in), float(out_bytes)
         achieved = (b_in + b_out) / (ans_ms / 1e3) / 1e9 if ans_ms > 0 else 0.0
-        traffic = None
+        traffic = xyb_traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_ans_chain_dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("k_ans_chain_dram_bytes_per_launch")
+            xyb_traffic = tj.get("k_xyb_dct_dram_bytes_per_launch")
         per_stage = {k: stages[k] / nb for k in ("xyb_dct_quant", "hf_tokens", "lf_group", "ans_chain", "ans_pack", "gather")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -337,7 +339,16 @@ def run_ours(args) -> int:
                          "algorithmic_bytes_per_launch": b_in + b_out,
                          "kernel_ms": ans_ms,
                          "hbm_read_roofline_frac_whole_step": (b_in / (ms_per_step / 1e3) / 1e9) / peak,
-                         "note": "latency-bound serial rANS chain per tile; see DESIGN.md"},
+                         "note": "serial rANS chain per tile, bound by in-order issue / dependent latency of one warp "
+                                 "(54.6 cycles per symbol, profiles/r01_chain_source_v3.txt); see DESIGN.md"},
+            # the stage the north star asks an HBM fraction for: RGB in, int16 coefficients out
+            "roofline_xyb_dct_quant": (lambda ms: {
+                "bound": "hbm", "kernel": "k_xyb_dct_quant", "achieved": b_in / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": b_in / (ms / 1e3) / 1e9 / peak, "traffic": xyb_traffic, "algorithmic_bytes_per_launch": b_in,
+                "kernel_ms": ms,
+                "note": "FP32 / issue bound (issue slots 82 % busy, profiles/r01b_ncu_summary.json): the format fixes the "
+                        "DCT's summation order, ~380 thread instructions per pixel"})(per_stage["xyb_dct_quant"])
+            if per_stage["xyb_dct_quant"] > 0 else None,
             "stages_ms": per_stage,
             "xyb_dct_quant_gbs": (b_in / (per_stage["xyb_dct_quant"] / 1e3) / 1e9) if per_stage["xyb_dct_quant"] > 0 else None,
             "cpu_baseline": cpu_baseline,
