@@ -232,28 +232,9 @@ k_ans_chain(Workspace ws) {
             s.inv[c * kAnsTotal + s.cl[c].cum[sym] + off] = (uint16_t)slot;
         }
     }
-    // ---- 2. section D -------------------------------------------------------------------------
-    if (tid == 0) {
-        BitSink bw;
-        bw.init(s.dbits, kDBitsWords);
-        bw.put_bool(0);                               // use_prefix_codes = 0
-        bw.put((uint32_t)(log_alpha - 5), 2);
-        for (int c = 0; c < kHfClusters; c++)
-            ps_put_hybrid_cfg(bw, 4, 1, 0, log_alpha);
-        for (int c = 0; c < kHfClusters; c++)
-            ans_put_histogram(bw, s.cl[c].freq, s.alpha[c]);
-        bw.flush_partial();
-        s.dbitlen = bw.bitlen();
-        if (bw.overflow)
-            s.err |= kErrSlab;
-    }
+    // (section D is written further down by a third warp, while the chain is already running)
     __syncthreads();
     const bool sane = !s.err && N > 0 && log_alpha <= 6;
-    {
-        const uint32_t words = (s.dbitlen + 31) >> 5;
-        for (uint32_t i = tid; i < words && i < (uint32_t)kDBitsWords; i += kAnsThreads)
-            ws.dbits[(size_t)tile * kDBitsWords + i] = s.dbits[i];
-    }
     // Two warps stay: the CHAIN warp runs nothing but the state recurrence; a HELPER warp feeds it
     // staged per-symbol records through a small shared-memory ring and drains the states it leaves
     // behind (renormalisation flags / words).  Co-resident CTAs put their chain warps on different
@@ -276,14 +257,37 @@ k_ans_chain(Workspace ws) {
     if (s.chain_warp == 0xFFFFFFFFu && tid == 0)
         s.chain_warp = 0;
     __syncthreads();
-    const uint32_t chain_warp = s.chain_warp, helper_warp = chain_warp ^ 1u;
+    const uint32_t chain_warp = s.chain_warp, helper_warp = chain_warp ^ 1u, header_warp = chain_warp ^ 2u;
+    if (warp == header_warp) {
+        // ---- 2. section D: only the packer needs it, so it is written off the chain's path ---------
+        if (lane == 0) {
+            BitSink bw;
+            bw.init(s.dbits, kDBitsWords);
+            bw.put_bool(0);                               // use_prefix_codes = 0
+            bw.put((uint32_t)(log_alpha - 5), 2);
+            for (int c = 0; c < kHfClusters; c++)
+                ps_put_hybrid_cfg(bw, 4, 1, 0, log_alpha);
+            for (int c = 0; c < kHfClusters; c++)
+                ans_put_histogram(bw, s.cl[c].freq, s.alpha[c]);
+            bw.flush_partial();
+            s.dbitlen = bw.bitlen();
+            if (bw.overflow)
+                atomicOr(&ws.tile_err[tile], (uint32_t)kErrSlab);
+        }
+        __syncwarp();
+        const uint32_t words = (s.dbitlen + 31) >> 5;
+        for (uint32_t i = lane; i < words && i < (uint32_t)kDBitsWords; i += 32)
+            ws.dbits[(size_t)tile * kDBitsWords + i] = s.dbits[i];
+        if (lane == 0)
+            ws.chain_out[tile * 4 + 2] = s.dbitlen;
+        return;
+    }
     if (warp != chain_warp && warp != helper_warp)
         return;   // the remaining warps have nothing to do while the chain runs
     if (!sane) {
         if (warp == chain_warp && lane == 0) {
             ws.chain_out[tile * 4 + 0] = 0;
             ws.chain_out[tile * 4 + 1] = 0;
-            ws.chain_out[tile * 4 + 2] = s.dbitlen;
             ws.chain_out[tile * 4 + 3] = s.err ? s.err : (uint32_t)kErrAlphabet;
         }
         return;
@@ -362,7 +366,6 @@ k_ans_chain(Workspace ws) {
             gap_err = 1;   // the reference keeps this distance in a uint16_t (entropy.c:16, 1094, 1123)
         if (lane == 0) {
             ws.chain_out[tile * 4 + 0] = cnt;
-            ws.chain_out[tile * 4 + 2] = s.dbitlen;
             ws.chain_out[tile * 4 + 3] = gap_err ? (uint32_t)kErrAnsGap : 0u;
         }
     } else {
