@@ -49,7 +49,8 @@ struct HydbEngine {
     static constexpr int kBands = 4;
     cudaStream_t band_st[kBands] = {nullptr, nullptr, nullptr, nullptr}, band_st2[kBands] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t band_front[kBands] = {nullptr, nullptr, nullptr, nullptr}, band_lf[kBands] = {nullptr, nullptr, nullptr, nullptr},
-                band_done[kBands] = {nullptr, nullptr, nullptr, nullptr};
+                band_done[kBands] = {nullptr, nullptr, nullptr, nullptr}, band_h2d[kBands] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_st = nullptr;   // host path: the bands' pixels cross PCIe on ONE stream, in band order
     cudaEvent_t ev_desc = nullptr;
     // grow-only device buffers behind hydb_encode_image_host
     void *host_in = nullptr;
@@ -128,6 +129,7 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     // band 0 go before the front-end CTAs of later bands, so the first (3 ms long) chains start early
     int prio_least = 0, prio_greatest = 0;
     A(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    A(cudaStreamCreateWithPriority(&eng->copy_st, cudaStreamNonBlocking, prio_greatest));
     for (int b = 0; b < HydbEngine::kBands; b++) {
         const int prio = prio_greatest + b < prio_least ? prio_greatest + b : prio_least;
         A(cudaStreamCreateWithPriority(&eng->band_st[b], cudaStreamNonBlocking, prio));
@@ -135,6 +137,7 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
         A(cudaEventCreateWithFlags(&eng->band_front[b], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&eng->band_lf[b], cudaEventDisableTiming));
         A(cudaEventCreateWithFlags(&eng->band_done[b], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&eng->band_h2d[b], cudaEventDisableTiming));
     }
     A(dalloc(&w.tiles, T));
     A(dalloc(&w.coef, T * kMaxBlocks * 3 * 64));
@@ -205,11 +208,13 @@ void hydb_engine_destroy(HydbEngine *eng) {
     for (void *p : dev)
         if (p) cudaFree(p);
     for (int b = 0; b < HydbEngine::kBands; b++) {
+        if (b == 0 && eng->copy_st) cudaStreamDestroy(eng->copy_st);
         if (eng->band_st[b]) cudaStreamDestroy(eng->band_st[b]);
         if (eng->band_st2[b]) cudaStreamDestroy(eng->band_st2[b]);
         if (eng->band_front[b]) cudaEventDestroy(eng->band_front[b]);
         if (eng->band_lf[b]) cudaEventDestroy(eng->band_lf[b]);
         if (eng->band_done[b]) cudaEventDestroy(eng->band_done[b]);
+        if (eng->band_h2d[b]) cudaEventDestroy(eng->band_h2d[b]);
     }
     if (eng->ev_desc) cudaEventDestroy(eng->ev_desc);
     if (eng->host_in) cudaFree(eng->host_in);
@@ -511,16 +516,26 @@ static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t ro
     if (trace) cudaEventRecord(tr[0], eng->st);
     CK(cudaEventRecord(eng->ev_desc, eng->st));
     const uint32_t nbands = rows < (uint32_t)HydbEngine::kBands ? rows : (uint32_t)HydbEngine::kBands;
+    if (h_src) {
+        // all copies first, on one stream: they reach the device in band order at full PCIe rate, and
+        // every band's kernels wait only for their own rows (separate per-band copies were served in
+        // an order of the copy engine's choosing, the heavy first bands not first)
+        CK(cudaStreamWaitEvent(eng->copy_st, eng->ev_desc, 0));
+        for (uint32_t b = 0; b < nbands; b++) {
+            const uint32_t r0 = (uint32_t)((uint64_t)rows * b / nbands), r1 = (uint32_t)((uint64_t)rows * (b + 1) / nbands);
+            const size_t y0 = (size_t)r0 * 256, y1 = (size_t)r1 * 256 < pixel_rows ? (size_t)r1 * 256 : pixel_rows;
+            CK(cudaMemcpyAsync((uint8_t *)d_dst + y0 * row_bytes, (const uint8_t *)h_src + y0 * row_bytes,
+                               (y1 - y0) * row_bytes, cudaMemcpyHostToDevice, eng->copy_st));
+            CK(cudaEventRecord(eng->band_h2d[b], eng->copy_st));
+        }
+    }
     for (uint32_t b = 0; b < nbands; b++) {
         const uint32_t r0 = (uint32_t)((uint64_t)rows * b / nbands), r1 = (uint32_t)((uint64_t)rows * (b + 1) / nbands);
         const uint32_t first = r0 * tiles_x, n = (r1 - r0) * tiles_x;
         cudaStream_t sb = eng->band_st[b], sb2 = eng->band_st2[b];
         CK(cudaStreamWaitEvent(sb, eng->ev_desc, 0));
-        if (h_src) {
-            const size_t y0 = (size_t)r0 * 256, y1 = (size_t)r1 * 256 < pixel_rows ? (size_t)r1 * 256 : pixel_rows;
-            CK(cudaMemcpyAsync((uint8_t *)d_dst + y0 * row_bytes, (const uint8_t *)h_src + y0 * row_bytes,
-                               (y1 - y0) * row_bytes, cudaMemcpyHostToDevice, sb));
-        }
+        if (h_src)
+            CK(cudaStreamWaitEvent(sb, eng->band_h2d[b], 0));
         const Workspace v = ws_view(eng->ws, first);
         if (trace) cudaEventRecord(tr[1 + b * 5 + 0], sb);
         launch_xyb_dct_quant(v, eng->luts, n, sb);
