@@ -60,6 +60,15 @@ struct TileDesc {
     uint32_t flags;           // kTile* below
     uint32_t shape;           // index of the (vbw, vbh) template set
     uint32_t image_w, image_h;   // only read when kTileFirst is set
+    // frames with more than one 256x256 group (tile_size_shift > 0, one-frame mode): the frame takes
+    // 1 + G consecutive workspace slots, a PREFIX pseudo-tile (frame header, TOC, LFGlobal, LFGroup,
+    // HFGlobal) followed by its G groups in raster order; zero for classic one-group frames
+    uint32_t frame_groups;    // G
+    uint32_t frame_gx;        // groups per frame row
+    uint32_t group_index;     // raster index of this group inside the frame
+    uint32_t frame_w, frame_h;   // frame size in pixels
+    uint32_t frame_x0, frame_y0; // frame origin inside the image (crop offset)
+    uint32_t pad_;
 };
 enum : uint32_t {
     kTileLast = 1u << 0,      // is_last frame (reference: encoder.c:482-485)
@@ -68,6 +77,9 @@ enum : uint32_t {
     kTileLinear = 1u << 3,    // linear-light input
     kTileFirst = 1u << 4,     // first frame of a codestream: the image header goes in front of it
     kTileFmtF32 = 1u << 5,    // HYD_FLOAT32 samples (reference: format.c:111-140)
+    kTilePrefix = 1u << 6,    // pseudo-tile holding the shared sections of a multi-group frame
+    kTileMulti = 1u << 7,     // group of a multi-group frame: its slab carries only the PassGroup section
+    kTileOneFrame = 1u << 8,  // one-frame mode header flavour: no crop, always last (encoder.c:339-342)
 };
 
 // ---- integer helpers (reference: math-functions.h:8-88) ----------------------------------

@@ -304,7 +304,14 @@ static Workspace ws_view(const Workspace &w, uint32_t first) {
 }
 
 // validate + translate the caller's tiles, build templates for new shapes, upload the descriptors
-static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, cudaStream_t st) {
+// per-slot additions for multi-group frames (see TileDesc in common.cuh)
+struct SlotExtra {
+    uint32_t flags;
+    uint32_t frame_groups, frame_gx, group_index, frame_w, frame_h, frame_x0, frame_y0;
+};
+
+static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, cudaStream_t st,
+                                   const SlotExtra *extra = nullptr) {
     std::vector<uint32_t> fresh;
     const uint32_t first_fresh = (uint32_t)eng->shapes.size();
     eng->h_tiles.resize(n);
@@ -337,6 +344,18 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
                   ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
                   (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.sample_fmt == HYD_FLOAT32 ? kTileFmtF32 : 0u) |
                   (s.linear_light ? kTileLinear : 0u);
+        d.frame_groups = d.frame_gx = d.group_index = d.frame_w = d.frame_h = d.frame_x0 = d.frame_y0 = d.pad_ = 0;
+        if (extra) {
+            const SlotExtra &e = extra[i];
+            d.flags |= e.flags;
+            d.frame_groups = e.frame_groups;
+            d.frame_gx = e.frame_gx;
+            d.group_index = e.group_index;
+            d.frame_w = e.frame_w;
+            d.frame_h = e.frame_h;
+            d.frame_x0 = e.frame_x0;
+            d.frame_y0 = e.frame_y0;
+        }
     }
     if (!fresh.empty()) {
         std::vector<uint32_t> dims;
@@ -403,6 +422,121 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     eng->timed_pending = tm;
     eng->launches += 7;
     return queue_readback(eng, n, d_out_pos);
+}
+
+// Frames of up to 8 x 8 groups.  A frame of one group is an ordinary tile; a larger one becomes a
+// prefix pseudo-tile plus its groups (k_frame.cu).
+HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames, uint32_t n, uint8_t *d_out,
+                                        uint64_t d_out_cap, uint64_t d_out_pos) {
+    if (!eng || !frames || !n || !d_out) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_encode_frames";
+        return HYD_API_ERROR;
+    }
+    std::vector<HydbTile> tiles;
+    std::vector<SlotExtra> extra;
+    bool any_multi = false;
+    for (uint32_t f = 0; f < n; f++) {
+        const HydbFrame &fr = frames[f];
+        if (!fr.width || !fr.height || fr.width > 2048 || fr.height > 2048 || (fr.x0 & 255) || (fr.y0 & 255) ||
+            (fr.sample_fmt != HYD_UINT8 && fr.sample_fmt != HYD_UINT16 && fr.sample_fmt != HYD_FLOAT32) ||
+            !fr.plane[0] || !fr.plane[1] || !fr.plane[2]) {
+            eng->error = "invalid frame descriptor";
+            return HYD_API_ERROR;
+        }
+        const uint32_t gx = (fr.width + 255) >> 8, gy = (fr.height + 255) >> 8, G = gx * gy;
+        const size_t item = sample_item_bytes(fr.sample_fmt);
+        HydbTile t;
+        memset(&t, 0, sizeof(t));
+        t.row_stride = fr.row_stride;
+        t.pixel_stride = fr.pixel_stride;
+        t.image_width = fr.image_width;
+        t.image_height = fr.image_height;
+        t.is_last = fr.is_last;
+        t.sample_fmt = fr.sample_fmt;
+        t.linear_light = fr.linear_light;
+        SlotExtra e;
+        memset(&e, 0, sizeof(e));
+        if (G == 1) {   // single section: the classic path (encoder.c:992-1004)
+            for (int k = 0; k < 3; k++) t.plane[k] = fr.plane[k];
+            t.width = fr.width;
+            t.height = fr.height;
+            t.x0 = fr.x0;
+            t.y0 = fr.y0;
+            t.with_image_header = fr.with_image_header;
+            if (fr.one_frame) {
+                // one-frame mode, image inside one group: no crop, last (what hyd_api.c did so far)
+                t.is_last = 1;
+            }
+            tiles.push_back(t);
+            extra.push_back(e);
+            continue;
+        }
+        any_multi = true;
+        e.frame_groups = G;
+        e.frame_gx = gx;
+        e.frame_w = fr.width;
+        e.frame_h = fr.height;
+        e.frame_x0 = fr.x0;
+        e.frame_y0 = fr.y0;
+        // prefix pseudo-tile
+        HydbTile p = t;
+        for (int k = 0; k < 3; k++) p.plane[k] = fr.plane[k];
+        p.width = p.height = 8;
+        p.x0 = p.y0 = 0;
+        p.with_image_header = fr.with_image_header;
+        SlotExtra pe = e;
+        pe.flags = kTilePrefix | (fr.one_frame ? kTileOneFrame : 0u);
+        pe.group_index = 0xFFFFFFFFu;
+        tiles.push_back(p);
+        extra.push_back(pe);
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t cx = g % gx, cy = g / gx;
+            HydbTile q = t;
+            for (int k = 0; k < 3; k++)
+                q.plane[k] = (const uint8_t *)fr.plane[k] +
+                             ((int64_t)cy * 256 * fr.row_stride + (int64_t)cx * 256 * fr.pixel_stride) * (int64_t)item;
+            q.width = fr.width - cx * 256 < 256 ? fr.width - cx * 256 : 256;
+            q.height = fr.height - cy * 256 < 256 ? fr.height - cy * 256 : 256;
+            q.x0 = fr.x0 + cx * 256;
+            q.y0 = fr.y0 + cy * 256;
+            q.with_image_header = 0;
+            SlotExtra ge = e;
+            ge.flags = kTileMulti;
+            ge.group_index = g;
+            tiles.push_back(q);
+            extra.push_back(ge);
+        }
+    }
+    const uint32_t slots = (uint32_t)tiles.size();
+    if (slots > eng->max_batch) {
+        eng->error = "frames need more workspace slots than the engine's batch size";
+        return HYD_API_ERROR;
+    }
+    if (!any_multi)
+        return hydb_engine_encode_tiles(eng, tiles.data(), slots, d_out, d_out_cap, d_out_pos);
+    CK(cudaSetDevice(eng->device));
+    cudaStream_t st = eng->st;
+    {
+        const HYDStatusCode rc = prepare_tiles(eng, tiles.data(), slots, st, extra.data());
+        if (rc != HYD_OK)
+            return rc;
+    }
+    launch_xyb_dct_quant(eng->ws, eng->luts, slots, st);
+    CK(cudaEventRecord(eng->ev_front, st));
+    CK(cudaStreamWaitEvent(eng->st2, eng->ev_front, 0));
+    launch_lf_group(eng->ws, slots, eng->st2);   // classic single-group frames in the same batch
+    launch_frame_lf(eng->ws, slots, eng->st2);
+    CK(cudaEventRecord(eng->ev_lf, eng->st2));
+    launch_hf_tokens(eng->ws, slots, st);
+    launch_frame_hist_sum(eng->ws, slots, st);
+    launch_ans_chain(eng->ws, slots, st);
+    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));
+    launch_ans_pack(eng->ws, eng->templ, slots, st);
+    launch_frame_finish(eng->ws, slots, st);
+    launch_gather(eng->ws, slots, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    eng->timed_pending = false;
+    eng->launches += 10;
+    return queue_readback(eng, slots, d_out_pos);
 }
 
 HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {

@@ -43,8 +43,9 @@ HDN inline uint32_t put_level10_prefix(uint8_t *dst) {
     return 49;
 }
 
-// Frame header of one 256x256-group frame, byte aligned at both ends.
-HDN inline void put_frame_header(BitSink &bw, bool crop, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool last) {
+// Frame header up to (not including) the TOC-permutation flag (encoder.c:327-398).
+HDN inline void put_frame_header_fields(BitSink &bw, bool crop, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h,
+                                        bool last) {
     const U32Dist kFrameSize = {{0, 256, 2304, 18688}, {8, 11, 14, 30}};   // encoder.c:102-105
     bw.put(0, 1);                  // all_default = 0
     bw.put(last ? 0u : 3u, 2);     // regular frame / skip-progressive
@@ -70,13 +71,23 @@ HDN inline void put_frame_header(BitSink &bw, bool crop, uint32_t x0, uint32_t y
     bw.put(0, 2);                  // epf_iters
     bw.put(0, 2);                  // extensions
     bw.put(0, 2);                  // frame header extensions
+}
+
+// Frame header of one 256x256-group frame, byte aligned at both ends.
+HDN inline void put_frame_header(BitSink &bw, bool crop, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, bool last) {
+    put_frame_header_fields(bw, crop, x0, y0, w, h, last);
     bw.put_bool(0);                // TOC not permuted (single section)
     bw.align_byte();
 }
 
-HDN inline bool put_toc_entry(BitSink &bw, uint32_t payload_bytes) {
+// one TOC entry, no alignment (multi-section frames write several back to back, encoder.c:996-1001)
+HDN inline bool put_toc_value(BitSink &bw, uint32_t section_bytes) {
     const U32Dist kToc = {{0, 1024, 17408, 4211712}, {10, 14, 22, 30}};    // encoder.c:117-120
-    const bool ok = put_u32(bw, kToc, payload_bytes);
+    return put_u32(bw, kToc, section_bytes);
+}
+
+HDN inline bool put_toc_entry(BitSink &bw, uint32_t payload_bytes) {
+    const bool ok = put_toc_value(bw, payload_bytes);
     bw.align_byte();
     return ok;
 }

@@ -33,6 +33,8 @@ struct HYDEncoder {
     HYDImageMetadata metadata;
     int have_metadata;
     int one_frame;
+    uint32_t tile_w, tile_h;        /* pixels one hyd_send_tile covers (2048 in one-frame mode) */
+    uint32_t groups_per_tile;       /* 256x256 groups in a full tile: > 1 means multi-group frames */
     const char *error;
 
     /* lent output buffer (libhydrium.c:114-145) */
@@ -50,7 +52,9 @@ struct HYDEncoder {
     int device;
     uint32_t batch;
     HydbEngine *engine;
-    uint8_t *stage_host;   /* page-locked, batch * TILE_STAGE_BYTES */
+    uint32_t slots;        /* engine workspace slots: max(batch, 1 + groups_per_tile) */
+    size_t stage_cap;      /* bytes of each staging buffer */
+    uint8_t *stage_host;   /* page-locked */
     uint8_t *stage_dev;
     uint8_t *out_dev;      /* batch * TILE_OUT_BYTES */
     HydbTile *tiles;
@@ -66,11 +70,12 @@ struct HYDEncoder {
 static struct {
     pthread_mutex_t lock;
     int valid, device;
-    uint32_t batch;
+    uint32_t batch, slots;
+    size_t stage_cap;
     HydbEngine *engine;
     uint8_t *stage_host, *stage_dev, *out_dev;
     HydbTile *tiles;
-} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
+} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
 
 static uint32_t env_u32(const char *name, uint32_t fallback) {
     const char *v = getenv(name);
@@ -100,6 +105,8 @@ static void release_gpu(HYDEncoder *enc) {
             g_parked.valid = 1;
             g_parked.device = enc->device;
             g_parked.batch = enc->batch;
+            g_parked.slots = enc->slots;
+            g_parked.stage_cap = enc->stage_cap;
             g_parked.engine = enc->engine;
             g_parked.stage_host = enc->stage_host;
             g_parked.stage_dev = enc->stage_dev;
@@ -172,13 +179,20 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMet
         return HYD_API_ERROR;
     }
     const int one_frame = md->tile_size_shift_x < 0 || md->tile_size_shift_y < 0;
-    if (one_frame ? (w > TILE || h > TILE) : (md->tile_size_shift_x != 0 || md->tile_size_shift_y != 0)) {
-        /* multi-group frames are outside this library's accelerated path (scope) */
-        enc->error = "tile size not supported by the B200 encoder (use tile_size_shift 0/0)";
+    if (one_frame && (w > 2048 || h > 2048)) {
+        /* several LF groups in one frame (shared histograms per preset, permuted TOC) are not built yet */
+        enc->error = "one-frame mode is limited to 2048x2048 in the B200 encoder (use tile_size_shift 0..3)";
         return HYD_API_ERROR;
     }
     enc->metadata = *md;
     enc->one_frame = one_frame;
+    /* libhydrium.c:99-100, encoder.c:441-446 */
+    enc->tile_w = one_frame ? 2048u : (TILE << md->tile_size_shift_x);
+    enc->tile_h = one_frame ? 2048u : (TILE << md->tile_size_shift_y);
+    {
+        const uint64_t fw = w < enc->tile_w ? w : enc->tile_w, fh = h < enc->tile_h ? h : enc->tile_h;
+        enc->groups_per_tile = (uint32_t)(((fw + TILE - 1) / TILE) * ((fh + TILE - 1) / TILE));
+    }
     enc->have_metadata = 1;
     return HYD_OK;
 }
@@ -278,7 +292,12 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
     if (enc->engine)
         return HYD_OK;
     pthread_mutex_lock(&g_parked.lock);
-    if (g_parked.valid && g_parked.device == enc->device && g_parked.batch == enc->batch) {
+    enc->slots = enc->groups_per_tile > 1 && enc->batch < 1 + enc->groups_per_tile ? 1 + enc->groups_per_tile : enc->batch;
+    enc->stage_cap = (size_t)enc->batch * TILE_STAGE_BYTES;
+    if (enc->groups_per_tile > 1 && enc->stage_cap < (size_t)enc->tile_w * enc->tile_h * 16u)
+        enc->stage_cap = (size_t)enc->tile_w * enc->tile_h * 16u;   /* one whole tile, RGBA float */
+    if (g_parked.valid && g_parked.device == enc->device && g_parked.batch == enc->batch &&
+        g_parked.slots == enc->slots && g_parked.stage_cap == enc->stage_cap) {
         g_parked.valid = 0;
         enc->engine = g_parked.engine;
         enc->stage_host = g_parked.stage_host;
@@ -289,15 +308,15 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
     pthread_mutex_unlock(&g_parked.lock);
     if (enc->engine)
         return HYD_OK;
-    HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->batch);
+    HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->slots);
     if (rc < HYD_ERROR_START) {
         enc->error = "could not create the CUDA engine (no usable GPU? this encoder has no CPU path)";
         return rc;
     }
-    enc->stage_host = hydb_host_alloc((size_t)enc->batch * TILE_STAGE_BYTES);
-    enc->stage_dev = hydb_device_alloc((size_t)enc->batch * TILE_STAGE_BYTES);
-    enc->out_dev = hydb_device_alloc((size_t)enc->batch * TILE_OUT_BYTES);
-    enc->tiles = calloc(enc->batch, sizeof(HydbTile));
+    enc->stage_host = hydb_host_alloc(enc->stage_cap);
+    enc->stage_dev = hydb_device_alloc(enc->stage_cap);
+    enc->out_dev = hydb_device_alloc((size_t)enc->slots * TILE_OUT_BYTES);
+    enc->tiles = calloc(enc->slots, sizeof(HydbTile));
     if (!enc->stage_host || !enc->stage_dev || !enc->out_dev || !enc->tiles) {
         release_gpu(enc);
         enc->error = "out of memory allocating tile staging";
@@ -313,7 +332,7 @@ static HYDStatusCode run_batch(HYDEncoder *enc) {
     if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
     HYDStatusCode rc = hydb_engine_encode_tiles(enc->engine, enc->tiles, enc->queued, enc->out_dev,
-                                                (uint64_t)enc->batch * TILE_OUT_BYTES, 0);
+                                                (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
     if (rc < HYD_ERROR_START)
         return gpu_error(enc, rc);
     uint64_t bytes = 0;
@@ -332,12 +351,13 @@ static HYDStatusCode run_batch(HYDEncoder *enc) {
 }
 
 /* copy one tile's samples into staging and fill its device-side descriptor */
-static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3], ptrdiff_t row_stride,
-                       ptrdiff_t pixel_stride, size_t item) {
+static void stage_pixels(HYDEncoder *enc, uint32_t w, uint32_t h, const void **plane, int64_t *out_row_stride,
+                         int64_t *out_pixel_stride, const void *const buffer[3], ptrdiff_t row_stride,
+                         ptrdiff_t pixel_stride, size_t item) {
+    struct { const void *plane[3]; int64_t row_stride, pixel_stride; } tt, *t = &tt;
     uint8_t *dst = enc->stage_host + enc->stage_used;
     uint8_t *ddst = enc->stage_dev + enc->stage_used;
     const uint8_t *p[3] = {buffer[0], buffer[1], buffer[2]};
-    const uint32_t w = t->width, h = t->height;
     const uint8_t *lo = p[0] < p[1] ? (p[0] < p[2] ? p[0] : p[2]) : (p[1] < p[2] ? p[1] : p[2]);
     const uint8_t *hi = p[0] > p[1] ? (p[0] > p[2] ? p[0] : p[2]) : (p[1] > p[2] ? p[1] : p[2]);
     size_t used;
@@ -379,6 +399,38 @@ static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3]
         used = (size_t)w * h * 3 * item;
     }
     enc->stage_used += (used + 255) & ~(size_t)255;
+    for (int k = 0; k < 3; k++)
+        plane[k] = tt.plane[k];
+    *out_row_stride = tt.row_stride;
+    *out_pixel_stride = tt.pixel_stride;
+}
+
+static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3], ptrdiff_t row_stride,
+                       ptrdiff_t pixel_stride, size_t item) {
+    stage_pixels(enc, t->width, t->height, t->plane, &t->row_stride, &t->pixel_stride, buffer, row_stride, pixel_stride,
+                 item);
+}
+
+/* a tile of several 256x256 groups: one frame with shared sections (k_frame.cu), encoded at once */
+static HYDStatusCode run_frame(HYDEncoder *enc, HydbFrame *fr) {
+    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    HYDStatusCode rc = hydb_engine_encode_frames(enc->engine, fr, 1, enc->out_dev,
+                                                 (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
+    if (rc < HYD_ERROR_START)
+        return gpu_error(enc, rc);
+    uint64_t bytes = 0;
+    rc = hydb_engine_finish(enc->engine, &bytes);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    rc = pend_reserve(enc, (size_t)bytes);
+    if (rc < HYD_ERROR_START)
+        return rc;
+    if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    enc->pend_len += (size_t)bytes;
+    enc->stage_used = 0;
+    return HYD_OK;
 }
 
 HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const buffer[3], uint32_t tile_x,
@@ -395,25 +447,48 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     }
     /* encoder.c:437-472: bounds and the tile's real size */
     const uint64_t W = enc->metadata.width, H = enc->metadata.height;
-    const uint64_t span = enc->one_frame ? 2048 : TILE;
-    if (tile_x >= (W + span - 1) / span || tile_y >= (H + span - 1) / span) {
+    const uint64_t span_x = enc->tile_w, span_y = enc->tile_h;
+    if (tile_x >= (W + span_x - 1) / span_x || tile_y >= (H + span_y - 1) / span_y) {
         enc->error = "tile out of bounds";
         return HYD_API_ERROR;
     }
     HYDStatusCode rc = ensure_gpu(enc);
     if (rc < HYD_ERROR_START)
         return rc;
-    const uint32_t tw = (uint32_t)(((uint64_t)tile_x + 1) * span > W ? W - (uint64_t)tile_x * span : span);
-    const uint32_t th = (uint32_t)(((uint64_t)tile_y + 1) * span > H ? H - (uint64_t)tile_y * span : span);
+    const uint32_t tw = (uint32_t)(((uint64_t)tile_x + 1) * span_x > W ? W - (uint64_t)tile_x * span_x : span_x);
+    const uint32_t th = (uint32_t)(((uint64_t)tile_y + 1) * span_y > H ? H - (uint64_t)tile_y * span_y : span_y);
     /* encoder.c:482-485 */
-    enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span >= W && ((uint64_t)tile_y + 1) * span >= H) : !!is_last;
+    enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span_x >= W && ((uint64_t)tile_y + 1) * span_y >= H) : !!is_last;
+    const size_t item = sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4);
+    if (tw > TILE || th > TILE) {
+        /* several groups in this frame: everything queued so far goes first, then the frame at once */
+        rc = run_batch(enc);
+        if (rc < HYD_ERROR_START)
+            return rc;
+        HydbFrame fr;
+        memset(&fr, 0, sizeof(fr));
+        fr.width = tw;
+        fr.height = th;
+        fr.x0 = tile_x * enc->tile_w;
+        fr.y0 = tile_y * enc->tile_h;
+        fr.image_width = (uint32_t)W;
+        fr.image_height = (uint32_t)H;
+        fr.is_last = enc->one_frame || enc->last_tile;
+        fr.sample_fmt = sample_fmt;
+        fr.linear_light = enc->metadata.linear_light != 0;
+        fr.with_image_header = !enc->wrote_header;
+        fr.one_frame = enc->one_frame;
+        enc->wrote_header = 1;
+        stage_pixels(enc, tw, th, fr.plane, &fr.row_stride, &fr.pixel_stride, buffer, row_stride, pixel_stride, item);
+        return run_frame(enc, &fr);
+    }
 
     HydbTile *t = &enc->tiles[enc->queued];
     memset(t, 0, sizeof(*t));
     t->width = tw;
     t->height = th;
-    t->x0 = tile_x * TILE;
-    t->y0 = tile_y * TILE;
+    t->x0 = tile_x * enc->tile_w;
+    t->y0 = tile_y * enc->tile_h;
     t->image_width = (uint32_t)W;
     t->image_height = (uint32_t)H;
     t->is_last = enc->one_frame || enc->last_tile; /* encoder.c:339 */
@@ -421,8 +496,7 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     t->linear_light = enc->metadata.linear_light != 0;
     t->with_image_header = !enc->wrote_header; /* encoder.c:490-494: the image header precedes the first frame */
     enc->wrote_header = 1;
-    stage_tile(enc, t, buffer, row_stride, pixel_stride,
-               sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4));
+    stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
     enc->queued++;
 
     if (enc->queued == enc->batch || enc->last_tile) {

@@ -169,6 +169,8 @@ k_ans_chain(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AnsShared &s = *reinterpret_cast<AnsShared *>(smem_raw);
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (ws.tiles[tile].flags & kTilePrefix)   // pseudo-tile of a multi-group frame (k_frame.cu)
+        return;
     const uint32_t N = ws.nsyms[tile];
     const uint32_t *__restrict__ sy = ws.syms + (size_t)tile * kMaxHfSyms;
     uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
@@ -486,6 +488,9 @@ k_ans_pack(Workspace ws, Templates tp) {
     __shared__ PackShared s;
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
     const TileDesc t = ws.tiles[tile];
+    if (t.flags & kTilePrefix)   // pseudo-tile of a multi-group frame: filled by k_frame_finish
+        return;
+    const bool multi = (t.flags & kTileMulti) != 0;   // group of a multi-group frame: PassGroup section only
     const uint32_t N = ws.nsyms[tile];
     const uint32_t *__restrict__ sy = ws.syms + (size_t)tile * kMaxHfSyms;
     const uint32_t *__restrict__ flags = ws.flags + (size_t)tile * (kMaxHfSyms / 32);
@@ -501,13 +506,14 @@ k_ans_pack(Workspace ws, Templates tp) {
     }
 
     // ---- 4. payload prefix A | L | B | D ---------------------------------------------------------
-    const uint32_t la = tp.bits[0], lb = tp.bits[1 + t.shape], ll = ws.lfbitlen[tile];
-    const uint32_t e_start = la + ll + lb + ld;
+    const uint32_t la = multi ? 0u : tp.bits[0], lb = multi ? 0u : tp.bits[1 + t.shape];
+    const uint32_t ll = multi ? 0u : ws.lfbitlen[tile];
+    const uint32_t e_start = multi ? 0u : la + ll + lb + ld;   // multi: A / L / B / D live in the frame's prefix
     const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !chain_err && N > 0 && !ws.tile_err[tile];
     for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kPackThreads)
         payload[w] = 0;
     __syncthreads();
-    if (sane) {
+    if (sane && !multi) {
         append_bits(payload, 0, tp.words, la, tid, kPackThreads);
         append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kPackThreads);
         append_bits(payload, (uint64_t)la + ll, tp.words + (size_t)(1 + t.shape) * kTemplWords, lb, tid, kPackThreads);
@@ -626,7 +632,9 @@ k_ans_pack(Workspace ws, Templates tp) {
         if (!sane && !err)
             err |= kErrSlab;
         uint32_t flen = 0, foff = kSlabHeaderReserve;
-        if (fits && !err) {
+        if (fits && !err && multi) {
+            flen = (total_bits + 7) >> 3;   // the section, byte aligned (encoder.c:976-981)
+        } else if (fits && !err) {
             const uint32_t payload_bytes = (total_bits + 7) >> 3;
             uint8_t hb[kSlabHeaderReserve];
             uint32_t n = 0;

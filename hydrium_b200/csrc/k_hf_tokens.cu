@@ -51,6 +51,8 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
 
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileDesc t = tiles[tile];
+    if (t.flags & kTilePrefix)   // pseudo-tile of a multi-group frame (k_frame.cu): no pixels
+        return;
     const uint32_t vbw = (t.w + 7) >> 3, vbh = (t.h + 7) >> 3, nb = vbw * vbh, ne = 3 * nb;
 
     for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)

@@ -223,6 +223,8 @@ k_lf_group(const TileDesc *__restrict__ tiles, const int32_t *__restrict__ lfq, 
     PrefixWork &w = s.work;
     const uint32_t tile = blockIdx.x, lane = threadIdx.x;
     const TileDesc t = tiles[tile];
+    if (t.flags & (kTilePrefix | kTileMulti))   // multi-group frames code ONE LF image per frame (k_frame.cu)
+        return;
     const uint32_t vbw = (t.w + 7) >> 3, vbh = (t.h + 7) >> 3, nb = vbw * vbh, n = 3 * nb;
     const uint32_t rounds = (n + 31) >> 5;
     const PrefixParams prm = lf_stream_params();

@@ -206,7 +206,7 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     const uint32_t tile = blockIdx.y, by = blockIdx.x;
     const TileDesc t = tiles[tile];
     const uint32_t vbw = (t.w + 7) >> 3, vbh = (t.h + 7) >> 3;
-    if (by >= vbh)
+    if (by >= vbh || (t.flags & kTilePrefix))
         return;
     const uint32_t tid = threadIdx.x, b = tid >> 3, r = tid & 7;
     const bool fmt16 = (t.flags & kTileFmt16) != 0, fmt32 = (t.flags & kTileFmtF32) != 0;

@@ -63,6 +63,10 @@ void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
+// frames with several groups (k_frame.cu): shared ANS model, LFGroup section, frame prefix
+void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st);
+void launch_frame_lf(const Workspace &ws, uint32_t nslots, cudaStream_t st);
+void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st);
 // compaction: out[prefix_len + out_off[i] ...] = frame i ; total written to ws.out_off[ntiles]
 void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
                    uint32_t *d_overflow, cudaStream_t st);

@@ -60,8 +60,9 @@ HDN inline void build_section_a(PrefixWork &w, uint32_t *syms, BitSink &bw) {
     put_ma_tree(w, syms, bw, 5);
 }
 
-// section B for a tile of vbw x vbh varblocks
-HDN inline void build_section_b(PrefixWork &w, uint32_t *syms, BitSink &bw, uint32_t vbw, uint32_t vbh) {
+// tail of the LF group: nb_blocks, the zero-predictor MA tree and the constant HF-metadata image of
+// an LF group of vbw x vbh varblocks (encoder.c:598-626).  `cap` = words of symbol scratch.
+HDN inline void put_hf_metadata(PrefixWork &w, uint32_t *syms, uint32_t cap, BitSink &bw, uint32_t vbw, uint32_t vbh) {
     const uint32_t nb = vbw * vbh;
     bw.put(nb - 1, ceil_log2_u32(nb));
     bw.put(2, 4);
@@ -75,10 +76,25 @@ HDN inline void build_section_b(PrefixWork &w, uint32_t *syms, BitSink &bw, uint
         p.modular = 1;
         p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
         p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
-        ps_encode_stream(w, syms, kSectionSymCap, p, total, HfMetaValues{zeros_pre, nb}, bw);
+        ps_encode_stream(w, syms, cap, p, total, HfMetaValues{zeros_pre, nb}, bw);
     }
+}
+
+// HFGlobal and the head of the ANS stream header, up to and including the context map
+// (encoder.c:959-964, entropy.c:108-167).  `frame_groups` = PassGroups in the frame: the preset
+// count is written in ceil(log2(groups)) bits.
+HDN inline void put_hf_global(PrefixWork &w, uint32_t *syms, BitSink &bw, uint32_t frame_groups);
+
+// section B for a tile of vbw x vbh varblocks
+HDN inline void build_section_b(PrefixWork &w, uint32_t *syms, BitSink &bw, uint32_t vbw, uint32_t vbh) {
+    put_hf_metadata(w, syms, kSectionSymCap, bw, vbw, vbh);
+    put_hf_global(w, syms, bw, 1);
+}
+
+HDN inline void put_hf_global(PrefixWork &w, uint32_t *syms, BitSink &bw, uint32_t frame_groups) {
     bw.put_bool(1);    // HFGlobal: default dequant matrices
-    bw.put(2, 2);      // (num_presets - 1 takes 0 bits) ; HF pass order
+    bw.put(0, ceil_log2_u32(frame_groups));   // num_presets - 1 = 0
+    bw.put(2, 2);      // HF pass order
     bw.put_bool(0);    // ANS stream: no lz77
     bw.put_bool(0);    // context map: not simple
     bw.put_bool(1);    // move-to-front
@@ -108,6 +124,39 @@ HDN inline void build_section_b(PrefixWork &w, uint32_t *syms, BitSink &bw, uint
         // tokens produced (<= ~60) never reach the staged indices (upper ~750 words)
         ps_encode_stream(w, syms, kSectionSymCap - 800, p, kHfContexts, StagedValues{idx}, bw);
     }
+}
+
+// ---- frames with more than one PassGroup (tile_size_shift > 0, one-frame mode) -----------------
+// TOC of such a frame: LFGlobal, LFGroup, HFGlobal, then the groups in raster order -- which is the
+// order the sections are written in, so the permutation the reference encodes is the identity
+// (encoder.c:241-325) and its Lehmer code is all zeros.
+struct TocPermValues {
+    uint32_t toc_size;
+    HD uint32_t operator()(uint32_t i) const { return i == 0 ? toc_size : 0u; }
+};
+
+// frame header of a multi-section frame, byte aligned at the end (encoder.c:327-435)
+HDN inline void put_frame_header_multi(PrefixWork &w, uint32_t *syms, BitSink &bw, bool crop, uint32_t x0, uint32_t y0,
+                                       uint32_t fw, uint32_t fh, bool last, uint32_t toc_size) {
+    put_frame_header_fields(bw, crop, x0, y0, fw, fh, last);
+    bw.put_bool(1);                // permuted TOC
+    PrefixParams p;
+    p.num_plain_dists = 8;
+    p.lz_min_symbol = 0;
+    p.modular = 0;
+    p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
+    p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
+    ps_encode_stream(w, syms, kSectionSymCap, p, 1 + toc_size, TocPermValues{toc_size}, bw);
+    bw.align_byte();
+}
+
+// head of an LFGroup section: modular sub-image preamble + gradient-predictor MA tree (encoder.c:539-564)
+HDN inline void put_lf_group_head(PrefixWork &w, uint32_t *syms, BitSink &bw) {
+    bw.put(0, 2);      // extra precision
+    bw.put_bool(0);    // use global tree
+    bw.put_bool(1);    // wp_params all_default
+    bw.put(0, 2);      // nb_transforms
+    put_ma_tree(w, syms, bw, 5);
 }
 
 }  // namespace hydb

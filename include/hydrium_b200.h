@@ -143,6 +143,27 @@ HYDRIUM_EXPORT uint64_t hydb_engine_launch_count(const HydbEngine *engine);
  * synchronise, collect per-tile errors and learn how many bytes the batch appended. */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_tiles(HydbEngine *engine, const HydbTile *tiles, uint32_t n,
                                                       uint8_t *d_out, uint64_t d_out_cap, uint64_t d_out_pos);
+/* One FRAME of up to 2048x2048 pixels = up to 8x8 groups of 256x256 (what hyd_send_tile receives with
+ * tile_size_shift 1..3, or in one-frame mode for an image of at most one LF group; reference:
+ * libhydrium.h:198-206, encoder.c:437-472).  Pointers are DEVICE pointers.  A frame takes
+ * 1 + groups workspace slots of the engine's batch (1 slot when it is a single group). */
+typedef struct HydbFrame {
+    const void *plane[3];
+    int64_t row_stride;      /* samples */
+    int64_t pixel_stride;    /* samples */
+    uint32_t width, height;  /* frame size in pixels, <= 2048 */
+    uint32_t x0, y0;         /* origin in the image, multiples of the tile size */
+    uint32_t image_width, image_height;
+    int32_t is_last;         /* 0 / 1 */
+    int32_t sample_fmt;
+    int32_t linear_light;
+    int32_t with_image_header;
+    int32_t one_frame;       /* 1: one-frame mode header flavour (no crop, always last) */
+} HydbFrame;
+/* Encode n frames and append them, in order, to d_out at byte d_out_pos (asynchronous like
+ * hydb_engine_encode_tiles; finish with hydb_engine_finish). */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_frames(HydbEngine *engine, const HydbFrame *frames, uint32_t n,
+                                                       uint8_t *d_out, uint64_t d_out_cap, uint64_t d_out_pos);
 /* Synchronise, check per-tile error flags of the last batch, return total bytes appended by it. */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_finish(HydbEngine *engine, uint64_t *batch_bytes);
 

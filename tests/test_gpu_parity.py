@@ -271,6 +271,43 @@ def test_float32_samples(product_lib, engine, oracle):
     assert engine.encode_image(img) == want   # the engine is still usable afterwards
 
 
+def _split_frames(stream: bytes, header_len: int):
+    """(for diagnostics) nothing format-aware: just report the first differing byte offset"""
+    return stream[header_len:]
+
+
+@pytest.mark.parametrize("case", [
+    # (width, height, shift_x, shift_y, bits, linear, seed)
+    (600, 520, 1, 1, 8, 0, 1),        # 2 x 2 tiles of 512^2: frames of 4, 2, 2 groups and a partial one
+    (700, 300, 2, 0, 8, 0, 2),        # tiles 1024 x 256: one frame of 3 groups in a row
+    (300, 700, 0, 2, 16, 1, 3),       # tiles 256 x 1024: a column of 3 groups, 16-bit linear
+    (1100, 600, 3, 3, 8, 0, 4),       # one 2048^2 tile: 5 x 3 groups
+    (520, 260, -1, -1, 8, 0, 5),      # one-frame mode, one LF group, 3 x 2 groups
+    (256, 257, 1, 1, 8, 0, 6),        # second group one pixel row high
+])
+def test_multi_group_frames_match_reference(product_lib, reflib, case):
+    """tile_size_shift 1..3 and one-frame mode within one LF group: the frame
+    carries LFGlobal / LFGroup / HFGlobal sections shared by its groups, a TOC entry per section and
+    one ANS model for all groups.  Compared with the reference library itself."""
+    w, h, sx, sy, bits, lin, seed = case
+    img = synth_image(w, h, bits, seed=seed)
+    want = encode_cli_loop(reflib, img, linear_light=lin, shift_x=sx, shift_y=sy)
+    got = encode_cli_loop(product_lib, img, linear_light=lin, shift_x=sx, shift_y=sy)
+    if got != want:
+        n = min(len(got), len(want))
+        first = next((i for i in range(n) if got[i] != want[i]), n)
+        raise AssertionError(f"{case}: {len(got)} vs {len(want)} bytes, first difference at byte {first}: "
+                             f"{got[max(0, first - 4):first + 12].hex()} vs {want[max(0, first - 4):first + 12].hex()}")
+
+
+def test_multi_group_golden_and_float(product_lib, reflib):
+    e = kat_table()["H_1024_tile512_ref_only"]
+    out = encode_cli_loop(product_lib, kat_image(e), shift_x=e["shift"], shift_y=e["shift"])
+    assert len(out) == e["length"] and sha256(out) == e["sha256"]
+    img = (synth_image(530, 300, 16, seed=8).astype(np.float32) / np.float32(65535))
+    assert encode_cli_loop(product_lib, img, shift_x=1, shift_y=1) == encode_cli_loop(reflib, img, shift_x=1, shift_y=1)
+
+
 def test_far_tiles_of_huge_images(engine, oracle):
     """Frame headers of tiles deep inside config-3 / config-5 sized images, and the level-10 container."""
     buf = np.zeros(128, np.uint8)
