@@ -68,8 +68,14 @@ struct TileDesc {
     uint32_t group_index;     // raster index of this group inside the frame
     uint32_t frame_w, frame_h;   // frame size in pixels
     uint32_t frame_x0, frame_y0; // frame origin inside the image (crop offset)
-    uint32_t pad_;
+    // one-frame mode over several LF groups (each LF group is encoded as a "frame part"):
+    // bits 0-7 HF preset of the LF group, 8-11 bits the preset id is written in, 12-19 largest token
+    // alphabet of the LF groups sent before (the reference's running max_alphabet_size, entropy.c:459)
+    uint32_t preset_info;
 };
+HD uint32_t tile_preset(const TileDesc &t) { return t.preset_info & 0xFFu; }
+HD uint32_t tile_preset_bits(const TileDesc &t) { return (t.preset_info >> 8) & 0xFu; }
+HD uint32_t tile_alpha_floor(const TileDesc &t) { return (t.preset_info >> 12) & 0xFFu; }
 enum : uint32_t {
     kTileLast = 1u << 0,      // is_last frame (reference: encoder.c:482-485)
     kTileCrop = 1u << 1,      // image larger than the tile (reference: encoder.c:340-342)
@@ -80,6 +86,7 @@ enum : uint32_t {
     kTilePrefix = 1u << 6,    // pseudo-tile holding the shared sections of a multi-group frame
     kTileMulti = 1u << 7,     // group of a multi-group frame: its slab carries only the PassGroup section
     kTileOneFrame = 1u << 8,  // one-frame mode header flavour: no crop, always last (encoder.c:339-342)
+    kTileLfPart = 1u << 9,    // prefix of one LF group of a larger one-frame image: LFGroup section only
 };
 
 // ---- integer helpers (reference: math-functions.h:8-88) ----------------------------------

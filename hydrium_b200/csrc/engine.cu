@@ -307,7 +307,7 @@ static Workspace ws_view(const Workspace &w, uint32_t first) {
 // per-slot additions for multi-group frames (see TileDesc in common.cuh)
 struct SlotExtra {
     uint32_t flags;
-    uint32_t frame_groups, frame_gx, group_index, frame_w, frame_h, frame_x0, frame_y0;
+    uint32_t frame_groups, frame_gx, group_index, frame_w, frame_h, frame_x0, frame_y0, preset_info;
 };
 
 static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, cudaStream_t st,
@@ -344,7 +344,7 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
                   ((s.image_width > s.width || s.image_height > s.height) ? kTileCrop : 0u) |
                   (s.sample_fmt == HYD_UINT16 ? kTileFmt16 : 0u) | (s.sample_fmt == HYD_FLOAT32 ? kTileFmtF32 : 0u) |
                   (s.linear_light ? kTileLinear : 0u);
-        d.frame_groups = d.frame_gx = d.group_index = d.frame_w = d.frame_h = d.frame_x0 = d.frame_y0 = d.pad_ = 0;
+        d.frame_groups = d.frame_gx = d.group_index = d.frame_w = d.frame_h = d.frame_x0 = d.frame_y0 = d.preset_info = 0;
         if (extra) {
             const SlotExtra &e = extra[i];
             d.flags |= e.flags;
@@ -355,6 +355,7 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
             d.frame_h = e.frame_h;
             d.frame_x0 = e.frame_x0;
             d.frame_y0 = e.frame_y0;
+            d.preset_info = e.preset_info;
         }
     }
     if (!fresh.empty()) {
@@ -456,7 +457,7 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
         t.linear_light = fr.linear_light;
         SlotExtra e;
         memset(&e, 0, sizeof(e));
-        if (G == 1) {   // single section: the classic path (encoder.c:992-1004)
+        if (G == 1 && !fr.lf_part) {   // single section: the classic path (encoder.c:992-1004)
             for (int k = 0; k < 3; k++) t.plane[k] = fr.plane[k];
             t.width = fr.width;
             t.height = fr.height;
@@ -478,6 +479,8 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
         e.frame_h = fr.height;
         e.frame_x0 = fr.x0;
         e.frame_y0 = fr.y0;
+        if (fr.lf_part)
+            e.preset_info = (fr.preset & 0xFFu) | ((fr.preset_bits & 0xFu) << 8) | ((fr.alpha_floor & 0xFFu) << 12);
         // prefix pseudo-tile
         HydbTile p = t;
         for (int k = 0; k < 3; k++) p.plane[k] = fr.plane[k];
@@ -485,7 +488,7 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
         p.x0 = p.y0 = 0;
         p.with_image_header = fr.with_image_header;
         SlotExtra pe = e;
-        pe.flags = kTilePrefix | (fr.one_frame ? kTileOneFrame : 0u);
+        pe.flags = kTilePrefix | (fr.one_frame ? kTileOneFrame : 0u) | (fr.lf_part ? kTileLfPart : 0u);
         pe.group_index = 0xFFFFFFFFu;
         tiles.push_back(p);
         extra.push_back(pe);
@@ -537,6 +540,80 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
     eng->timed_pending = false;
     eng->launches += 10;
     return queue_readback(eng, slots, d_out_pos);
+}
+
+HYDStatusCode hydb_engine_read_model(HydbEngine *eng, uint32_t slot, uint32_t *bits_out, uint32_t *nbits,
+                                     uint32_t *max_alphabet) {
+    if (!eng || !bits_out || !nbits || !max_alphabet || slot >= eng->last_n)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaStreamSynchronize(eng->st));
+    uint32_t meta = 0;
+    std::vector<uint32_t> d(kDBitsWords);
+    CK(cudaMemcpy(&meta, eng->ws.chain_out + (size_t)slot * 4 + 2, sizeof(meta), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d.data(), eng->ws.dbits + (size_t)slot * kDBitsWords, kDBitsWords * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const uint32_t len = meta & 0xFFFFu, off = (meta >> 16) & 0xFFu;
+    *max_alphabet = meta >> 24;
+    *nbits = len - off;
+    // histograms start `off` bits into section D: shift them down to bit 0
+    for (uint32_t i = 0; i < kDBitsWords; i++) {
+        const uint32_t b = off + 32u * i, w = b >> 5, r = b & 31u;
+        const uint32_t lo = w < (uint32_t)kDBitsWords ? d[w] : 0u, hi = w + 1 < (uint32_t)kDBitsWords ? d[w + 1] : 0u;
+        bits_out[i] = r ? ((lo >> r) | (hi << (32u - r))) : lo;
+    }
+    return HYD_OK;
+}
+
+// info words (all uint32):
+//   [0] image width  [1] image height  [2] with_image_header  [3] largest token alphabet of the frame
+//   [4] n = LF groups of the image (all sent exactly once)     [5] total PassGroups
+//   [8 .. 8+n)            lfid of the k-th LF group sent (raster id)
+//   [8+n .. 8+2n)         byte length of the k-th sent LF group's LFGroup section
+//   [8+2n .. 8+2n+G)      byte length of every PassGroup section, in the order the parts produced them
+//   then per preset p = 0..n-1:  nbits[p], followed by ceil(nbits/32) words of histogram bits
+HYDStatusCode hydb_oneframe_finish(HydbEngine *eng, const uint32_t *info, uint32_t info_words, uint8_t *head,
+                                   uint32_t head_cap, uint32_t *head_len, uint8_t *hf_global, uint32_t hf_cap,
+                                   uint32_t *hf_len) {
+    if (!eng || !info || info_words < 8 || !head || !head_len || !hf_global || !hf_len)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    uint32_t *d_info = nullptr, *d_scratch = nullptr;
+    uint8_t *d_out = nullptr;
+    const uint32_t n = info[4];
+    const size_t scratch_words = (size_t)2 * 1485 * n + 16384 + (size_t)4 * (8 + n + info[5]);
+    const size_t out_bytes = (size_t)head_cap + hf_cap + 64;
+    if (cudaMalloc(&d_info, (size_t)info_words * 4) != cudaSuccess || cudaMalloc(&d_scratch, scratch_words * 4) != cudaSuccess ||
+        cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
+        cudaFree(d_info); cudaFree(d_scratch); cudaFree(d_out);
+        eng->error = "device allocation failed";
+        return HYD_NOMEM;
+    }
+    HYDStatusCode rc = HYD_OK;
+    uint32_t res[4] = {0, 0, 0, 0};
+    if (cudaMemcpyAsync(d_info, info, (size_t)info_words * 4, cudaMemcpyHostToDevice, eng->st) != cudaSuccess)
+        rc = HYD_INTERNAL_ERROR;
+    if (rc == HYD_OK) {
+        launch_oneframe_finish(d_info, info_words, d_scratch, (uint32_t)scratch_words, d_out, head_cap, hf_cap, eng->st);
+        eng->launches++;
+        if (cudaMemcpyAsync(res, d_out + head_cap + hf_cap, 16, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
+            cudaStreamSynchronize(eng->st) != cudaSuccess)
+            rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc == HYD_OK && (res[2] || res[0] > head_cap || res[1] > hf_cap)) {
+        eng->error = "one-frame head does not fit its buffer";
+        rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc == HYD_OK) {
+        *head_len = res[0];
+        *hf_len = res[1];
+        if (cudaMemcpy(head, d_out, res[0], cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(hf_global, d_out + head_cap, res[1], cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = HYD_INTERNAL_ERROR;
+    }
+    cudaFree(d_info); cudaFree(d_scratch); cudaFree(d_out);
+    if (rc != HYD_OK && eng->error.empty())
+        eng->error = "CUDA failure while assembling the one-frame head";
+    return rc;
 }
 
 HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {

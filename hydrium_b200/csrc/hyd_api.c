@@ -61,6 +61,21 @@ struct HYDEncoder {
     uint32_t queued;
     size_t stage_used;
     char errbuf[256];
+
+    /* one-frame mode over several LF groups (encoder.c:752-1011): every hyd_send_tile encodes one
+     * 2048x2048 LF group as a frame part; nothing surfaces until the last one (libhydrium.c:147-166) */
+    uint32_t of_n, of_cx;           /* LF groups of the image, per row */
+    uint32_t of_nsent;
+    uint32_t *of_sent;              /* raster id of the k-th LF group sent */
+    uint8_t *of_seen;
+    uint32_t *of_len1;              /* byte length of the k-th sent LFGroup section */
+    uint8_t **of_lf;                /* ... and its bytes */
+    uint32_t *of_elen;              /* PassGroup section lengths, in production order */
+    uint32_t of_ngroups, of_elen_cap;
+    uint8_t *of_e;                  /* PassGroup sections, concatenated */
+    size_t of_e_len, of_e_cap;
+    uint32_t *of_hist;              /* [of_n][385]: bit count + histogram bits of each preset */
+    uint32_t of_max_alpha;
 };
 
 /* One engine + staging set is kept alive across encoders (creating the CUDA workspace and the
@@ -130,11 +145,30 @@ static void release_gpu(HYDEncoder *enc) {
     enc->stage_used = 0;
 }
 
+static void of_reset(HYDEncoder *enc) {
+    if (enc->of_lf)
+        for (uint32_t k = 0; k < enc->of_n; k++)
+            free(enc->of_lf[k]);
+    free(enc->of_lf);
+    free(enc->of_sent);
+    free(enc->of_seen);
+    free(enc->of_len1);
+    free(enc->of_elen);
+    free(enc->of_e);
+    free(enc->of_hist);
+    enc->of_lf = NULL;
+    enc->of_sent = enc->of_len1 = enc->of_elen = enc->of_hist = NULL;
+    enc->of_seen = enc->of_e = NULL;
+    enc->of_n = enc->of_nsent = enc->of_ngroups = enc->of_elen_cap = enc->of_max_alpha = 0;
+    enc->of_e_len = enc->of_e_cap = 0;
+}
+
 HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydrium.c:21-44 */
     if (!enc)
         return HYD_OK;
     release_gpu(enc);
     free(enc->pend);
+    of_reset(enc);
     free(enc);
     return HYD_OK;
 }
@@ -179,9 +213,10 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMet
         return HYD_API_ERROR;
     }
     const int one_frame = md->tile_size_shift_x < 0 || md->tile_size_shift_y < 0;
-    if (one_frame && (w > 2048 || h > 2048)) {
-        /* several LF groups in one frame (shared histograms per preset, permuted TOC) are not built yet */
-        enc->error = "one-frame mode is limited to 2048x2048 in the B200 encoder (use tile_size_shift 0..3)";
+    if (one_frame && ((w + 2047) / 2048) * ((h + 2047) / 2048) > 28) {
+        /* beyond 28 LF groups the reference folds the nine HF clusters of a preset into 3, 2 or 1
+         * (encoder.c:878-899): not built */
+        enc->error = "one-frame mode is limited to 28 LF groups of 2048x2048 in the B200 encoder (use tile_size_shift 0..3)";
         return HYD_API_ERROR;
     }
     enc->metadata = *md;
@@ -192,6 +227,20 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMet
     {
         const uint64_t fw = w < enc->tile_w ? w : enc->tile_w, fh = h < enc->tile_h ? h : enc->tile_h;
         enc->groups_per_tile = (uint32_t)(((fw + TILE - 1) / TILE) * ((fh + TILE - 1) / TILE));
+    }
+    of_reset(enc);
+    if (one_frame && (w > 2048 || h > 2048)) {
+        enc->of_cx = (uint32_t)((w + 2047) / 2048);
+        enc->of_n = enc->of_cx * (uint32_t)((h + 2047) / 2048);
+        enc->of_sent = calloc(enc->of_n, sizeof(uint32_t));
+        enc->of_seen = calloc(enc->of_n, 1);
+        enc->of_len1 = calloc(enc->of_n, sizeof(uint32_t));
+        enc->of_lf = calloc(enc->of_n, sizeof(uint8_t *));
+        enc->of_hist = calloc((size_t)enc->of_n * 385, sizeof(uint32_t));
+        if (!enc->of_sent || !enc->of_seen || !enc->of_len1 || !enc->of_lf || !enc->of_hist) {
+            of_reset(enc);
+            return HYD_NOMEM;
+        }
     }
     enc->have_metadata = 1;
     return HYD_OK;
@@ -433,6 +482,166 @@ static HYDStatusCode run_frame(HYDEncoder *enc, HydbFrame *fr) {
     return HYD_OK;
 }
 
+static uint32_t cllog2_u32(uint32_t v) {
+    uint32_t n = 0;
+    while ((1u << n) < v)
+        n++;
+    return n;
+}
+
+/* one LF group of a one-frame image with several of them: encode it as a frame part and keep what it
+ * produced; when it is the last one, assemble the whole frame into the pending-output queue */
+static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) {
+    if (enc->of_seen[lfid] || enc->of_nsent >= enc->of_n) {
+        enc->error = "LF group sent twice in one-frame mode";
+        return HYD_API_ERROR;
+    }
+    const uint32_t G = ((fr->width + TILE - 1) / TILE) * ((fr->height + TILE - 1) / TILE);
+    fr->lf_part = 1;
+    fr->preset = lfid;
+    fr->preset_bits = cllog2_u32(enc->of_n);
+    fr->alpha_floor = enc->of_max_alpha;
+    fr->with_image_header = 0;
+    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    enc->stage_used = 0;
+    HYDStatusCode rc = hydb_engine_encode_frames(enc->engine, fr, 1, enc->out_dev, (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
+    if (rc < HYD_ERROR_START)
+        return gpu_error(enc, rc);
+    uint64_t bytes = 0;
+    rc = hydb_engine_finish(enc->engine, &bytes);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    uint32_t lens[65];
+    rc = hydb_engine_frame_lengths(enc->engine, lens, 1 + G);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i <= G; i++)
+        sum += lens[i];
+    if (sum != bytes) {
+        enc->error = "inconsistent section lengths";
+        return HYD_INTERNAL_ERROR;
+    }
+    const uint32_t k = enc->of_nsent;
+    uint8_t *lf = malloc(lens[0] ? lens[0] : 1);
+    if (!lf)
+        return HYD_NOMEM;
+    if (enc->of_e_len + (size_t)(bytes - lens[0]) > enc->of_e_cap) {
+        size_t cap = enc->of_e_cap ? enc->of_e_cap * 2 : (size_t)1 << 22;
+        while (cap < enc->of_e_len + (size_t)(bytes - lens[0]))
+            cap *= 2;
+        uint8_t *p = realloc(enc->of_e, cap);
+        if (!p) {
+            free(lf);
+            return HYD_NOMEM;
+        }
+        enc->of_e = p;
+        enc->of_e_cap = cap;
+    }
+    if (enc->of_ngroups + G > enc->of_elen_cap) {
+        uint32_t cap = enc->of_elen_cap ? enc->of_elen_cap * 2 : 256;
+        while (cap < enc->of_ngroups + G)
+            cap *= 2;
+        uint32_t *p = realloc(enc->of_elen, (size_t)cap * sizeof(uint32_t));
+        if (!p) {
+            free(lf);
+            return HYD_NOMEM;
+        }
+        enc->of_elen = p;
+        enc->of_elen_cap = cap;
+    }
+    if (hydb_memcpy_d2h(lf, enc->out_dev, lens[0]) ||
+        hydb_memcpy_d2h(enc->of_e + enc->of_e_len, enc->out_dev + lens[0], (size_t)(bytes - lens[0]))) {
+        free(lf);
+        return gpu_error(enc, HYD_INTERNAL_ERROR);
+    }
+    enc->of_lf[k] = lf;
+    enc->of_len1[k] = lens[0];
+    enc->of_e_len += (size_t)(bytes - lens[0]);
+    for (uint32_t g = 0; g < G; g++)
+        enc->of_elen[enc->of_ngroups + g] = lens[1 + g];
+    enc->of_ngroups += G;
+    uint32_t *hist = enc->of_hist + (size_t)lfid * 385;
+    uint32_t alpha = 0;
+    rc = hydb_engine_read_model(enc->engine, 1, hist + 1, &hist[0], &alpha);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    if (alpha > enc->of_max_alpha)
+        enc->of_max_alpha = alpha;
+    enc->of_sent[k] = lfid;
+    enc->of_seen[lfid] = 1;
+    enc->of_nsent = k + 1;
+    if (!enc->last_tile)
+        return HYD_OK;
+
+    /* last LF group: head and HFGlobal from the device, then  head | LFGroups | HFGlobal | PassGroups */
+    if (enc->of_nsent != enc->of_n) {
+        enc->error = "one-frame mode: the last tile arrived before every LF group was sent";
+        return HYD_API_ERROR;
+    }
+    const uint32_t n = enc->of_n, NG = enc->of_ngroups;
+    size_t words = 8 + 2 * (size_t)n + NG;
+    for (uint32_t p = 0; p < n; p++)
+        words += 1 + ((enc->of_hist[(size_t)p * 385] + 31) >> 5);
+    uint32_t *info = calloc(words, sizeof(uint32_t));
+    const uint32_t head_cap = 65536 + 8 * NG, hf_cap = 8192 + 2048 * n;
+    uint8_t *head = malloc(head_cap), *hf = malloc(hf_cap);
+    if (!info || !head || !hf) {
+        free(info); free(head); free(hf);
+        return HYD_NOMEM;
+    }
+    info[0] = (uint32_t)enc->metadata.width;
+    info[1] = (uint32_t)enc->metadata.height;
+    info[2] = !enc->wrote_header;
+    info[3] = enc->of_max_alpha;
+    info[4] = n;
+    info[5] = NG;
+    memcpy(info + 8, enc->of_sent, n * sizeof(uint32_t));
+    memcpy(info + 8 + n, enc->of_len1, n * sizeof(uint32_t));
+    memcpy(info + 8 + 2 * n, enc->of_elen, NG * sizeof(uint32_t));
+    {
+        uint32_t *q = info + 8 + 2 * n + NG;
+        for (uint32_t p = 0; p < n; p++) {
+            const uint32_t *h = enc->of_hist + (size_t)p * 385;
+            const uint32_t hw = (h[0] + 31) >> 5;
+            q[0] = h[0];
+            memcpy(q + 1, h + 1, hw * sizeof(uint32_t));
+            q += 1 + hw;
+        }
+    }
+    uint32_t head_len = 0, hf_len = 0;
+    rc = hydb_oneframe_finish(enc->engine, info, (uint32_t)words, head, head_cap, &head_len, hf, hf_cap, &hf_len);
+    free(info);
+    if (rc != HYD_OK) {
+        free(head); free(hf);
+        return gpu_error(enc, rc);
+    }
+    size_t total = (size_t)head_len + hf_len + enc->of_e_len;
+    for (uint32_t i = 0; i < n; i++)
+        total += enc->of_len1[i];
+    rc = pend_reserve(enc, total);
+    if (rc < HYD_ERROR_START) {
+        free(head); free(hf);
+        return rc;
+    }
+    uint8_t *d = enc->pend + enc->pend_len;
+    memcpy(d, head, head_len);
+    d += head_len;
+    for (uint32_t i = 0; i < n; i++) {
+        memcpy(d, enc->of_lf[i], enc->of_len1[i]);
+        d += enc->of_len1[i];
+    }
+    memcpy(d, hf, hf_len);
+    d += hf_len;
+    memcpy(d, enc->of_e, enc->of_e_len);
+    enc->pend_len += total;
+    enc->wrote_header = 1;
+    free(head);
+    free(hf);
+    return HYD_OK;
+}
+
 HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const buffer[3], uint32_t tile_x,
                                            uint32_t tile_y, ptrdiff_t row_stride, ptrdiff_t pixel_stride,
                                            int is_last, HYDSampleFormat sample_fmt) {
@@ -460,6 +669,23 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     /* encoder.c:482-485 */
     enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span_x >= W && ((uint64_t)tile_y + 1) * span_y >= H) : !!is_last;
     const size_t item = sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4);
+    if (enc->of_n) {
+        /* one-frame mode over several LF groups: this tile is LF group (tile_x, tile_y) */
+        HydbFrame fr;
+        memset(&fr, 0, sizeof(fr));
+        fr.width = tw;
+        fr.height = th;
+        fr.x0 = tile_x * enc->tile_w;
+        fr.y0 = tile_y * enc->tile_h;
+        fr.image_width = (uint32_t)W;
+        fr.image_height = (uint32_t)H;
+        fr.is_last = 1;
+        fr.sample_fmt = sample_fmt;
+        fr.linear_light = enc->metadata.linear_light != 0;
+        fr.one_frame = 1;
+        stage_pixels(enc, tw, th, fr.plane, &fr.row_stride, &fr.pixel_stride, buffer, row_stride, pixel_stride, item);
+        return run_lf_part(enc, &fr, tile_y * enc->of_cx + tile_x);
+    }
     if (tw > TILE || th > TILE) {
         /* several groups in this frame: everything queued so far goes first, then the frame at once */
         rc = run_batch(enc);

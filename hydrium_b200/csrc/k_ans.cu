@@ -55,6 +55,7 @@ struct AnsShared {
     uint32_t hist[kHfClusters * kHfTokens];             //  2,304 B
     uint32_t dbits[kDBitsWords];                        //  1,536 B
     uint32_t alpha[kHfClusters];
+    uint32_t own_alpha, dhist_off;
     int log_alpha;
     uint32_t dbitlen, err;
 };
@@ -195,6 +196,11 @@ k_ans_chain(Workspace ws) {
         uint32_t mx = 0;
         for (int c = 0; c < kHfClusters; c++)
             mx = s.alpha[c] > mx ? s.alpha[c] : mx;
+        s.own_alpha = mx;
+        // one-frame mode over several LF groups: the alphabet bound is the largest seen so far in the
+        // frame's stream, not this LF group's alone (entropy.c:459, 952)
+        const uint32_t floor_alpha = tile_alpha_floor(ws.tiles[tile]);
+        mx = floor_alpha > mx ? floor_alpha : mx;
         int la = mx ? ceil_log2_u32(mx) : 0;
         s.log_alpha = la < 5 ? 5 : la;   // reference: entropy.c:952 (<= 6 because tokens < 64)
     }
@@ -269,6 +275,7 @@ k_ans_chain(Workspace ws) {
             bw.put((uint32_t)(log_alpha - 5), 2);
             for (int c = 0; c < kHfClusters; c++)
                 ps_put_hybrid_cfg(bw, 4, 1, 0, log_alpha);
+            s.dhist_off = bw.bitlen();
             for (int c = 0; c < kHfClusters; c++)
                 ans_put_histogram(bw, s.cl[c].freq, s.alpha[c]);
             bw.flush_partial();
@@ -280,8 +287,8 @@ k_ans_chain(Workspace ws) {
         const uint32_t words = (s.dbitlen + 31) >> 5;
         for (uint32_t i = lane; i < words && i < (uint32_t)kDBitsWords; i += 32)
             ws.dbits[(size_t)tile * kDBitsWords + i] = s.dbits[i];
-        if (lane == 0)
-            ws.chain_out[tile * 4 + 2] = s.dbitlen;
+        if (lane == 0)   // bits 0-15 length of D, 16-23 where its histograms start, 24-31 this tile's largest alphabet
+            ws.chain_out[tile * 4 + 2] = s.dbitlen | (s.dhist_off << 16) | (s.own_alpha << 24);
         return;
     }
     if (warp != chain_warp && warp != helper_warp)
@@ -499,7 +506,7 @@ k_ans_pack(Workspace ws, Templates tp) {
     uint32_t *payload = reinterpret_cast<uint32_t *>(slab + kSlabHeaderReserve);
     constexpr uint32_t kPayloadCapBits = (uint32_t)(kSlabBytes - kSlabHeaderReserve) * 8u - 64u;
     const uint32_t W = ws.chain_out[tile * 4 + 0], final_state = ws.chain_out[tile * 4 + 1];
-    const uint32_t ld = ws.chain_out[tile * 4 + 2], chain_err = ws.chain_out[tile * 4 + 3];
+    const uint32_t ld = ws.chain_out[tile * 4 + 2] & 0xFFFFu, chain_err = ws.chain_out[tile * 4 + 3];
     if (tid == 0) {
         s.err = chain_err;
         s.ebits_total = 0;
@@ -508,11 +515,15 @@ k_ans_pack(Workspace ws, Templates tp) {
     // ---- 4. payload prefix A | L | B | D ---------------------------------------------------------
     const uint32_t la = multi ? 0u : tp.bits[0], lb = multi ? 0u : tp.bits[1 + t.shape];
     const uint32_t ll = multi ? 0u : ws.lfbitlen[tile];
-    const uint32_t e_start = multi ? 0u : la + ll + lb + ld;   // multi: A / L / B / D live in the frame's prefix
+    // multi: A / L / B / D live in the frame's prefix; the section opens with the group's HF preset id
+    // (zero bits wide unless the frame has several LF groups, encoder.c:937)
+    const uint32_t e_start = multi ? tile_preset_bits(t) : la + ll + lb + ld;
     const bool sane = la != 0xFFFFFFFFu && lb != 0xFFFFFFFFu && !chain_err && N > 0 && !ws.tile_err[tile];
     for (uint32_t w = tid; w < (e_start >> 5) + 3; w += kPackThreads)
         payload[w] = 0;
     __syncthreads();
+    if (sane && multi && tid == 0 && tile_preset_bits(t))
+        atomicOr(&payload[0], tile_preset(t));
     if (sane && !multi) {
         append_bits(payload, 0, tp.words, la, tid, kPackThreads);
         append_bits(payload, la, ws.lfbits + (size_t)tile * kLfBitsWords, ll, tid, kPackThreads);

@@ -159,7 +159,26 @@ typedef struct HydbFrame {
     int32_t linear_light;
     int32_t with_image_header;
     int32_t one_frame;       /* 1: one-frame mode header flavour (no crop, always last) */
+    /* one-frame mode over SEVERAL LF groups: each 2048x2048 LF group is encoded as a frame part
+     * (lf_part = 1).  The part's output is  LFGroup section | PassGroup sections  without any frame
+     * header; hydb_engine_frame_lengths gives the section lengths, hydb_engine_read_model the part's
+     * ANS histograms, and hydb_oneframe_finish assembles the frame's head once all parts exist. */
+    int32_t lf_part;
+    uint32_t preset;         /* HF preset of this LF group (its raster index while the image has <= 256 of them) */
+    uint32_t preset_bits;    /* ceil(log2(number of presets)) */
+    uint32_t alpha_floor;    /* largest token alphabet of the parts sent before (the reference's running maximum) */
 } HydbFrame;
+/* ANS model of the slot's group after hydb_engine_finish: the nine cluster histograms as a bit string
+ * (bits_out: >= 384 words; *nbits), and the largest token alphabet seen in that frame part. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_read_model(HydbEngine *engine, uint32_t slot, uint32_t *bits_out,
+                                                    uint32_t *nbits, uint32_t *max_alphabet);
+/* Head of a one-frame image of several LF groups, from what the parts produced (host buffers in and out):
+ * [image header] + frame header with the TOC permutation + TOC + LFGlobal section  -> head
+ * HFGlobal section (presets, context map, ANS header with every preset's histograms) -> hf_global
+ * info words: see hydb_oneframe_finish in csrc/engine.cu. */
+HYDRIUM_EXPORT HYDStatusCode hydb_oneframe_finish(HydbEngine *engine, const uint32_t *info, uint32_t info_words,
+                                                  uint8_t *head, uint32_t head_cap, uint32_t *head_len,
+                                                  uint8_t *hf_global, uint32_t hf_cap, uint32_t *hf_len);
 /* Encode n frames and append them, in order, to d_out at byte d_out_pos (asynchronous like
  * hydb_engine_encode_tiles; finish with hydb_engine_finish). */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_frames(HydbEngine *engine, const HydbFrame *frames, uint32_t n,

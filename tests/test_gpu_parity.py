@@ -300,6 +300,62 @@ def test_multi_group_frames_match_reference(product_lib, reflib, case):
                              f"{got[max(0, first - 4):first + 12].hex()} vs {want[max(0, first - 4):first + 12].hex()}")
 
 
+@pytest.mark.parametrize("case", [
+    # (width, height, bits, linear, seed, tile order or None)
+    (2304, 2100, 8, 0, 0, None),                      # 2 x 2 LF groups (the golden G case)
+    (4200, 300, 8, 0, 3, None),                       # three LF groups in a row, the last 104 px wide
+    (300, 4200, 16, 1, 4, None),                      # a column of three, 16-bit linear
+    (2100, 2060, 8, 0, 5, [(1, 1), (0, 0), (1, 0), (0, 1)]),   # sent out of raster order
+])
+def test_one_frame_mode_over_several_lf_groups(product_lib, reflib, case):
+    """The reference CLI's default mode for images beyond 2048x2048: one frame, a
+    preset of nine ANS clusters per LF group, TOC permuted by send order, output only at the end."""
+    w, h, bits, lin, seed, order = case
+    img = synth_image(w, h, bits, seed=seed, smooth=True)
+
+    def run(lib):
+        if order is None:
+            return encode_cli_loop(lib, img, linear_light=lin, shift_x=-1, shift_y=-1)
+        return _encode_in_order(lib, img, lin, order)
+
+    want, got = run(reflib), run(product_lib)
+    if got != want:
+        n = min(len(got), len(want))
+        first = next((i for i in range(n) if got[i] != want[i]), n)
+        raise AssertionError(f"{case[:5]}: {len(got)} vs {len(want)} bytes, first difference at byte {first}: "
+                             f"{got[max(0, first - 4):first + 12].hex()} vs {want[max(0, first - 4):first + 12].hex()}")
+    if (w, h) == (2304, 2100):
+        e = kat_table()["G_2304x2100_oneframe_ref_only"]
+        assert e["smooth"] is False   # the golden entry is the noisy variant: checked below
+        noisy = kat_image(e)
+        out = encode_cli_loop(product_lib, noisy, shift_x=-1, shift_y=-1)
+        assert len(out) == e["length"] and sha256(out) == e["sha256"]
+
+
+def _encode_in_order(lib, img, lin, order):
+    """one-frame mode, LF groups sent in the given order, is_last set on the final call only"""
+    h, w, ch = img.shape
+    item = img.dtype.itemsize
+    enc = HYDEncoder(lib)
+    obuf = np.empty(1 << 20, np.uint8)
+    out = bytearray()
+    enc.check(enc.set_metadata(w, h, lin, -1, -1))
+    enc.check(enc.provide_output_buffer(obuf))
+    for i, (tx, ty) in enumerate(order):
+        p = img.ctypes.data + (ty * 2048 * w * ch + tx * 2048 * ch) * item
+        enc.check(enc.send_tile((p, p + item, p + 2 * item), tx, ty, w * ch, ch, int(i == len(order) - 1), E._fmt_of(img)))
+        while True:
+            ret = enc.flush()
+            _, written = enc.release_output_buffer()
+            out += obuf[:written].tobytes()
+            enc.check(enc.provide_output_buffer(obuf))
+            if ret != HYD_NEED_MORE_OUTPUT:
+                break
+        enc.check(ret)
+    enc.destroy()
+    return bytes(out)
+
+
 def test_multi_group_golden_and_float(product_lib, reflib):
     e = kat_table()["H_1024_tile512_ref_only"]
     out = encode_cli_loop(product_lib, kat_image(e), shift_x=e["shift"], shift_y=e["shift"])
