@@ -76,6 +76,22 @@ struct TileDesc {
 HD uint32_t tile_preset(const TileDesc &t) { return t.preset_info & 0xFFu; }
 HD uint32_t tile_preset_bits(const TileDesc &t) { return (t.preset_info >> 8) & 0xFu; }
 HD uint32_t tile_alpha_floor(const TileDesc &t) { return (t.preset_info >> 12) & 0xFFu; }
+// bits 20-23: HF clusters per preset.  Nine normally; a one-frame image with more than 28 LF groups
+// folds them so that presets x clusters stays within 256 (encoder.c:862-899): 3 = one for the
+// non-zero counts + two for the coefficients by parity, 2 = counts / coefficients, 1 = everything.
+HD uint32_t tile_clusters(const TileDesc &t) { const uint32_t k = (t.preset_info >> 20) & 0xFu; return k ? k : 9u; }
+HD uint32_t hf_fold_cluster(uint32_t c9, uint32_t clusters_per_preset) {
+    if (clusters_per_preset >= 9)
+        return c9;
+    if (clusters_per_preset == 3)
+        return c9 < 3 ? 0u : 1u + ((c9 - 3u) & 1u);
+    if (clusters_per_preset == 2)
+        return c9 < 3 ? 0u : 1u;
+    return 0u;
+}
+HD uint32_t hf_clusters_for_presets(uint32_t presets) {   // encoder.c:862, 878, 892, 897
+    return presets * 9 <= 256 ? 9u : (presets * 3 <= 256 ? 3u : (presets * 2 <= 256 ? 2u : 1u));
+}
 enum : uint32_t {
     kTileLast = 1u << 0,      // is_last frame (reference: encoder.c:482-485)
     kTileCrop = 1u << 1,      // image larger than the tile (reference: encoder.c:340-342)

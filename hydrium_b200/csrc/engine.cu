@@ -480,7 +480,8 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
         e.frame_x0 = fr.x0;
         e.frame_y0 = fr.y0;
         if (fr.lf_part)
-            e.preset_info = (fr.preset & 0xFFu) | ((fr.preset_bits & 0xFu) << 8) | ((fr.alpha_floor & 0xFFu) << 12);
+            e.preset_info = (fr.preset & 0xFFu) | ((fr.preset_bits & 0xFu) << 8) | ((fr.alpha_floor & 0xFFu) << 12) |
+                            ((fr.clusters_per_preset & 0xFu) << 20);
         // prefix pseudo-tile
         HydbTile p = t;
         for (int k = 0; k < 3; k++) p.plane[k] = fr.plane[k];

@@ -213,10 +213,10 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMet
         return HYD_API_ERROR;
     }
     const int one_frame = md->tile_size_shift_x < 0 || md->tile_size_shift_y < 0;
-    if (one_frame && ((w + 2047) / 2048) * ((h + 2047) / 2048) > 28) {
-        /* beyond 28 LF groups the reference folds the nine HF clusters of a preset into 3, 2 or 1
-         * (encoder.c:878-899): not built */
-        enc->error = "one-frame mode is limited to 28 LF groups of 2048x2048 in the B200 encoder (use tile_size_shift 0..3)";
+    if (one_frame && ((w + 2047) / 2048) * ((h + 2047) / 2048) > 256) {
+        /* beyond 256 LF groups several of them share an HF preset and the reference defers their ANS
+         * coding until the preset is complete (encoder.c:922-926): not built */
+        enc->error = "one-frame mode is limited to 256 LF groups of 2048x2048 in the B200 encoder (use tile_size_shift 0..3)";
         return HYD_API_ERROR;
     }
     enc->metadata = *md;
@@ -501,6 +501,7 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
     fr->preset = lfid;
     fr->preset_bits = cllog2_u32(enc->of_n);
     fr->alpha_floor = enc->of_max_alpha;
+    fr->clusters_per_preset = enc->of_n * 9 <= 256 ? 9 : (enc->of_n * 3 <= 256 ? 3 : (enc->of_n * 2 <= 256 ? 2 : 1)); /* encoder.c:862-899 */
     fr->with_image_header = 0;
     if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
         return gpu_error(enc, HYD_INTERNAL_ERROR);

@@ -224,8 +224,11 @@ k_ans_chain(Workspace ws) {
     }
     __syncthreads();
     // per-symbol chain constants (one 64-bit division each): all threads
+    // symbols carry one of nine local clusters; with folded presets (many LF groups in one frame)
+    // several of them share a model (the histograms were folded by k_frame_hist_sum)
+    const uint32_t kclusters = tile_clusters(ws.tiles[tile]);
     for (uint32_t idx = tid; idx < kHfClusters * kHfTokens; idx += kAnsThreads) {
-        const uint32_t c = idx / kHfTokens, k = idx - c * kHfTokens;
+        const uint32_t c9 = idx / kHfTokens, k = idx - c9 * kHfTokens, c = hf_fold_cluster(c9, kclusters);
         const AnsCluster &cl = s.cl[c];
         const AnsSymInfo si = ans_sym_info(cl.freq[k], c * kAnsTotal + cl.cum[k]);
         s.info4[idx] = make_uint4(si.mc, si.ne, si.nf2, si.b2);
@@ -273,10 +276,10 @@ k_ans_chain(Workspace ws) {
             bw.init(s.dbits, kDBitsWords);
             bw.put_bool(0);                               // use_prefix_codes = 0
             bw.put((uint32_t)(log_alpha - 5), 2);
-            for (int c = 0; c < kHfClusters; c++)
+            for (uint32_t c = 0; c < kclusters; c++)
                 ps_put_hybrid_cfg(bw, 4, 1, 0, log_alpha);
             s.dhist_off = bw.bitlen();
-            for (int c = 0; c < kHfClusters; c++)
+            for (uint32_t c = 0; c < kclusters; c++)
                 ans_put_histogram(bw, s.cl[c].freq, s.alpha[c]);
             bw.flush_partial();
             s.dbitlen = bw.bitlen();

@@ -44,11 +44,18 @@ k_frame_hist_sum(Workspace ws) {
     if (!(t.flags & kTilePrefix))
         return;
     constexpr uint32_t kH = kHfClusters * kHfTokens;
+    __shared__ uint32_t s_sum[kH];
     uint32_t sum = 0;
     for (uint32_t g = 0; g < t.frame_groups; g++)
         sum += ws.hist[(size_t)(slot + 1 + g) * kH + tid];
+    // fold the nine local clusters onto the preset's (fewer) clusters when the frame has many presets
+    const uint32_t K = tile_clusters(ws.tiles[slot + 1]);
+    s_sum[tid] = 0;
+    __syncthreads();
+    atomicAdd(&s_sum[hf_fold_cluster(tid / kHfTokens, K) * kHfTokens + tid % kHfTokens], sum);
+    __syncthreads();
     for (uint32_t g = 0; g < t.frame_groups; g++)
-        ws.hist[(size_t)(slot + 1 + g) * kH + tid] = sum;
+        ws.hist[(size_t)(slot + 1 + g) * kH + tid] = s_sum[tid];
 }
 
 // quantised LF value of channel c at block (bx, by) of the frame
@@ -219,6 +226,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t W = info[0], H = info[1], with_header = info[2], max_alpha = info[3], n = info[4], G = info[5];
+    const uint32_t K = hf_clusters_for_presets(n);   // HF clusters per preset
     const uint32_t *sent = info + 8, *len1 = info + 8 + n, *elen = info + 8 + 2 * n;
     const uint32_t cx = (W + 2047) >> 11;
     const uint32_t frame_gx = (W + 255) >> 8, frame_gy = (H + 255) >> 8;
@@ -227,7 +235,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     // scratch: [toc: toc_size][inv: toc_size][lehmer+1: toc_size + 1][tokens ...]
     uint32_t *toc = scratch, *inv = toc + toc_size, *leh = inv + toc_size, *tokens = leh + toc_size + 1;
     const uint32_t fixed = 3 * toc_size + 1;
-    const bool bad = frame_gx * frame_gy != G || fixed + 1485u * n + 4096u > scratch_words || n == 0 || n > 28;
+    const bool bad = frame_gx * frame_gy != G || fixed + 1485u * n + 4096u > scratch_words || n == 0 || n > 256;
     if (bad) {
         if (tid == 0) { res[0] = res[1] = 0; res[2] = 1; }
         return;
@@ -272,7 +280,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     b2.put(n - 1, ceil_log2_u32(G));                      // num_presets - 1 (encoder.c:961)
     b2.put(2, 2);                                         // HF pass order
     b2.put_bool(0);                                       // ANS stream: no lz77
-    {   // context map of 1485 n contexts onto 9 n clusters: never "simple" for n >= 2 (entropy.c:108-167)
+    {   // context map of 1485 n contexts onto K n clusters: never "simple" for n >= 2 (entropy.c:108-167)
         b2.put_bool(0);
         b2.put_bool(1);                                   // move-to-front
         uint16_t *idx = reinterpret_cast<uint16_t *>(tokens + 1485u * n / 2 + 2048u);   // upper part of the token scratch
@@ -280,7 +288,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         for (int i = 0; i < 256; i++)
             mtf[i] = (uint8_t)i;
         for (uint32_t j = 0; j < 1485u * n; j++) {
-            const uint8_t c = (uint8_t)(9u * (j / 1485u) + hf_context_cluster(j % 1485u));
+            const uint8_t c = (uint8_t)(K * (j / 1485u) + hf_fold_cluster(hf_context_cluster(j % 1485u), K));
             int k = 0;
             while (mtf[k] != c)
                 k++;
@@ -302,7 +310,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         err |= kErrAlphabet;
     b2.put_bool(0);                                       // use_prefix_codes = 0
     b2.put((uint32_t)(log_alpha - 5), 2);
-    for (uint32_t c = 0; c < 9 * n; c++)
+    for (uint32_t c = 0; c < K * n; c++)
         ps_put_hybrid_cfg(b2, 4, 1, 0, log_alpha);
     {
         const uint32_t *p = info + 8 + 2 * n + G;
@@ -339,7 +347,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
         p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
         s.work.error = 0;
-        ps_encode_stream(s.work, tokens, 4096u, p, 1 + toc_size, WordValues{leh}, bh);
+        ps_encode_stream(s.work, tokens, scratch_words - fixed, p, 1 + toc_size, WordValues{leh}, bh);
     }
     bh.align_byte();
     bool ok = put_toc_value(bh, 16);

@@ -167,6 +167,7 @@ typedef struct HydbFrame {
     uint32_t preset;         /* HF preset of this LF group (its raster index while the image has <= 256 of them) */
     uint32_t preset_bits;    /* ceil(log2(number of presets)) */
     uint32_t alpha_floor;    /* largest token alphabet of the parts sent before (the reference's running maximum) */
+    uint32_t clusters_per_preset; /* 9, or 3 / 2 / 1 when the image has more than 28 / 85 / 128 LF groups; 0 = 9 */
 } HydbFrame;
 /* ANS model of the slot's group after hydb_engine_finish: the nine cluster histograms as a bit string
  * (bits_out: >= 384 words; *nbits), and the largest token alphabet seen in that frame part. */

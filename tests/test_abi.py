@@ -76,11 +76,11 @@ def test_destroy_null_is_ok(product_lib):
 
 
 def test_unsupported_modes_fail_loudly(product_lib):
-    """One-frame mode with more than 28 LF groups of 2048x2048 is the only geometry not built."""
+    """One-frame mode with more than 256 LF groups of 2048x2048 is the only geometry not built."""
     enc = HYDEncoder(product_lib)
-    assert enc.set_metadata(2048 * 29, 1024, 0, -1, -1) == abi.HYD_API_ERROR
+    assert enc.set_metadata(2048 * 257, 8, 0, -1, -1) == abi.HYD_API_ERROR
     assert "one-frame mode is limited" in enc.error_message_get()
-    assert enc.set_metadata(2048 * 7, 2048 * 4, 0, -1, -1) == abi.HYD_OK   # 28 LF groups
+    assert enc.set_metadata(2048 * 16, 2048 * 16, 0, -1, -1) == abi.HYD_OK   # 256 LF groups
     assert enc.set_metadata(1024, 1024, 0, 1, 1) == abi.HYD_OK       # larger tiles: multi-group frames
     assert enc.set_metadata(1024, 1024, 0, 3, 0) == abi.HYD_OK
     assert enc.set_metadata(2048, 1100, 0, -1, -1) == abi.HYD_OK    # one LF group

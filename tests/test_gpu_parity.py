@@ -306,6 +306,10 @@ def test_multi_group_frames_match_reference(product_lib, reflib, case):
     (4200, 300, 8, 0, 3, None),                       # three LF groups in a row, the last 104 px wide
     (300, 4200, 16, 1, 4, None),                      # a column of three, 16-bit linear
     (2100, 2060, 8, 0, 5, [(1, 1), (0, 0), (1, 0), (0, 1)]),   # sent out of raster order
+    (2048 * 28 + 5, 9, 8, 0, 6, None),                # 29 LF groups: three HF clusters per preset
+    (2048 * 85 + 300, 8, 8, 0, 7, None),              # 86 LF groups: two clusters per preset
+    (2048 * 128 + 1, 5, 8, 0, 8, None),               # 129 LF groups: one cluster per preset
+    # (256 LF groups run through the same one-cluster path; the reference itself needs many minutes there)
 ])
 def test_one_frame_mode_over_several_lf_groups(product_lib, reflib, case):
     """The reference CLI's default mode for images beyond 2048x2048: one frame, a
