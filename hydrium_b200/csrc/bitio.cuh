@@ -26,6 +26,15 @@ struct BitSink {
         acc = 0;
         overflow = 0;
     }
+    // continue a bit string whose first `bitpos` bits are already in w (the partial last word too)
+    HD void resume(uint32_t *w, uint32_t cap, uint32_t bitpos) {
+        words = w;
+        cap_words = cap;
+        wpos = bitpos >> 5;
+        nacc = bitpos & 31u;
+        acc = nacc && wpos < cap ? (uint64_t)(w[wpos] & ((1u << nacc) - 1u)) : 0;
+        overflow = 0;
+    }
     // append the low n bits of v, n in [0, 32]
     HD void put(uint32_t v, int n) {
         if (n <= 0)

@@ -65,55 +65,290 @@ __device__ __forceinline__ int32_t frame_lf_at(const Workspace &ws, uint32_t slo
     return ws.lfq[((size_t)(slot + 1 + g) * 3 + c) * kMaxBlocks + (by & 31u) * kBlocksPerRow + (bx & 31u)];
 }
 
-__global__ void __launch_bounds__(256)
+// ---- block-wide scans over kLfThreads threads ------------------------------------------------------
+constexpr int kLfThreads = 1024;
+
+// exclusive scan; OP(a, b) associative, `identity` its neutral element.  Also returns the total.
+template <typename Op>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t identity, Op op, uint32_t *s_warp,
+                                                         uint32_t &total) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d)
+            incl = op(o, incl);
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (uint32_t)d)
+                wi = op(o, wi);
+        }
+        s_warp[32 + lane] = wi;   // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t warp_excl = warp ? s_warp[32 + warp - 1] : identity;
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    const uint32_t excl = op(warp_excl, lane ? prev : identity);
+    total = s_warp[63];
+    __syncthreads();
+    return excl;
+}
+
+// what position i of the LF value sequence emits (the reference's run-length front end,
+// entropy.c:473-524, as a per-position rule): s / e = first position and end of its maximal run
+struct LfEmit {
+    uint32_t n;          // 0, 1 or 2 symbols
+    uint32_t sym[2];
+};
+__device__ __forceinline__ LfEmit lf_position_symbols(uint32_t v, uint32_t i, uint32_t s, uint32_t e,
+                                                      const PrefixParams &p) {
+    LfEmit out;
+    out.n = 0;
+    const uint32_t o = i - s, r = o & 127u, L = (e - s) - (o & ~127u) < 128u ? (e - s) - (o & ~127u) : 128u;
+    uint32_t res, nb;
+    if (r == 0 || L - 1 <= 3) {   // the chunk's literal, or one of its (at most three) repeats
+        const uint32_t tok = hybrid_token(v, p.split0, p.msb0, p.lsb0, res, nb);
+        out.sym[0] = ps_pack(tok, 0, nb, res);
+        out.n = 1;
+    } else if (r == 1) {          // length token + distance symbol
+        out.sym[0] = ps_pack(p.lz_min_symbol + (L - 1 - 3), 0, 0, 0);
+        const uint32_t tok = hybrid_token(p.modular ? 1u : 0u, p.split1, p.msb1, p.lsb1, res, nb);
+        out.sym[1] = ps_pack(tok, 1, nb, res);
+        out.n = 2;
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(kLfThreads)
 k_frame_lf(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
+    __shared__ uint32_t s_warp[64];
+    __shared__ uint32_t s_bitpos, s_err;
     const uint32_t slot = blockIdx.x, tid = threadIdx.x;
     const TileDesc t = ws.tiles[slot];
     if (!(t.flags & kTilePrefix))
         return;
+    PrefixWork &w = s.work;
     const uint32_t vbw = (t.frame_w + 7) >> 3, vbh = (t.frame_h + 7) >> 3, nb = vbw * vbh, total = 3 * nb;
+    const PrefixParams prm = lf_stream_params();
+    const uint32_t lz = prm.lz_min_symbol;
+    uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
+    uint8_t *slab = ws.slab + (size_t)slot * kSlabBytes;
+    uint32_t *outw = reinterpret_cast<uint32_t *>(slab + kPrefixLfOffset);
+    constexpr uint32_t kOutWords = (kSlabBytes - kPrefixLfOffset - kPrefixTailReserve) / 4;
     // ---- residuals of the whole LF image, channel order Y, X, B (encoder.c:574-592) ---------------
     uint16_t *resid = reinterpret_cast<uint16_t *>(ws.coef + (size_t)slot * kMaxBlocks * 3 * 64);   // 196 608 x u16
-    uint32_t too_big = 0;
-    for (uint32_t i = tid; i < total; i += 256) {
+    uint32_t my_err = 0;
+    for (uint32_t i = tid; i < total; i += kLfThreads) {
         const uint32_t ci = i / nb, r = i - ci * nb;
         const uint32_t c = ci < 2 ? 1 - ci : ci;
         const uint32_t by = r / vbw, bx = r - by * vbw;
         const int32_t v = frame_lf_at(ws, slot, t.frame_gx, c, bx, by);
         const int32_t up = by ? frame_lf_at(ws, slot, t.frame_gx, c, bx, by - 1) : 0;
-        const int32_t w = bx ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by) : up;
-        const int32_t n = by ? up : w;
-        const int32_t nw = (bx && by) ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by - 1) : w;
-        const int32_t lo = w < n ? w : n, hi = w < n ? n : w;
-        int32_t pred = w + n - nw;
+        const int32_t wv = bx ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by) : up;
+        const int32_t n = by ? up : wv;
+        const int32_t nw = (bx && by) ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by - 1) : wv;
+        const int32_t lo = wv < n ? wv : n, hi = wv < n ? n : wv;
+        int32_t pred = wv + n - nw;
         pred = pred < lo ? lo : (pred > hi ? hi : pred);
         const uint32_t packed = pack_signed(v - pred);
         if (packed > 0xFFFFu)
-            too_big = 1;   // would need more than 12 residue bits: outside what the LF coder holds
+            my_err = kErrLfAlphabet;   // would need more than 12 residue bits: outside what the LF coder holds
         resid[i] = (uint16_t)(packed > 0xFFFFu ? 0xFFFFu : packed);
     }
-    if (too_big)
-        atomicOr(&ws.tile_err[slot], (uint32_t)kErrLfAlphabet);
+    // ---- section head (one thread; uses the prefix work area for the small MA-tree stream) ---------
+    BitSink bw;
+    if (tid == 0) {
+        s_err = 0;
+        w.error = 0;
+        bw.init(outw, kOutWords);
+        put_lf_group_head(w, syms, bw);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads)
+        w.freq[i] = 0;
+    if (tid == 0)
+        w.alpha0 = w.alpha1 = 0;
+    __syncthreads();
+    // ---- the LF stream's symbols, in parallel: thread = contiguous range of positions ---------------
+    const uint32_t per = (total + kLfThreads - 1) / kLfThreads;
+    const uint32_t a = tid * per < total ? tid * per : total, b = a + per < total ? a + per : total;
+    // last run start inside [a, b) (+1; 0 = none) and first run start inside it (total = none)
+    uint32_t last_start = 0, first_start = total;
+    for (uint32_t i = a; i < b; i++) {
+        const bool st = i == 0 || resid[i] != resid[i - 1];
+        if (st) {
+            last_start = i + 1;
+            if (first_start == total)
+                first_start = i;
+        }
+    }
+    uint32_t dummy;
+    const uint32_t carry_start = block_exclusive_scan(last_start, 0u, [](uint32_t x, uint32_t y) { return x > y ? x : y; },
+                                                      s_warp, dummy);   // start (+1) of the run reaching into a
+    // next run start at or after b: exclusive scan from the right of first_start with min
+    uint32_t carry_end;
+    {
+        // reverse the thread order by scanning mirrored values
+        __shared__ uint32_t s_first[kLfThreads];
+        s_first[kLfThreads - 1 - tid] = first_start;
+        __syncthreads();
+        const uint32_t mirrored = s_first[tid];
+        const uint32_t ex = block_exclusive_scan(mirrored, total, [](uint32_t x, uint32_t y) { return x < y ? x : y; },
+                                                 s_warp, dummy);
+        s_first[tid] = ex;
+        __syncthreads();
+        carry_end = s_first[kLfThreads - 1 - tid];
+        __syncthreads();
+    }
+    auto run_end = [&](uint32_t i) -> uint32_t {   // end of the run containing position i (i in [a, b))
+        uint32_t e = i + 1;
+        while (e < b && resid[e] == resid[e - 1])
+            e++;
+        return e < b ? e : carry_end;
+    };
+    // pass 1: count
+    uint32_t count = 0;
+    {
+        uint32_t i = a;
+        uint32_t sr = (a < b && !(a == 0 || resid[a] != resid[a - 1])) ? carry_start - 1 : a;
+        while (i < b) {
+            const uint32_t e = run_end(i);
+            const uint32_t v = resid[i];
+            const uint32_t stop = e < b ? e : b;
+            for (; i < stop; i++)
+                count += lf_position_symbols(v, i, sr, e, prm).n;
+            sr = i;
+        }
+    }
+    uint32_t nsyms_total;
+    uint32_t off = block_exclusive_scan(count, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, nsyms_total);
+    if (nsyms_total > (uint32_t)kMaxHfSyms)
+        my_err |= kErrLfCapacity;
+    // pass 2: emit + histogram
+    if (nsyms_total <= (uint32_t)kMaxHfSyms) {
+        uint32_t i = a;
+        uint32_t sr = (a < b && !(a == 0 || resid[a] != resid[a - 1])) ? carry_start - 1 : a;
+        while (i < b) {
+            const uint32_t e = run_end(i);
+            const uint32_t v = resid[i];
+            const uint32_t stop = e < b ? e : b;
+            for (; i < stop; i++) {
+                const LfEmit em = lf_position_symbols(v, i, sr, e, prm);
+                for (uint32_t k = 0; k < em.n; k++) {
+                    const uint32_t sym = em.sym[k];
+                    const uint32_t token = sym & 0x7FFFu, cluster = (sym >> 15) & 1u, nbits = (sym >> 16) & 0xFu;
+                    bool fits;
+                    if (cluster)
+                        fits = token < (uint32_t)kDistBins;
+                    else if (token >= lz)
+                        fits = token - lz < (uint32_t)kLzBins;
+                    else
+                        fits = token < (uint32_t)kLitBins;
+                    if (!fits || nbits > 12) {
+                        my_err |= kErrLfAlphabet;
+                        syms[off++] = ps_pack(0, 0, 0, 0);
+                        continue;
+                    }
+                    syms[off++] = sym;
+                    atomicAdd(&w.freq[ps_bin(token, cluster, lz)], 1u);
+                    if (cluster)
+                        atomicMax(&w.alpha1, token + 1);
+                    else
+                        atomicMax(&w.alpha0, token + 1);
+                }
+            }
+            sr = i;
+        }
+    }
+    if (my_err)
+        atomicOr(&s_err, my_err);
+    __syncthreads();
+    // ---- stream header: code construction, one thread -----------------------------------------------
+    if (tid == 0) {
+        w.nsyms = nsyms_total;
+        ps_put_header(w, bw, prm);
+        bw.flush_partial();
+        s_bitpos = bw.bitlen();
+        if (bw.overflow)
+            s_err |= kErrSlab;
+    }
+    __syncthreads();
+    const uint32_t p0 = s_bitpos;
+    const bool ok = !s_err && !w.error;
+    // ---- symbol bits, in parallel: thread = contiguous range of symbols -----------------------------
+    uint32_t total_bits = 0;
+    if (ok) {
+        const uint32_t sper = (nsyms_total + kLfThreads - 1) / kLfThreads;
+        const uint32_t sa = tid * sper < nsyms_total ? tid * sper : nsyms_total;
+        const uint32_t sb = sa + sper < nsyms_total ? sa + sper : nsyms_total;
+        uint32_t bits = 0;
+        for (uint32_t i = sa; i < sb; i++) {
+            const uint32_t sym = syms[i];
+            bits += w.len[ps_bin(sym & 0x7FFFu, (sym >> 15) & 1u, lz)] + ((sym >> 16) & 0xFu);
+        }
+        const uint32_t boff = block_exclusive_scan(bits, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, total_bits);
+        const uint64_t endbit = (uint64_t)p0 + total_bits;
+        if (endbit + 64 > (uint64_t)kOutWords * 32) {
+            if (tid == 0)
+                s_err |= kErrSlab;
+        } else {
+            for (uint32_t wd = (p0 >> 5) + 1 + tid; wd <= (uint32_t)(endbit >> 5) + 1; wd += kLfThreads)
+                outw[wd] = 0;
+            __syncthreads();
+            uint64_t pos = (uint64_t)p0 + boff;
+            uint32_t wpos = (uint32_t)(pos >> 5), nacc = (uint32_t)(pos & 31u);
+            uint64_t acc = 0;
+            auto put = [&](uint32_t v, uint32_t n) {
+                acc |= (uint64_t)v << nacc;
+                nacc += n;
+                if (nacc >= 32) {
+                    atomicOr(&outw[wpos], (uint32_t)acc);
+                    wpos++;
+                    acc >>= 32;
+                    nacc -= 32;
+                }
+            };
+            for (uint32_t i = sa; i < sb; i++) {
+                const uint32_t sym = syms[i];
+                const uint32_t bin = ps_bin(sym & 0x7FFFu, (sym >> 15) & 1u, lz);
+                const uint32_t nbits = (sym >> 16) & 0xFu;
+                if (w.len[bin])
+                    put(w.code[bin], w.len[bin]);
+                if (nbits)
+                    put(sym >> 20, nbits);
+            }
+            if (nacc && (uint32_t)acc)
+                atomicOr(&outw[wpos], (uint32_t)acc);
+        }
+    }
     __syncthreads();
     if (tid != 0)
         return;
-    // ---- LFGroup section, one thread (see the file header) -----------------------------------------
-    uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
-    uint8_t *slab = ws.slab + (size_t)slot * kSlabBytes;
-    BitSink bw;
-    bw.init(reinterpret_cast<uint32_t *>(slab + kPrefixLfOffset), (kSlabBytes - kPrefixLfOffset - kPrefixTailReserve) / 4);
-    s.work.error = 0;
-    put_lf_group_head(s.work, syms, bw);
-    ps_encode_stream(s.work, syms, (uint32_t)kMaxHfSyms, lf_stream_params(), total, StagedValues{resid}, bw);
-    put_hf_metadata(s.work, syms, (uint32_t)kMaxHfSyms, bw, vbw, vbh);
-    bw.align_byte();
-    bw.flush_partial();
-    ws.lfbitlen[slot] = bw.bitlen() >> 3;   // bytes of the LFGroup section
-    uint32_t err = s.work.error;
-    if (bw.overflow)
-        err |= kErrSlab;
+    // ---- the constant HF-metadata image behind it, then the section is closed ------------------------
+    uint32_t err = s_err | w.error;
+    if (!err) {
+        bw.resume(outw, kOutWords, p0 + total_bits);
+        put_hf_metadata(w, syms, (uint32_t)kMaxHfSyms, bw, vbw, vbh);
+        bw.align_byte();
+        bw.flush_partial();
+        ws.lfbitlen[slot] = bw.bitlen() >> 3;   // bytes of the LFGroup section
+        err |= w.error;
+        if (bw.overflow)
+            err |= kErrSlab;
+    } else {
+        ws.lfbitlen[slot] = 0;
+    }
     if (err)
         atomicOr(&ws.tile_err[slot], err);
 }
@@ -386,7 +621,7 @@ void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st
 void launch_frame_lf(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
     prefer_max_shared(k_frame_lf);
     cudaFuncSetAttribute(k_frame_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
-    k_frame_lf<<<nslots, 256, sizeof(FrameShared), st>>>(ws);
+    k_frame_lf<<<nslots, kLfThreads, sizeof(FrameShared), st>>>(ws);
 }
 
 void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st) {

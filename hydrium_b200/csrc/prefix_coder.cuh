@@ -140,6 +140,38 @@ HDN inline void ps_tokenize(PrefixWork &w, uint32_t *syms, uint32_t cap, const P
     }
 }
 
+// the same front end for a value sequence given as (value, length) runs of DISTINCT neighbouring
+// values: O(symbols) instead of O(values) for the long constant stretches of the HF-metadata image
+struct PsRun {
+    uint32_t value, length;
+};
+HDN inline void ps_tokenize_runs(PrefixWork &w, uint32_t *syms, uint32_t cap, const PrefixParams &p,
+                                 const PsRun *runs, uint32_t nruns) {
+    for (int i = 0; i < kAllBins; i++)
+        w.freq[i] = 0;
+    w.nsyms = 0;
+    w.alpha0 = w.alpha1 = 0;
+    for (uint32_t k = 0; k < nruns; k++) {
+        uint32_t left = runs[k].length;
+        const uint32_t v = runs[k].value;
+        while (left) {
+            const uint32_t run = (p.lz_min_symbol && left > 128) ? 128 : (p.lz_min_symbol ? left : 1);
+            ps_literal(w, syms, cap, p, v);
+            const uint32_t rep = run - 1;
+            if (rep > 3) {
+                ps_emit(w, syms, cap, p.lz_min_symbol + (rep - 3), 0, 0, 0, p.lz_min_symbol);
+                uint32_t res, nb;
+                const uint32_t tok = hybrid_token(p.modular ? 1u : 0u, p.split1, p.msb1, p.lsb1, res, nb);
+                ps_emit(w, syms, cap, tok, 1, nb, res, p.lz_min_symbol);
+            } else {
+                for (uint32_t j = 0; j < rep; j++)
+                    ps_literal(w, syms, cap, p, v);
+            }
+            left -= run;
+        }
+    }
+}
+
 // ---- length-limited code lengths on live nodes only ---------------------------------------
 // Simulates reference entropy.c:592-662: pass k takes the two cheapest eligible nodes from array
 // slots [2k, n+k), swaps them into slots 2k / 2k+1 and parks the parent in slot n+k.  Order:

@@ -76,7 +76,13 @@ HDN inline void put_hf_metadata(PrefixWork &w, uint32_t *syms, uint32_t cap, Bit
         p.modular = 1;
         p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
         p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
-        ps_encode_stream(w, syms, cap, p, total, HfMetaValues{zeros_pre, nb}, bw);
+        // three constant stretches: zeros, (hf_mult - 1) * 2 = 8 for every block, zeros
+        (void)total;
+        const PsRun runs[3] = {{0u, zeros_pre}, {8u, nb}, {0u, nb}};
+        ps_tokenize_runs(w, syms, cap, p, runs, 3);
+        ps_put_header(w, bw, p);
+        for (uint32_t i = 0; i < w.nsyms; i++)
+            ps_put_symbol(w, bw, syms[i], p.lz_min_symbol);
     }
 }
 
