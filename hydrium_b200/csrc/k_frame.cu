@@ -303,7 +303,8 @@ k_frame_lf(Workspace ws) {
             if (tid == 0)
                 s_err |= kErrSlab;
         } else {
-            for (uint32_t wd = (p0 >> 5) + 1 + tid; wd <= (uint32_t)(endbit >> 5) + 1; wd += kLfThreads)
+            // flush_partial() wrote word p0 >> 5 only when the header left a partial word there
+            for (uint32_t wd = ((p0 + 31) >> 5) + tid; wd <= (uint32_t)(endbit >> 5) + 1; wd += kLfThreads)
                 outw[wd] = 0;
             __syncthreads();
             uint64_t pos = (uint64_t)p0 + boff;
