@@ -617,6 +617,49 @@ HYDStatusCode hydb_oneframe_finish(HydbEngine *eng, const uint32_t *info, uint32
     return rc;
 }
 
+// Image header of an ICC-tagged codestream (k_icc_header): `icc` is the profile as
+// hyd_set_suggested_icc_profile mangles it.  Synchronous; dst receives [container prefix] + header bytes.
+HYDStatusCode hydb_engine_icc_header(HydbEngine *eng, uint32_t width, uint32_t height, const uint8_t *icc,
+                                     uint32_t icc_size, uint8_t *dst, uint64_t cap, uint64_t *len) {
+    if (!eng || !icc || !icc_size || !dst || !len || icc_size > (64u << 20))
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    const size_t bits_words = (size_t)icc_size * 21 / 32 + 2048;
+    const size_t out_cap = bits_words * 4 + 64;
+    uint8_t *d_icc = nullptr, *d_out = nullptr;
+    uint32_t *d_bits = nullptr, *d_res = nullptr;
+    if (cudaMalloc(&d_icc, icc_size) != cudaSuccess || cudaMalloc(&d_bits, bits_words * 4) != cudaSuccess ||
+        cudaMalloc(&d_out, out_cap) != cudaSuccess || cudaMalloc(&d_res, 16) != cudaSuccess) {
+        cudaFree(d_icc); cudaFree(d_bits); cudaFree(d_out); cudaFree(d_res);
+        eng->error = "device allocation failed";
+        return HYD_NOMEM;
+    }
+    HYDStatusCode rc = HYD_OK;
+    uint32_t res[2] = {0, 0};
+    if (cudaMemcpyAsync(d_icc, icc, icc_size, cudaMemcpyHostToDevice, eng->st) != cudaSuccess)
+        rc = HYD_INTERNAL_ERROR;
+    if (rc == HYD_OK) {
+        launch_icc_header(d_icc, icc_size, width, height, d_bits, (uint32_t)bits_words, d_out, (uint32_t)out_cap, d_res, eng->st);
+        eng->launches++;
+        if (cudaMemcpyAsync(res, d_res, 8, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
+            cudaStreamSynchronize(eng->st) != cudaSuccess)
+            rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc == HYD_OK && (res[1] || res[0] > cap)) {
+        eng->error = res[1] ? "ICC profile could not be entropy coded" : "image header does not fit its buffer";
+        rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc == HYD_OK) {
+        *len = res[0];
+        if (cudaMemcpy(dst, d_out, res[0], cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = HYD_INTERNAL_ERROR;
+    }
+    cudaFree(d_icc); cudaFree(d_bits); cudaFree(d_out); cudaFree(d_res);
+    if (rc != HYD_OK && eng->error.empty())
+        eng->error = "CUDA failure while writing the ICC image header";
+    return rc;
+}
+
 HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     if (!eng)
         return HYD_API_ERROR;

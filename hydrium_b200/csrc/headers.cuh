@@ -30,6 +30,30 @@ HDN inline void put_image_header(BitSink &bw, uint32_t width, uint32_t height) {
     bw.align_byte();
 }
 
+// The same header for an image tagged with an ICC profile (encoder.c:203-225): colour encoding
+// all_default = 0, want_icc = 1, colour space RGB; the entropy-coded profile follows default_matrix
+// and the byte alignment comes after it (k_icc_header in k_frame.cu).
+HDN inline void put_image_header_icc_fields(BitSink &bw, uint32_t width, uint32_t height, uint64_t icc_stream_bytes) {
+    const U32Dist kSize = {{1, 1, 1, 1}, {9, 13, 18, 30}};
+    bw.put(0x0AFF, 17);
+    put_u32(bw, kSize, height);
+    bw.put(0, 3);
+    put_u32(bw, kSize, width);
+    bw.put_bool(0);                // ImageMetadata all_default
+    bw.put_bool(0);                // extra_fields
+    bw.put_bool(0);                // float samples
+    bw.put(0, 2);                  // 8-bit
+    bw.put_bool(1);                // modular 16-bit buffers
+    bw.put(0, 2);                  // no extra channels
+    bw.put_bool(1);                // xyb_encoded
+    bw.put_bool(0);                // colour encoding all_default = 0
+    bw.put_bool(1);                // want_icc
+    bw.put(0, 2);                  // colour space enum: RGB (U32 selector 0 = value 0)
+    put_u64(bw, 0);                // extensions
+    bw.put_bool(1);                // default_matrix
+    put_u64(bw, icc_stream_bytes); // encoded ICC stream length
+}
+
 // level-10 container prefix (encoder.c:23-30), emitted when libhydrium.c:67-68 says so
 HD bool image_needs_level10(uint64_t w, uint64_t h) { return w > (1u << 20) || h > (1u << 20) || w * h > (1u << 28); }
 HDN inline uint32_t put_level10_prefix(uint8_t *dst) {

@@ -48,6 +48,10 @@ struct HYDEncoder {
     int wrote_header;
     int last_tile;
 
+    /* suggested ICC profile, already in the form the image header codes (libhydrium.c:242-305) */
+    uint8_t *icc;
+    size_t icc_size;
+
     /* GPU side */
     int device;
     uint32_t batch;
@@ -168,6 +172,7 @@ HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydriu
         return HYD_OK;
     release_gpu(enc);
     free(enc->pend);
+    free(enc->icc);
     of_reset(enc);
     free(enc);
     return HYD_OK;
@@ -298,11 +303,63 @@ HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-16
 
 HYDRIUM_EXPORT const char *hyd_error_message_get(HYDEncoder *enc) { return enc->error; } /* libhydrium.c:168-170 */
 
+/* what the profile's first 128 bytes are predicted to be (libhydrium.c:205-240): the coded header is
+ * the difference, so a typical display profile turns into a run of zeros */
+static uint8_t icc_header_guess(const uint8_t *h, uint32_t icc_size, unsigned i) {
+    if (i < 4)
+        return (uint8_t)(icc_size >> (8 * (3 - i)));
+    if (i == 8)
+        return 4;
+    if (i >= 12 && i < 24)
+        return (uint8_t)"mntrRGB XYZ "[i - 12];
+    if (i >= 36 && i < 40)
+        return (uint8_t)"acsp"[i - 36];
+    if (i >= 41 && i < 44) {
+        if (h[40] == 'A')
+            return (uint8_t)"PPL"[i - 41];
+        if (h[40] == 'M')
+            return (uint8_t)"SFT"[i - 41];
+        /* "SGI " / "SUNW": the reference indexes its two-byte strings with i - 42, which is -1 for
+         * i = 41 (undefined); the format's predictor expects the vendor's second letter there */
+        if (h[40] == 'S' && h[41] == 'G')
+            return i == 41 ? (uint8_t)'G' : (uint8_t)"I "[i - 42];
+        if (h[40] == 'S' && h[41] == 'U')
+            return i == 41 ? (uint8_t)'U' : (uint8_t)"NW"[i - 42];
+    }
+    switch (i) {
+    case 70: return 246;
+    case 71: return 214;
+    case 73: return 1;
+    case 78: return 211;
+    case 79: return 45;
+    default: break;
+    }
+    if (i >= 80 && i < 84)
+        return h[i - 76];
+    return 0;
+}
+
+static size_t icc_put_varint(uint8_t *dst, uint64_t v) { /* bitwriter.c:174-180 */
+    size_t n = 0;
+    while (v > 0x7f) {
+        dst[n++] = (uint8_t)((v & 0x7f) | 0x80);
+        v >>= 7;
+    }
+    dst[n++] = (uint8_t)v;
+    return n;
+}
+
 HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *enc, const uint8_t *icc_data, size_t icc_size) {
-    /* libhydrium.c:242-259.  ICC tagging is one-frame-only in the reference and outside the
-     * accelerated path; clearing is a no-op, setting reports the tile-mode error. */
-    if (!icc_data && !icc_size)
+    /* libhydrium.c:242-305.  The profile is rearranged here, on the host, exactly as the reference does
+     * at this call: output size, command-stream size, [one "copy the rest" command], the 128-byte
+     * header as prediction residuals, the remaining bytes verbatim.  Its entropy coding into the
+     * image header happens on the device when the first tile is sent (k_icc_header). */
+    if (!icc_data && !icc_size) {
+        free(enc->icc);
+        enc->icc = NULL;
+        enc->icc_size = 0;
         return HYD_OK;
+    }
     if (!enc->one_frame) {
         enc->error = "one-frame mode required to set the suggested ICC profile";
         return HYD_API_ERROR;
@@ -311,8 +368,33 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *enc, cons
         enc->error = "invalid ICC size or data buffer";
         return HYD_API_ERROR;
     }
-    enc->error = "ICC tagging is not supported by the B200 encoder";
-    return HYD_API_ERROR;
+    if (icc_size > (63u << 20)) {
+        enc->error = "ICC profiles above 63 MiB are not supported by the B200 encoder";
+        return HYD_API_ERROR;
+    }
+    uint8_t *m = malloc(icc_size + 32);
+    if (!m)
+        return HYD_NOMEM;
+    const size_t head = icc_size < 128 ? icc_size : 128, rest = icc_size - head;
+    size_t n = icc_put_varint(m, icc_size);
+    unsigned log2rest = 0;
+    while (rest >> (log2rest + 1))
+        log2rest++;
+    n += icc_put_varint(m + n, rest ? 3 + log2rest / 7 : 0);
+    if (rest) {
+        n += icc_put_varint(m + n, 0);   /* empty tag list */
+        m[n++] = 1;                      /* command 1: copy `rest` bytes */
+        n += icc_put_varint(m + n, rest);
+    }
+    for (unsigned i = 0; i < head; i++)
+        m[n + i] = (uint8_t)(icc_data[i] - icc_header_guess(icc_data, (uint32_t)icc_size, i));
+    n += head;
+    memcpy(m + n, icc_data + head, rest);
+    n += rest;
+    free(enc->icc);
+    enc->icc = m;
+    enc->icc_size = n;
+    return HYD_OK;
 }
 
 static HYDStatusCode pend_reserve(HYDEncoder *enc, size_t extra) {
@@ -375,6 +457,23 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
 }
 
 /* encode everything queued and move the frames to the pending-output queue */
+/* ICC-tagged image: the image header (with the entropy-coded profile) goes out ahead of the first
+ * frame, from its own kernel; the frame paths then run as if the header had been written already */
+static HYDStatusCode emit_icc_header(HYDEncoder *enc) {
+    const size_t cap = enc->icc_size * 3 + 16384;
+    HYDStatusCode rc = pend_reserve(enc, cap);
+    if (rc < HYD_ERROR_START)
+        return rc;
+    uint64_t len = 0;
+    rc = hydb_engine_icc_header(enc->engine, (uint32_t)enc->metadata.width, (uint32_t)enc->metadata.height, enc->icc,
+                                (uint32_t)enc->icc_size, enc->pend + enc->pend_len, cap, &len);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    enc->pend_len += (size_t)len;
+    enc->wrote_header = 1;
+    return HYD_OK;
+}
+
 static HYDStatusCode run_batch(HYDEncoder *enc) {
     if (!enc->queued)
         return HYD_OK;
@@ -665,6 +764,11 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     HYDStatusCode rc = ensure_gpu(enc);
     if (rc < HYD_ERROR_START)
         return rc;
+    if (enc->icc && !enc->wrote_header) { /* encoder.c:490-494 with encoder.c:203-236 */
+        rc = emit_icc_header(enc);
+        if (rc < HYD_ERROR_START)
+            return rc;
+    }
     const uint32_t tw = (uint32_t)(((uint64_t)tile_x + 1) * span_x > W ? W - (uint64_t)tile_x * span_x : span_x);
     const uint32_t th = (uint32_t)(((uint64_t)tile_y + 1) * span_y > H ? H - (uint64_t)tile_y * span_y : span_y);
     /* encoder.c:482-485 */

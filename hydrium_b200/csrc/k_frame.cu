@@ -608,6 +608,207 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     res[2] = err;
 }
 
+// ---- image header of an ICC-tagged image (hyd_set_suggested_icc_profile) ----------------------------
+// reference: encoder.c:122-162 (context model), 203-236 (header fields + the profile as a prefix-coded
+// stream over 41 contexts in 9 clusters, default hybrid config 4/1/1, no lz77).  `icc` is the profile
+// as hyd_set_suggested_icc_profile mangles it (libhydrium.c:242-305; host code, hyd_api.c).
+// One CTA: the histograms and the symbol bits are done by all threads, the code construction by one.
+__device__ __forceinline__ uint32_t icc_context_of(uint32_t i, uint32_t b1, uint32_t b2) {
+    if (i <= 128)
+        return 0;
+    auto alpha = [](uint32_t b) { return (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z'); };
+    auto digit = [](uint32_t b) { return (b >= '0' && b <= '9') || b == '.' || b == ','; };
+    uint32_t p1, p2;
+    if (alpha(b1)) p1 = 0;
+    else if (digit(b1)) p1 = 1;
+    else if (b1 <= 1) p1 = b1 + 2;
+    else if (b1 < 16) p1 = 4;
+    else if (b1 > 240 && b1 < 255) p1 = 5;
+    else if (b1 == 255) p1 = 6;
+    else p1 = 7;
+    if (alpha(b2)) p2 = 0;
+    else if (digit(b2)) p2 = 1;
+    else if (b2 < 16) p2 = 2;
+    else if (b2 > 240) p2 = 3;
+    else p2 = 4;
+    return 1 + p1 + p2 * 8;
+}
+// contexts 1 + p1 + 8 * p2 share cluster 1 + p1; context 0 (the 128-byte header) is cluster 0
+__device__ __forceinline__ uint32_t icc_cluster_of(uint32_t ctx) { return ctx ? 1u + ((ctx - 1u) & 7u) : 0u; }
+constexpr uint32_t kIccClusters = 9, kIccContexts = 41, kIccBins = 32;   // byte tokens under 4/1/1 are < 32
+
+__device__ __forceinline__ uint32_t icc_symbol(const uint8_t *__restrict__ icc, uint32_t i, uint32_t &cluster,
+                                               uint32_t &res, uint32_t &nb) {
+    const uint32_t b1 = i >= 1 ? icc[i - 1] : 0u, b2 = i >= 2 ? icc[i - 2] : 0u;
+    cluster = icc_cluster_of(icc_context_of(i, b1, b2));
+    return hybrid_token(icc[i], 4, 1, 1, res, nb);
+}
+
+__global__ void __launch_bounds__(kLfThreads)
+k_icc_header(const uint8_t *__restrict__ icc, uint32_t n, uint32_t W, uint32_t H, uint32_t *bits, uint32_t bits_words,
+             uint8_t *out, uint32_t out_cap, uint32_t *res_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
+    __shared__ uint32_t s_warp[64];
+    __shared__ uint32_t s_alpha[kIccClusters];
+    __shared__ uint32_t s_bitpos, s_err;
+    __shared__ uint16_t s_idx[kIccContexts];
+    PrefixWork &w = s.work;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads)
+        w.freq[i] = 0, w.len[i] = 0, w.code[i] = 0;
+    if (tid < kIccClusters)
+        s_alpha[tid] = 0;
+    BitSink bw;
+    if (tid == 0) {
+        s_err = 0;
+        w.error = 0;
+        bw.init(bits, bits_words);
+        put_image_header_icc_fields(bw, W, H, n);
+        bw.put_bool(0);    // no lz77
+        bw.put_bool(0);    // cluster map: 9 clusters need 4 bits per entry, so not the simple form ...
+        bw.put_bool(1);    // ... but move-to-front + a nested prefix stream (entropy.c:125-158)
+        uint8_t mtf[kIccClusters];
+        for (uint32_t k = 0; k < kIccClusters; k++)
+            mtf[k] = (uint8_t)k;
+        for (uint32_t j = 0; j < kIccContexts; j++) {
+            const uint8_t c = (uint8_t)icc_cluster_of(j);
+            int k = 0;
+            while (mtf[k] != c)
+                k++;
+            s_idx[j] = (uint16_t)k;
+            for (; k > 0; k--)
+                mtf[k] = mtf[k - 1];
+            mtf[0] = c;
+        }
+        PrefixParams p;
+        p.num_plain_dists = 1;
+        p.lz_min_symbol = 64;
+        p.modular = 0;
+        p.split0 = 4; p.msb0 = 1; p.lsb0 = 0;
+        p.split1 = 4; p.msb1 = 1; p.lsb1 = 0;
+        ps_encode_stream(w, s.s2, 128, p, kIccContexts, ClusterMapMtf{s_idx}, bw);
+        if (w.error)
+            s_err |= kErrSlab;
+        for (int i = 0; i < kAllBins; i++)
+            w.freq[i] = 0, w.len[i] = 0, w.code[i] = 0;
+    }
+    __syncthreads();
+    // ---- histograms: bin = cluster * 32 + token ------------------------------------------------------
+    for (uint32_t i = tid; i < n; i += kLfThreads) {
+        uint32_t c, r, nb;
+        const uint32_t tok = icc_symbol(icc, i, c, r, nb);
+        atomicAdd(&w.freq[c * kIccBins + tok], 1u);
+        atomicMax(&s_alpha[c], tok + 1);
+    }
+    __syncthreads();
+    // ---- stream header: prefix codes, hybrid configs, alphabet sizes, the nine codes ----------------
+    if (tid == 0) {
+        bw.put_bool(1);   // use prefix codes
+        for (uint32_t c = 0; c < kIccClusters; c++)
+            ps_put_hybrid_cfg(bw, 4, 1, 1, 15);
+        for (uint32_t c = 0; c < kIccClusters; c++) {   // entropy.c:835-844
+            if (s_alpha[c] <= 1) {
+                bw.put_bool(0);
+                continue;
+            }
+            bw.put_bool(1);
+            const int nb = floor_log2_u32(s_alpha[c] - 1);
+            bw.put((uint32_t)nb, 4);
+            bw.put(s_alpha[c] - 1, nb);
+        }
+        for (uint32_t c = 0; c < kIccClusters; c++)
+            if (s_alpha[c] > 1)
+                ps_put_cluster_code(w, bw, c * kIccBins, kIccBins, s_alpha[c], 0, true);
+        bw.flush_partial();
+        s_bitpos = bw.bitlen();
+        if (bw.overflow || w.error)
+            s_err |= kErrSlab;
+    }
+    __syncthreads();
+    const uint32_t p0 = s_bitpos;
+    // ---- symbol bits: thread = contiguous range of profile bytes --------------------------------------
+    uint32_t total_bits = 0;
+    if (!s_err) {
+        const uint32_t per = (n + kLfThreads - 1) / kLfThreads;
+        const uint32_t a = tid * per < n ? tid * per : n, b = a + per < n ? a + per : n;
+        uint32_t cnt = 0;
+        for (uint32_t i = a; i < b; i++) {
+            uint32_t c, r, nb;
+            const uint32_t tok = icc_symbol(icc, i, c, r, nb);
+            cnt += w.len[c * kIccBins + tok] + nb;
+        }
+        const uint32_t boff = block_exclusive_scan(cnt, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, total_bits);
+        const uint64_t endbit = (uint64_t)p0 + total_bits;
+        if (endbit + 64 > (uint64_t)bits_words * 32) {
+            if (tid == 0)
+                s_err |= kErrSlab;
+        } else {
+            for (uint32_t wd = ((p0 + 31) >> 5) + tid; wd <= (uint32_t)(endbit >> 5) + 1; wd += kLfThreads)
+                bits[wd] = 0;
+            __syncthreads();
+            uint64_t pos = (uint64_t)p0 + boff;
+            uint32_t wpos = (uint32_t)(pos >> 5), nacc = (uint32_t)(pos & 31u);
+            uint64_t acc = 0;
+            auto put = [&](uint32_t v, uint32_t nbit) {
+                acc |= (uint64_t)v << nacc;
+                nacc += nbit;
+                if (nacc >= 32) {
+                    atomicOr(&bits[wpos], (uint32_t)acc);
+                    wpos++;
+                    acc >>= 32;
+                    nacc -= 32;
+                }
+            };
+            for (uint32_t i = a; i < b; i++) {
+                uint32_t c, r, nb;
+                const uint32_t tok = icc_symbol(icc, i, c, r, nb);
+                const uint32_t bi = c * kIccBins + tok;
+                if (w.len[bi])
+                    put(w.code[bi], w.len[bi]);
+                if (nb)
+                    put(r, nb);
+            }
+            if (nacc && (uint32_t)acc)
+                atomicOr(&bits[wpos], (uint32_t)acc);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && !s_err) {
+        bw.resume(bits, bits_words, p0 + total_bits);
+        bw.align_byte();
+        bw.flush_partial();
+        s_bitpos = bw.bitlen() >> 3;
+        if (bw.overflow)
+            s_err |= kErrSlab;
+    }
+    __syncthreads();
+    const uint32_t nbytes = s_bitpos;
+    uint32_t pre = 0;
+    if (image_needs_level10(W, H))
+        pre = 49;
+    if (!s_err && pre + nbytes <= out_cap) {
+        if (pre && tid == 0)
+            put_level10_prefix(out);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(bits);
+        for (uint32_t i = tid; i < nbytes; i += kLfThreads)
+            out[pre + i] = src[i];
+    } else if (tid == 0) {
+        s_err |= kErrSlab;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        res_out[0] = pre + nbytes;
+        res_out[1] = s_err;
+    }
+}
+
+void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H, uint32_t *d_bits, uint32_t bits_words,
+                       uint8_t *d_out, uint32_t out_cap, uint32_t *d_res, cudaStream_t st) {
+    cudaFuncSetAttribute(k_icc_header, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
+    k_icc_header<<<1, kLfThreads, sizeof(FrameShared), st>>>(d_icc, n, W, H, d_bits, bits_words, d_out, out_cap, d_res);
+}
+
 void launch_oneframe_finish(const uint32_t *d_info, uint32_t info_words, uint32_t *d_scratch, uint32_t scratch_words,
                             uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, cudaStream_t st) {
     cudaFuncSetAttribute(k_oneframe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));

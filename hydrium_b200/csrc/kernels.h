@@ -71,6 +71,10 @@ void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st);
 // out = [head: head_cap bytes][hf_global: hf_cap bytes][4 words: head_len, hf_len, error, -]
 void launch_oneframe_finish(const uint32_t *d_info, uint32_t info_words, uint32_t *d_scratch, uint32_t scratch_words,
                             uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, cudaStream_t st);
+// image header of an ICC-tagged image: [49-byte container prefix] signature, size, metadata, entropy-coded
+// profile, byte aligned; d_res = {bytes, error}
+void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H, uint32_t *d_bits, uint32_t bits_words,
+                       uint8_t *d_out, uint32_t out_cap, uint32_t *d_res, cudaStream_t st);
 // compaction: out[prefix_len + out_off[i] ...] = frame i ; total written to ws.out_off[ntiles]
 void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
                    uint32_t *d_overflow, cudaStream_t st);

@@ -423,8 +423,9 @@ HDN inline void ps_clc_lengths(PrefixWork &w, ClcWork &c) {
         w.error |= kErrHuffman;
 }
 
+// `dense`: the cluster's tokens are first_bin-relative bin numbers (distance cluster, ICC clusters)
 HDN inline void ps_put_complex_code(PrefixWork &w, BitSink &bw, uint32_t first_bin, uint32_t nbins,
-                                    uint32_t alphabet, uint32_t lz_min) {
+                                    uint32_t alphabet, uint32_t lz_min, bool dense = false) {
     static const uint8_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};  // entropy.c:42
     static const uint8_t kL0Bits[6] = {0, 7, 3, 2, 1, 15};                                             // entropy.c:44-46
     static const uint8_t kL0Len[6] = {2, 4, 3, 2, 2, 4};
@@ -437,7 +438,7 @@ HDN inline void ps_put_complex_code(PrefixWork &w, BitSink &bw, uint32_t first_b
     for (uint32_t b = first_bin; b < first_bin + nbins; b++) {
         if (!w.len[b])
             continue;
-        const uint32_t tok = ps_bin_token(b, lz_min);
+        const uint32_t tok = dense ? b - first_bin : ps_bin_token(b, lz_min);
         ps_zero_run_count(tok - prev_tok_p1, c.freq);
         c.freq[w.len[b]]++;
         prev_tok_p1 = tok + 1;
@@ -461,7 +462,7 @@ HDN inline void ps_put_complex_code(PrefixWork &w, BitSink &bw, uint32_t first_b
     for (uint32_t b = first_bin; b < first_bin + nbins; b++) {
         if (!w.len[b])
             continue;
-        const uint32_t tok = ps_bin_token(b, lz_min);
+        const uint32_t tok = dense ? b - first_bin : ps_bin_token(b, lz_min);
         ps_zero_run_put(bw, c, tok - prev_tok_p1);
         bw.put(c.code[w.len[b]], c.len[w.len[b]]);
         prev_tok_p1 = tok + 1;
@@ -492,7 +493,7 @@ HDN inline void ps_put_cluster_code(PrefixWork &w, BitSink &bw, uint32_t first_b
             break;
     }
     if (used > 4) {
-        ps_put_complex_code(w, bw, first_bin, nbins, alphabet, lz_min);
+        ps_put_complex_code(w, bw, first_bin, nbins, alphabet, lz_min, dist_cluster);
         ps_assign_codes(w, first_bin, nbins);
         return;
     }

@@ -22,7 +22,7 @@ HYDB_SYMBOLS = (
     "hydb_image_header", "hydb_host_alloc", "hydb_host_free", "hydb_device_alloc", "hydb_device_free",
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
     "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
-    "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish",
+    "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header",
 )
 
 

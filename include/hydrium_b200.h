@@ -93,9 +93,9 @@ HYDRIUM_EXPORT HYDStatusCode hyd_release_output_buffer(HYDEncoder *encoder, size
 HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *encoder);
 /* libhydrium.h:295 */
 HYDRIUM_EXPORT const char *hyd_error_message_get(HYDEncoder *encoder);
-/* libhydrium.h:313-314.  ICC tagging is a one-frame-mode side feature outside the accelerated
- * path: NULL/0 clears (HYD_OK); anything else returns HYD_API_ERROR with the reference's message
- * for tile mode. */
+/* libhydrium.h:296-314.  One-frame mode only, like the reference ("one-frame mode required to set the
+ * suggested ICC profile" otherwise); NULL/0 clears.  The profile is copied; it is entropy coded into
+ * the image header when the first tile is sent. */
 HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *encoder, const uint8_t *icc_data,
                                                            size_t icc_size);
 
@@ -216,6 +216,13 @@ HYDRIUM_EXPORT HYDStatusCode hydb_engine_stage_ms(HydbEngine *engine, double out
 
 /* image header bytes (with the level-10 container prefix where the reference emits it) */
 HYDRIUM_EXPORT int64_t hydb_image_header(uint32_t width, uint32_t height, uint8_t *dst, uint64_t cap);
+
+/* Image header of a codestream tagged with an ICC profile (reference: encoder.c:203-236, the 41-context
+ * prefix-coded profile stream): `mangled` is the profile as hyd_set_suggested_icc_profile prepares it
+ * (libhydrium.c:242-305).  Runs k_icc_header on the engine's device; host buffers; synchronous. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_icc_header(HydbEngine *engine, uint32_t width, uint32_t height,
+                                                    const uint8_t *mangled, uint32_t mangled_size, uint8_t *dst,
+                                                    uint64_t cap, uint64_t *len);
 
 /* page-locked host memory / device memory helpers for callers without a CUDA runtime of their own */
 HYDRIUM_EXPORT void *hydb_host_alloc(size_t bytes);

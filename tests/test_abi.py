@@ -63,6 +63,11 @@ def _api_script(lib):
     ret, written = enc.release_output_buffer()
     rec(ret)
     res.append(("written", written))
+    rec(enc.set_metadata(64, 64, 0, -1, -1))                          # one-frame mode: profiles are accepted
+    rec(enc.set_suggested_icc_profile(b""))                           # non-null pointer, zero size
+    rec(enc.set_suggested_icc_profile(bytes(range(200))))
+    rec(enc.set_suggested_icc_profile(bytes(60)))                     # shorter than the 128-byte header
+    rec(enc.set_suggested_icc_profile(None))
     enc.destroy()
     return res
 

@@ -553,3 +553,98 @@ def test_config5_streaming_window(product_lib, oracle):
         assert got == want
         eng.device_free(d_in)
         eng.device_free(d_out)
+
+
+def _fake_icc(size: int, seed: int, vendor: bytes = b"APPL") -> bytes:
+    """A profile-shaped byte string: a plausible 128-byte header (so that the header predictor mostly
+    hits), a tag table and a mix of text, small numbers and noise behind it, cut to `size` bytes."""
+    rng = np.random.default_rng(seed)
+    head = bytearray(128)
+    head[0:4] = size.to_bytes(4, "big")
+    head[4:8] = b"lcms"
+    head[8:12] = bytes([4, 0x30, 0, 0])
+    head[12:24] = b"mntrRGB XYZ "
+    head[24:36] = bytes([7, 0xE6, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0])
+    head[36:40] = b"acsp"
+    head[40:44] = vendor
+    head[68:80] = bytes([0, 0, 0xF6, 0xD6, 0, 1, 0, 0, 0, 0, 0xD3, 0x2D])
+    head[80:84] = head[4:8]
+    body = bytearray()
+    body += (9).to_bytes(4, "big")
+    for k, tag in enumerate([b"desc", b"cprt", b"wtpt", b"rXYZ", b"gXYZ", b"bXYZ", b"rTRC", b"gTRC", b"bTRC"]):
+        body += tag + (128 + 4 + 9 * 12 + 40 * k).to_bytes(4, "big") + (40).to_bytes(4, "big")
+    while len(body) + 128 < size:
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            body += b"Copyright 2026, no rights reserved. sRGB IEC61966-2.1, v1.0 "
+        elif kind == 1:
+            body += bytes(rng.integers(0, 16, 48, dtype=np.uint8))
+        elif kind == 2:
+            body += bytes(rng.integers(0, 256, 64, dtype=np.uint8))
+        else:
+            body += bytes(int(rng.integers(0, 2)) * 255 if i % 3 else 0 for i in range(40)) + bytes(24)
+    return bytes(head + body)[:size]
+
+
+@pytest.mark.parametrize("case", [
+    # (width, height, profile size, vendor, seed)
+    (64, 48, 60, b"APPL", 1),          # profile shorter than its 128-byte header: no command stream
+    (64, 48, 128, b"MSFT", 2),         # exactly the header
+    (64, 48, 129, b"ADBE", 3),         # one byte behind the header
+    (200, 120, 3144, b"MSFT", 4),      # the size of the common sRGB profile
+    (520, 260, 524, b"none", 5),       # several groups in the one frame
+    (2100, 300, 70000, b"APPL", 6),    # two LF groups; a large profile (lookup tables)
+])
+def test_icc_tagged_image_header_matches_reference(product_lib, reflib, case):
+    """hyd_set_suggested_icc_profile (libhydrium.c:242-305) + the ICC branch of the image header
+    (encoder.c:122-162, 203-236): mangled profile, 41-context / 9-cluster prefix stream, written by
+    k_icc_header on the device."""
+    w, h, size, vendor, seed = case
+    img = synth_image(w, h, 8, seed=seed)
+    icc = _fake_icc(size, seed, vendor)
+    want = encode_cli_loop(reflib, img, shift_x=-1, shift_y=-1, icc=icc)
+    got = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1, icc=icc)
+    plain = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1)
+    assert len(got) > len(plain) and got != plain
+    if got != want:
+        n = min(len(got), len(want))
+        first = next((i for i in range(n) if got[i] != want[i]), n)
+        raise AssertionError(f"{case}: {len(got)} vs {len(want)} bytes, first difference at byte {first}: "
+                             f"{got[max(0, first - 4):first + 12].hex()} vs {want[max(0, first - 4):first + 12].hex()}")
+
+
+def test_icc_vendors_the_reference_crashes_on(product_lib):
+    """Profiles whose platform signature is "SGI " or "SUNW" make the reference index a two-byte string
+    with (unsigned)(41 - 42) and segfault (libhydrium.c:225-230).  Here they are predicted as the format
+    says; the frame behind the header is the untagged image's."""
+    img = synth_image(64, 48, 8, seed=2)
+    plain = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1)
+    base = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1, icc=_fake_icc(700, 5, b"APPL"))
+    for vendor in (b"SGI ", b"SUNW"):
+        got = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1, icc=_fake_icc(700, 5, vendor))
+        frame = len(plain) - 16
+        assert got[-frame:] == plain[-frame:]
+        assert abs(len(got) - len(base)) <= 4   # the vendor is predicted, like "APPL"
+
+
+def test_icc_profile_cleared_and_refused_in_tile_mode(product_lib):
+    img = synth_image(64, 48, 8, seed=9)
+    enc = HYDEncoder(product_lib)
+    assert enc.set_metadata(64, 48, 0, 0, 0) == 0
+    assert enc.set_suggested_icc_profile(_fake_icc(300, 1)) == HYD_API_ERROR
+    assert "one-frame mode required" in enc.error_message_get()
+    enc.destroy()
+    # set, then cleared: the codestream is the untagged one
+    plain = encode_cli_loop(product_lib, img, shift_x=-1, shift_y=-1)
+    enc = HYDEncoder(product_lib)
+    enc.check(enc.set_metadata(64, 48, 0, -1, -1))
+    enc.check(enc.set_suggested_icc_profile(_fake_icc(300, 1)))
+    enc.check(enc.set_suggested_icc_profile(None))
+    obuf = np.empty(1 << 20, np.uint8)
+    enc.check(enc.provide_output_buffer(obuf))
+    p = img.ctypes.data
+    enc.check(enc.send_tile((p, p + 1, p + 2), 0, 0, 64 * 3, 3, -1, 0))
+    assert enc.flush() != HYD_NEED_MORE_OUTPUT
+    _, written = enc.release_output_buffer()
+    enc.destroy()
+    assert obuf[:written].tobytes() == plain
