@@ -115,14 +115,15 @@ def tile_grid(width: int, height: int, shift_x: int, shift_y: int) -> tuple[int,
 
 def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, shift_x: int = 0,
                     shift_y: int = 0, out_buf_size: int = 1 << 20, pixel_stride: int | None = None,
-                    tiles=None, is_last: int = -1, per_tile: list | None = None, icc: bytes | None = None) -> bytes:
+                    tiles=None, is_last=-1, per_tile: list | None = None, icc: bytes | None = None) -> bytes:
     """Encode `image` (H, W, C>=3 interleaved; uint8/uint16/float32) exactly the way the reference
     CLI drives the library: one output buffer, and after every tile the
     flush / release / consume / provide loop (hydrium.c:402-480).
 
     `tiles` optionally restricts/reorders the (tile_x, tile_y) sequence (gaps are legal,
     libhydrium.h:240); `per_tile`, if a list, receives the bytes surfaced after each tile; `icc` is a
-    suggested ICC profile (one-frame mode only, hydrium.c:288-296).
+    suggested ICC profile (one-frame mode only, hydrium.c:288-296); `is_last` may be a function of
+    (tile_x, tile_y), as the CLI's PFM path sets it explicitly (hydrium.c:459).
     """
     if image.ndim != 3 or image.shape[2] < 3:
         raise ValueError("image must be (H, W, C>=3)")
@@ -146,8 +147,9 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
         base = image.ctypes.data
         for (tx, ty) in tiles:
             p = base + (ty * th * row_stride + tx * tw * ch) * item
+            last = is_last(tx, ty) if callable(is_last) else is_last
             enc.check(enc.send_tile((p, p + item, p + 2 * item), tx, ty, row_stride, pstride,
-                                    is_last, fmt))
+                                    last, fmt))
             got = bytearray()
             while True:
                 ret = enc.flush()
