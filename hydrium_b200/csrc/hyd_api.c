@@ -17,9 +17,12 @@
  *   - with hydb_encoder_set_batch(n > 1) tiles are encoded n at a time; hyd_flush then returns
  *     HYD_OK with nothing written until a batch completes.
  */
+#define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/hydrium_b200.h"
 
@@ -397,6 +400,21 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *enc, cons
     return HYD_OK;
 }
 
+/* HYDRIUM_B200_APITRACE=1: where a hyd_send_tile spends its time (stderr, milliseconds) */
+static int api_trace(void) {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("HYDRIUM_B200_APITRACE");
+        on = e && *e && *e != '0';
+    }
+    return on;
+}
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+
 static HYDStatusCode pend_reserve(HYDEncoder *enc, size_t extra) {
     if (enc->pend_len + extra <= enc->pend_cap)
         return HYD_OK;
@@ -561,21 +579,28 @@ static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3]
 
 /* a tile of several 256x256 groups: one frame with shared sections (k_frame.cu), encoded at once */
 static HYDStatusCode run_frame(HYDEncoder *enc, HydbFrame *fr) {
+    const double t0 = now_ms();
     if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
+    const double t1 = now_ms();
     HYDStatusCode rc = hydb_engine_encode_frames(enc->engine, fr, 1, enc->out_dev,
                                                  (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
     if (rc < HYD_ERROR_START)
         return gpu_error(enc, rc);
+    const double t2 = now_ms();
     uint64_t bytes = 0;
     rc = hydb_engine_finish(enc->engine, &bytes);
     if (rc != HYD_OK)
         return gpu_error(enc, rc);
+    const double t3 = now_ms();
     rc = pend_reserve(enc, (size_t)bytes);
     if (rc < HYD_ERROR_START)
         return rc;
     if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
+    if (api_trace())
+        fprintf(stderr, "[hydrium_b200] frame %ux%u: h2d %.2f  launch %.2f  wait %.2f  d2h %.2f ms (%llu bytes)\n", fr->width,
+                fr->height, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, (unsigned long long)bytes);
     enc->pend_len += (size_t)bytes;
     enc->stage_used = 0;
     return HYD_OK;
@@ -810,7 +835,10 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
         fr.with_image_header = !enc->wrote_header;
         fr.one_frame = enc->one_frame;
         enc->wrote_header = 1;
+        const double ts = now_ms();
         stage_pixels(enc, tw, th, fr.plane, &fr.row_stride, &fr.pixel_stride, buffer, row_stride, pixel_stride, item);
+        if (api_trace())
+            fprintf(stderr, "[hydrium_b200] staging %.2f ms\n", now_ms() - ts);
         return run_frame(enc, &fr);
     }
 

@@ -19,9 +19,12 @@
 //                      with the (identity) TOC permutation; everything lands in the prefix slot's
 //                      slab so that the ordinary gather concatenates  prefix | group 0 | group 1 ...
 //
-// First correct version: the prefix coder runs on one thread per frame (the sequential routines of
-// prefix_coder.cuh); the LF stream of a 2048x2048 frame has 196 608 values, so this is the slow
-// part of a multi-group frame and the obvious next thing to parallelise.
+//   k_oneframe_finish  head and HFGlobal of a one-frame image of several LF groups
+//   k_icc_header       image header of an ICC-tagged image (the profile as a 41-context prefix stream)
+//
+// k_frame_lf and k_icc_header spread the per-value work (residuals, tokens, histograms, symbol bits)
+// over 1024 threads with block scans; what is inherently small and sequential (code construction,
+// stream headers) runs on one thread through prefix_coder.cuh.
 #include "kernels.h"
 #include "sections.cuh"
 #include "lf_values.cuh"
