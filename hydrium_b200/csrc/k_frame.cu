@@ -28,6 +28,7 @@
 #include "kernels.h"
 #include "sections.cuh"
 #include "lf_values.cuh"
+#include "prefix_warp.cuh"
 
 namespace hydb {
 
@@ -38,6 +39,7 @@ struct FrameShared {
     PrefixWork work;
     uint32_t head[256];      // frame header + TOC + LFGlobal, as words
     uint32_t s2[kDBitsWords + 128];
+    uint16_t mapidx[1488];   // move-to-front indices of one preset's 1485-entry context map
 };
 
 __global__ void __launch_bounds__(kHfClusters * kHfTokens)
@@ -118,7 +120,7 @@ __device__ __forceinline__ LfEmit lf_position_symbols(uint32_t v, uint32_t i, ui
     out.n = 0;
     const uint32_t o = i - s, r = o & 127u, L = (e - s) - (o & ~127u) < 128u ? (e - s) - (o & ~127u) : 128u;
     uint32_t res, nb;
-    if (r == 0 || L - 1 <= 3) {   // the chunk's literal, or one of its (at most three) repeats
+    if (r == 0 || L - 1 <= 3 || !p.lz_min_symbol) {   // the chunk's literal, or one of its (at most three) repeats
         const uint32_t tok = hybrid_token(v, p.split0, p.msb0, p.lsb0, res, nb);
         out.sym[0] = ps_pack(tok, 0, nb, res);
         out.n = 1;
@@ -131,66 +133,38 @@ __device__ __forceinline__ LfEmit lf_position_symbols(uint32_t v, uint32_t i, ui
     return out;
 }
 
-__global__ void __launch_bounds__(kLfThreads)
-k_frame_lf(Workspace ws) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
-    __shared__ uint32_t s_warp[64];
+// One prefix-coded stream by the whole CTA (kLfThreads threads): the values value_at(0 .. total) with the
+// stream parameters `prm`, appended to the bit string in `outw` that thread 0's `bw` has written so
+// far.  The run-length front end is applied as a per-position rule, so symbols are counted, placed
+// (block scans) and histogrammed by all threads; the first warp finds the code lengths, thread 0
+// writes the stream header, all threads pack the symbol bits (scanned bit offsets, atomicOr at word
+// boundaries).  On return thread 0's `bw` continues behind the stream.  Returns error flags (uniform).
+// `syms`: symbol scratch of sym_cap words; s_first: kLfThreads words, s_warp: 64 words of shared memory.
+template <typename ValueAt>
+__device__ uint32_t block_prefix_stream(PrefixWork &w, BitSink &bw, uint32_t *outw, uint32_t out_words, uint32_t *syms,
+                                        uint32_t sym_cap, const PrefixParams &prm, uint32_t total, ValueAt value_at,
+                                        uint32_t *s_warp, uint32_t *s_first) {
     __shared__ uint32_t s_bitpos, s_err;
-    const uint32_t slot = blockIdx.x, tid = threadIdx.x;
-    const TileDesc t = ws.tiles[slot];
-    if (!(t.flags & kTilePrefix))
-        return;
-    PrefixWork &w = s.work;
-    const uint32_t vbw = (t.frame_w + 7) >> 3, vbh = (t.frame_h + 7) >> 3, nb = vbw * vbh, total = 3 * nb;
-    const PrefixParams prm = lf_stream_params();
+    const uint32_t tid = threadIdx.x;
     const uint32_t lz = prm.lz_min_symbol;
-    uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
-    uint8_t *slab = ws.slab + (size_t)slot * kSlabBytes;
-    uint32_t *outw = reinterpret_cast<uint32_t *>(slab + kPrefixLfOffset);
-    constexpr uint32_t kOutWords = (kSlabBytes - kPrefixLfOffset - kPrefixTailReserve) / 4;
-    // ---- residuals of the whole LF image, channel order Y, X, B (encoder.c:574-592) ---------------
-    uint16_t *resid = reinterpret_cast<uint16_t *>(ws.coef + (size_t)slot * kMaxBlocks * 3 * 64);   // 196 608 x u16
-    uint32_t my_err = 0;
-    for (uint32_t i = tid; i < total; i += kLfThreads) {
-        const uint32_t ci = i / nb, r = i - ci * nb;
-        const uint32_t c = ci < 2 ? 1 - ci : ci;
-        const uint32_t by = r / vbw, bx = r - by * vbw;
-        const int32_t v = frame_lf_at(ws, slot, t.frame_gx, c, bx, by);
-        const int32_t up = by ? frame_lf_at(ws, slot, t.frame_gx, c, bx, by - 1) : 0;
-        const int32_t wv = bx ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by) : up;
-        const int32_t n = by ? up : wv;
-        const int32_t nw = (bx && by) ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by - 1) : wv;
-        const int32_t lo = wv < n ? wv : n, hi = wv < n ? n : wv;
-        int32_t pred = wv + n - nw;
-        pred = pred < lo ? lo : (pred > hi ? hi : pred);
-        const uint32_t packed = pack_signed(v - pred);
-        if (packed > 0xFFFFu)
-            my_err = kErrLfAlphabet;   // would need more than 12 residue bits: outside what the LF coder holds
-        resid[i] = (uint16_t)(packed > 0xFFFFu ? 0xFFFFu : packed);
-    }
-    // ---- section head (one thread; uses the prefix work area for the small MA-tree stream) ---------
-    BitSink bw;
-    if (tid == 0) {
-        s_err = 0;
-        w.error = 0;
-        bw.init(outw, kOutWords);
-        put_lf_group_head(w, syms, bw);
-    }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads)
         w.freq[i] = 0;
-    if (tid == 0)
+    if (tid == 0) {
         w.alpha0 = w.alpha1 = 0;
+        s_err = 0;
+    }
     __syncthreads();
-    // ---- the LF stream's symbols, in parallel: thread = contiguous range of positions ---------------
+    uint32_t my_err = 0;
+    // ---- symbols: thread = contiguous range of positions -------------------------------------------
     const uint32_t per = (total + kLfThreads - 1) / kLfThreads;
     const uint32_t a = tid * per < total ? tid * per : total, b = a + per < total ? a + per : total;
+    // without run-length mode every position is its own run
+    auto starts_run = [&](uint32_t i) -> bool { return !lz || i == 0 || value_at(i) != value_at(i - 1); };
     // last run start inside [a, b) (+1; 0 = none) and first run start inside it (total = none)
     uint32_t last_start = 0, first_start = total;
     for (uint32_t i = a; i < b; i++) {
-        const bool st = i == 0 || resid[i] != resid[i - 1];
-        if (st) {
+        if (starts_run(i)) {
             last_start = i + 1;
             if (first_start == total)
                 first_start = i;
@@ -199,11 +173,9 @@ k_frame_lf(Workspace ws) {
     uint32_t dummy;
     const uint32_t carry_start = block_exclusive_scan(last_start, 0u, [](uint32_t x, uint32_t y) { return x > y ? x : y; },
                                                       s_warp, dummy);   // start (+1) of the run reaching into a
-    // next run start at or after b: exclusive scan from the right of first_start with min
+    // next run start at or after b: exclusive min-scan from the right, done on mirrored thread order
     uint32_t carry_end;
     {
-        // reverse the thread order by scanning mirrored values
-        __shared__ uint32_t s_first[kLfThreads];
         s_first[kLfThreads - 1 - tid] = first_start;
         __syncthreads();
         const uint32_t mirrored = s_first[tid];
@@ -216,18 +188,18 @@ k_frame_lf(Workspace ws) {
     }
     auto run_end = [&](uint32_t i) -> uint32_t {   // end of the run containing position i (i in [a, b))
         uint32_t e = i + 1;
-        while (e < b && resid[e] == resid[e - 1])
+        while (e < b && !starts_run(e))
             e++;
         return e < b ? e : carry_end;
     };
+    const uint32_t sr0 = (a < b && !starts_run(a)) ? carry_start - 1 : a;
     // pass 1: count
     uint32_t count = 0;
     {
-        uint32_t i = a;
-        uint32_t sr = (a < b && !(a == 0 || resid[a] != resid[a - 1])) ? carry_start - 1 : a;
+        uint32_t i = a, sr = sr0;
         while (i < b) {
             const uint32_t e = run_end(i);
-            const uint32_t v = resid[i];
+            const uint32_t v = value_at(i);
             const uint32_t stop = e < b ? e : b;
             for (; i < stop; i++)
                 count += lf_position_symbols(v, i, sr, e, prm).n;
@@ -236,15 +208,14 @@ k_frame_lf(Workspace ws) {
     }
     uint32_t nsyms_total;
     uint32_t off = block_exclusive_scan(count, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, nsyms_total);
-    if (nsyms_total > (uint32_t)kMaxHfSyms)
+    if (nsyms_total > sym_cap)
         my_err |= kErrLfCapacity;
     // pass 2: emit + histogram
-    if (nsyms_total <= (uint32_t)kMaxHfSyms) {
-        uint32_t i = a;
-        uint32_t sr = (a < b && !(a == 0 || resid[a] != resid[a - 1])) ? carry_start - 1 : a;
+    if (nsyms_total <= sym_cap) {
+        uint32_t i = a, sr = sr0;
         while (i < b) {
             const uint32_t e = run_end(i);
-            const uint32_t v = resid[i];
+            const uint32_t v = value_at(i);
             const uint32_t stop = e < b ? e : b;
             for (; i < stop; i++) {
                 const LfEmit em = lf_position_symbols(v, i, sr, e, prm);
@@ -254,7 +225,7 @@ k_frame_lf(Workspace ws) {
                     bool fits;
                     if (cluster)
                         fits = token < (uint32_t)kDistBins;
-                    else if (token >= lz)
+                    else if (lz && token >= lz)
                         fits = token - lz < (uint32_t)kLzBins;
                     else
                         fits = token < (uint32_t)kLitBins;
@@ -277,21 +248,26 @@ k_frame_lf(Workspace ws) {
     if (my_err)
         atomicOr(&s_err, my_err);
     __syncthreads();
-    // ---- stream header: code construction, one thread -----------------------------------------------
+    // ---- code lengths of the literal / length cluster by the first warp, then the stream header --------
+    const bool warp_lengths = w.alpha0 > 1;
+    if (tid < 32 && warp_lengths)
+        warp_code_lengths(w, w.alpha0, 15, lz, tid);
+    __syncthreads();
     if (tid == 0) {
         w.nsyms = nsyms_total;
-        ps_put_header(w, bw, prm);
+        ps_put_header(w, bw, prm, warp_lengths);
         bw.flush_partial();
         s_bitpos = bw.bitlen();
         if (bw.overflow)
             s_err |= kErrSlab;
+        if (w.error)
+            s_err |= w.error;
     }
     __syncthreads();
     const uint32_t p0 = s_bitpos;
-    const bool ok = !s_err && !w.error;
     // ---- symbol bits, in parallel: thread = contiguous range of symbols -----------------------------
     uint32_t total_bits = 0;
-    if (ok) {
+    if (!s_err) {
         const uint32_t sper = (nsyms_total + kLfThreads - 1) / kLfThreads;
         const uint32_t sa = tid * sper < nsyms_total ? tid * sper : nsyms_total;
         const uint32_t sb = sa + sper < nsyms_total ? sa + sper : nsyms_total;
@@ -302,7 +278,8 @@ k_frame_lf(Workspace ws) {
         }
         const uint32_t boff = block_exclusive_scan(bits, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, total_bits);
         const uint64_t endbit = (uint64_t)p0 + total_bits;
-        if (endbit + 64 > (uint64_t)kOutWords * 32) {
+        if (endbit + 64 > (uint64_t)out_words * 32) {
+            __syncthreads();
             if (tid == 0)
                 s_err |= kErrSlab;
         } else {
@@ -337,12 +314,73 @@ k_frame_lf(Workspace ws) {
         }
     }
     __syncthreads();
+    const uint32_t err = s_err;
+    if (tid == 0 && !err)
+        bw.resume(outw, out_words, p0 + total_bits);
+    __syncthreads();
+    return err;
+}
+
+struct ResidValues {
+    const uint16_t *v;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return (uint32_t)v[i]; }
+};
+
+__global__ void __launch_bounds__(kLfThreads)
+k_frame_lf(Workspace ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
+    __shared__ uint32_t s_warp[64];
+    __shared__ uint32_t s_first[kLfThreads];
+    __shared__ uint32_t s_resid_err;
+    const uint32_t slot = blockIdx.x, tid = threadIdx.x;
+    const TileDesc t = ws.tiles[slot];
+    if (!(t.flags & kTilePrefix))
+        return;
+    PrefixWork &w = s.work;
+    const uint32_t vbw = (t.frame_w + 7) >> 3, vbh = (t.frame_h + 7) >> 3, nb = vbw * vbh, total = 3 * nb;
+    uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
+    uint8_t *slab = ws.slab + (size_t)slot * kSlabBytes;
+    uint32_t *outw = reinterpret_cast<uint32_t *>(slab + kPrefixLfOffset);
+    constexpr uint32_t kOutWords = (kSlabBytes - kPrefixLfOffset - kPrefixTailReserve) / 4;
+    if (tid == 0)
+        s_resid_err = 0;
+    __syncthreads();
+    // ---- residuals of the whole LF image, channel order Y, X, B (encoder.c:574-592) ---------------
+    uint16_t *resid = reinterpret_cast<uint16_t *>(ws.coef + (size_t)slot * kMaxBlocks * 3 * 64);   // 196 608 x u16
+    for (uint32_t i = tid; i < total; i += kLfThreads) {
+        const uint32_t ci = i / nb, r = i - ci * nb;
+        const uint32_t c = ci < 2 ? 1 - ci : ci;
+        const uint32_t by = r / vbw, bx = r - by * vbw;
+        const int32_t v = frame_lf_at(ws, slot, t.frame_gx, c, bx, by);
+        const int32_t up = by ? frame_lf_at(ws, slot, t.frame_gx, c, bx, by - 1) : 0;
+        const int32_t wv = bx ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by) : up;
+        const int32_t n = by ? up : wv;
+        const int32_t nw = (bx && by) ? frame_lf_at(ws, slot, t.frame_gx, c, bx - 1, by - 1) : wv;
+        const int32_t lo = wv < n ? wv : n, hi = wv < n ? n : wv;
+        int32_t pred = wv + n - nw;
+        pred = pred < lo ? lo : (pred > hi ? hi : pred);
+        const uint32_t packed = pack_signed(v - pred);
+        if (packed > 0xFFFFu)
+            s_resid_err = kErrLfAlphabet;   // would need more than 12 residue bits: outside what the LF coder holds
+        resid[i] = (uint16_t)(packed > 0xFFFFu ? 0xFFFFu : packed);
+    }
+    // ---- section head (one thread; uses the prefix work area for the small MA-tree stream) ---------
+    BitSink bw;
+    if (tid == 0) {
+        w.error = 0;
+        bw.init(outw, kOutWords);
+        put_lf_group_head(w, syms, bw);
+    }
+    // ---- the LF stream ---------------------------------------------------------------------------------
+    uint32_t err = block_prefix_stream(w, bw, outw, kOutWords, syms, (uint32_t)kMaxHfSyms, lf_stream_params(), total,
+                                       ResidValues{resid}, s_warp, s_first);
+    err |= s_resid_err;
     if (tid != 0)
         return;
     // ---- the constant HF-metadata image behind it, then the section is closed ------------------------
-    uint32_t err = s_err | w.error;
+    err |= w.error;
     if (!err) {
-        bw.resume(outw, kOutWords, p0 + total_bits);
         put_hf_metadata(w, syms, (uint32_t)kMaxHfSyms, bw, vbw, vbh);
         bw.align_byte();
         bw.flush_partial();
@@ -357,13 +395,42 @@ k_frame_lf(Workspace ws) {
         atomicOr(&ws.tile_err[slot], err);
 }
 
-__global__ void __launch_bounds__(32)
+struct ClusterMapMtf {
+    const uint16_t *idx;
+    HD uint32_t operator()(uint32_t i) const { return (uint32_t)idx[i]; }
+};
+struct WordValues {
+    const uint32_t *v;
+    HD uint32_t operator()(uint32_t i) const { return v[i]; }
+};
+
+// Move-to-front index of entry j of the HF context map (1485 contexts per preset, K clusters per
+// preset numbered K * preset + local; reference: entropy.c:136-151 evolves the list entry by entry).
+// Closed form: a cluster's previous occurrence is at most six entries back inside its preset, and the
+// index is the number of distinct clusters in between; at its first occurrence every cluster seen so
+// far is smaller, so it still sits at its initial place, index = its own number.
+__device__ __forceinline__ uint32_t hf_map_mtf_index(uint32_t j, uint32_t K) {
+    const uint32_t preset = j / 1485u, ctx = j - preset * 1485u;
+    const uint32_t c = hf_fold_cluster(hf_context_cluster(ctx), K);
+    uint32_t between = 0;
+    for (uint32_t d = 1; d <= 8 && d <= ctx; d++) {
+        const uint32_t cc = hf_fold_cluster(hf_context_cluster(ctx - d), K);
+        if (cc == c)
+            return (uint32_t)__popc(between);
+        between |= 1u << cc;
+    }
+    return K * preset + c;
+}
+
+__global__ void __launch_bounds__(kLfThreads)
 k_frame_finish(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
-    const uint32_t slot = blockIdx.x;
+    __shared__ uint32_t s_warp[64];
+    __shared__ uint32_t s_first[kLfThreads];
+    const uint32_t slot = blockIdx.x, tid = threadIdx.x;
     const TileDesc t = ws.tiles[slot];
-    if (!(t.flags & kTilePrefix) || threadIdx.x != 0)
+    if (!(t.flags & kTilePrefix))
         return;
     const uint32_t G = t.frame_groups;
     uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
@@ -375,17 +442,41 @@ k_frame_finish(Workspace ws) {
     if (t.flags & kTileLfPart) {
         // one LF group of a larger one-frame image: only its LFGroup section; the frame's head and
         // HFGlobal are assembled when the last LF group has been sent (k_oneframe_finish)
-        ws.frame_off[slot] = kPrefixLfOffset;
-        ws.frame_len[slot] = err ? 0u : len1;
-        if (err)
-            atomicOr(&ws.tile_err[slot], err);
+        if (tid == 0) {
+            ws.frame_off[slot] = kPrefixLfOffset;
+            ws.frame_len[slot] = err ? 0u : len1;
+            if (err)
+                atomicOr(&ws.tile_err[slot], err);
+        }
         return;
     }
     // ---- HFGlobal section: constants + the ANS header tail the first group's chain kernel wrote ---
+    // (sections.cuh::put_hf_global, with the context map's nested stream coded by the whole CTA)
     BitSink b2;
-    b2.init(s.s2, kDBitsWords + 128);
-    s.work.error = 0;
-    put_hf_global(s.work, syms, b2, G);
+    if (tid == 0) {
+        b2.init(s.s2, kDBitsWords + 128);
+        s.work.error = 0;
+        b2.put_bool(1);    // HFGlobal: default dequant matrices
+        b2.put(0, ceil_log2_u32(G));   // num_presets - 1 = 0
+        b2.put(2, 2);      // HF pass order
+        b2.put_bool(0);    // ANS stream: no lz77
+        b2.put_bool(0);    // context map: not simple
+        b2.put_bool(1);    // move-to-front
+    }
+    for (uint32_t j = tid; j < (uint32_t)kHfContexts; j += kLfThreads)
+        s.mapidx[j] = (uint16_t)hf_map_mtf_index(j, 9);
+    {
+        PrefixParams p;
+        p.num_plain_dists = 1;
+        p.lz_min_symbol = 64;
+        p.modular = 0;
+        p.split0 = 4; p.msb0 = 1; p.lsb0 = 0;
+        p.split1 = 4; p.msb1 = 1; p.lsb1 = 0;
+        err |= block_prefix_stream(s.work, b2, s.s2, kDBitsWords + 128, syms, (uint32_t)kSectionSymCap, p,
+                                   (uint32_t)kHfContexts, ClusterMapMtf{s.mapidx}, s_warp, s_first);
+    }
+    if (tid != 0)
+        return;
     {
         const uint32_t *d = ws.dbits + (size_t)(slot + 1) * kDBitsWords;
         uint32_t n = ws.chain_out[(slot + 1) * 4 + 2] & 0xFFFFu;
@@ -449,20 +540,14 @@ k_frame_finish(Workspace ws) {
 // whole frame shares.  Sections are written LF group by LF group in the order they were sent while
 // the TOC lists them in raster order, so the permutation and its Lehmer code are real here
 // (encoder.c:241-325).  info layout: hydb_oneframe_finish in engine.cu.
-struct ClusterMapMtf {
-    const uint16_t *idx;
-    HD uint32_t operator()(uint32_t i) const { return (uint32_t)idx[i]; }
-};
-struct WordValues {
-    const uint32_t *v;
-    HD uint32_t operator()(uint32_t i) const { return v[i]; }
-};
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kLfThreads)
 k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32_t *scratch, uint32_t scratch_words,
                   uint8_t *out, uint32_t head_cap, uint32_t hf_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
+    __shared__ uint32_t s_warp[64];
+    __shared__ uint32_t s_first[kLfThreads];
     const uint32_t tid = threadIdx.x;
     const uint32_t W = info[0], H = info[1], with_header = info[2], max_alpha = info[3], n = info[4], G = info[5];
     const uint32_t K = hf_clusters_for_presets(n);   // HF clusters per preset
@@ -499,7 +584,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     }
     __syncthreads();
     // Lehmer code of inv: how many not yet used smaller elements precede each one
-    for (uint32_t i = tid; i < toc_size; i += 256) {
+    for (uint32_t i = tid; i < toc_size; i += kLfThreads) {
         uint32_t smaller_before = 0;
         const uint32_t v = inv[i];
         for (uint32_t j = 0; j < i; j++)
@@ -507,43 +592,59 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         leh[1 + i] = v - smaller_before;
     }
     __syncthreads();
-    if (tid != 0)
-        return;
     uint32_t err = 0;
-    s.work.error = 0;
     // ---- HFGlobal section ------------------------------------------------------------------------------
     uint8_t *hf_bytes = out + head_cap;
     BitSink b2;
-    b2.init(reinterpret_cast<uint32_t *>(hf_bytes), hf_cap / 4);
-    b2.put_bool(1);                                       // default dequant matrices
-    b2.put(n - 1, ceil_log2_u32(G));                      // num_presets - 1 (encoder.c:961)
-    b2.put(2, 2);                                         // HF pass order
-    b2.put_bool(0);                                       // ANS stream: no lz77
-    {   // context map of 1485 n contexts onto K n clusters: never "simple" for n >= 2 (entropy.c:108-167)
+    if (tid == 0) {
+        s.work.error = 0;
+        b2.init(reinterpret_cast<uint32_t *>(hf_bytes), hf_cap / 4);
+        b2.put_bool(1);                                       // default dequant matrices
+        b2.put(n - 1, ceil_log2_u32(G));                      // num_presets - 1 (encoder.c:961)
+        b2.put(2, 2);                                         // HF pass order
+        b2.put_bool(0);                                       // ANS stream: no lz77
+        // context map of 1485 n contexts onto K n clusters: never "simple" for n >= 2 (entropy.c:108-167)
         b2.put_bool(0);
-        b2.put_bool(1);                                   // move-to-front
+        b2.put_bool(1);                                       // move-to-front
+    }
+    {
         uint16_t *idx = reinterpret_cast<uint16_t *>(tokens + 1485u * n / 2 + 2048u);   // upper part of the token scratch
-        uint8_t mtf[256];
-        for (int i = 0; i < 256; i++)
-            mtf[i] = (uint8_t)i;
-        for (uint32_t j = 0; j < 1485u * n; j++) {
-            const uint8_t c = (uint8_t)(K * (j / 1485u) + hf_fold_cluster(hf_context_cluster(j % 1485u), K));
-            int k = 0;
-            while (mtf[k] != c)
-                k++;
-            idx[j] = (uint16_t)k;
-            for (; k > 0; k--)
-                mtf[k] = mtf[k - 1];
-            mtf[0] = c;
-        }
+        for (uint32_t j = tid; j < 1485u * n; j += kLfThreads)
+            idx[j] = (uint16_t)hf_map_mtf_index(j, K);
         PrefixParams p;
         p.num_plain_dists = 1;
         p.lz_min_symbol = 64;
         p.modular = 0;
         p.split0 = 4; p.msb0 = 1; p.lsb0 = 0;
         p.split1 = 4; p.msb1 = 1; p.lsb1 = 0;
-        ps_encode_stream(s.work, tokens, 1485u * n / 2 + 2048u, p, 1485u * n, ClusterMapMtf{idx}, b2);
+        err |= block_prefix_stream(s.work, b2, reinterpret_cast<uint32_t *>(hf_bytes), hf_cap / 4, tokens,
+                                   1485u * n / 2 + 2048u, p, 1485u * n, ClusterMapMtf{idx}, s_warp, s_first);
     }
+    // ---- head, part 1: [image header] frame header + TOC permutation (all threads) ----------------------
+    uint32_t pre_bytes = 0;
+    BitSink bh;
+    if (tid == 0) {
+        if (with_header && image_needs_level10(W, H))
+            pre_bytes = put_level10_prefix(out);
+        bh.init(reinterpret_cast<uint32_t *>(out + 52), (head_cap - 52) / 4);   // 52: word aligned, past the 49-byte prefix
+        if (with_header)
+            put_image_header(bh, W, H);
+        put_frame_header_fields(bh, false, 0, 0, W, H, true);
+        bh.put_bool(1);                                       // permuted TOC
+        s.work.error = 0;
+    }
+    {
+        PrefixParams p;
+        p.num_plain_dists = 8;
+        p.lz_min_symbol = 0;
+        p.modular = 0;
+        p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
+        p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
+        err |= block_prefix_stream(s.work, bh, reinterpret_cast<uint32_t *>(out + 52), (head_cap - 52) / 4, tokens,
+                                   scratch_words - fixed, p, 1 + toc_size, WordValues{leh}, s_warp, s_first);
+    }
+    if (tid != 0)
+        return;
     const int log_alpha = max_alpha > 32 ? 6 : 5;          // entropy.c:952 with tokens < 64
     if (max_alpha > 64)
         err |= kErrAlphabet;
@@ -568,26 +669,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     const uint32_t len2 = b2.bitlen() >> 3;
     if (b2.overflow || s.work.error)
         err |= kErrSlab;
-    // ---- head: [image header] frame header + TOC permutation, TOC, LFGlobal ----------------------------
-    uint32_t pre_bytes = 0;
-    if (with_header && image_needs_level10(W, H))
-        pre_bytes = put_level10_prefix(out);
-    BitSink bh;
-    bh.init(reinterpret_cast<uint32_t *>(out + 52), (head_cap - 52) / 4);   // 52: word aligned, past the 49-byte prefix
-    if (with_header)
-        put_image_header(bh, W, H);
-    put_frame_header_fields(bh, false, 0, 0, W, H, true);
-    bh.put_bool(1);                                       // permuted TOC
-    {
-        PrefixParams p;
-        p.num_plain_dists = 8;
-        p.lz_min_symbol = 0;
-        p.modular = 0;
-        p.split0 = 4; p.msb0 = 1; p.lsb0 = 1;
-        p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
-        s.work.error = 0;
-        ps_encode_stream(s.work, tokens, scratch_words - fixed, p, 1 + toc_size, WordValues{leh}, bh);
-    }
+    // ---- head, part 2: TOC, LFGlobal ---------------------------------------------------------------------
     bh.align_byte();
     bool ok = put_toc_value(bh, 16);
     for (uint32_t k = 0; k < n; k++)
@@ -815,7 +897,7 @@ void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H,
 void launch_oneframe_finish(const uint32_t *d_info, uint32_t info_words, uint32_t *d_scratch, uint32_t scratch_words,
                             uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, cudaStream_t st) {
     cudaFuncSetAttribute(k_oneframe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
-    k_oneframe_finish<<<1, 256, sizeof(FrameShared), st>>>(d_info, info_words, d_scratch, scratch_words, d_out, head_cap, hf_cap);
+    k_oneframe_finish<<<1, kLfThreads, sizeof(FrameShared), st>>>(d_info, info_words, d_scratch, scratch_words, d_out, head_cap, hf_cap);
 }
 
 void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
@@ -832,7 +914,7 @@ void launch_frame_lf(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
 void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
     prefer_max_shared(k_frame_finish);
     cudaFuncSetAttribute(k_frame_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
-    k_frame_finish<<<nslots, 32, sizeof(FrameShared), st>>>(ws);
+    k_frame_finish<<<nslots, kLfThreads, sizeof(FrameShared), st>>>(ws);
 }
 
 }  // namespace hydb

@@ -477,9 +477,11 @@ HDN inline void ps_put_complex_code(PrefixWork &w, BitSink &bw, uint32_t first_b
 }
 
 // per-cluster code description + canonical code assignment (reference: entropy.c:846-927)
+// `lengths_ready`: w.len[] of the cluster's bins was filled in already (warp_code_lengths)
 HDN inline void ps_put_cluster_code(PrefixWork &w, BitSink &bw, uint32_t first_bin, uint32_t nbins,
-                                    uint32_t alphabet, uint32_t lz_min, bool dist_cluster) {
-    ps_code_lengths(w, first_bin, nbins, alphabet, 15, lz_min, dist_cluster);
+                                    uint32_t alphabet, uint32_t lz_min, bool dist_cluster, bool lengths_ready = false) {
+    if (!lengths_ready)
+        ps_code_lengths(w, first_bin, nbins, alphabet, 15, lz_min, dist_cluster);
     uint32_t used = 0;
     uint32_t fsym[4] = {0, 0, 0, 0}, flen[4] = {0, 0, 0, 0};
     for (uint32_t b = first_bin; b < first_bin + nbins; b++) {
@@ -540,7 +542,7 @@ HD void ps_put_hybrid_cfg(BitSink &bw, int split, int msb, int lsb, int log_alph
 
 // stream preamble + code descriptions (reference: entropy.c:546-575, 807-931).  After this,
 // w.code/w.len hold the per-bin codes for ps_put_symbols().
-HDN inline void ps_put_header(PrefixWork &w, BitSink &bw, const PrefixParams &p) {
+HDN inline void ps_put_header(PrefixWork &w, BitSink &bw, const PrefixParams &p, bool lengths0_ready = false) {
     const U32Dist kMinSymbol = {{224, 512, 4096, 8}, {0, 0, 0, 15}};    // entropy.c:48-51
     const U32Dist kMinLength = {{3, 4, 5, 9}, {0, 0, 2, 8}};            // entropy.c:52-55
     const uint32_t lz = p.lz_min_symbol;
@@ -575,10 +577,10 @@ HDN inline void ps_put_header(PrefixWork &w, BitSink &bw, const PrefixParams &p)
         bw.put((uint32_t)nb, 4);
         bw.put(alpha[c] - 1, nb);
     }
-    for (int b = 0; b < kAllBins; b++)
+    for (int b = lengths0_ready ? kBins : 0; b < kAllBins; b++)
         w.len[b] = 0, w.code[b] = 0;
     if (w.alpha0 > 1)
-        ps_put_cluster_code(w, bw, 0, kBins, w.alpha0, lz, false);
+        ps_put_cluster_code(w, bw, 0, kBins, w.alpha0, lz, false, lengths0_ready);
     if (lz && w.alpha1 > 1)
         ps_put_cluster_code(w, bw, kBins, kDistBins, w.alpha1, lz, true);
 }
