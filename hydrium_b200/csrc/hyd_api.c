@@ -51,6 +51,8 @@ struct HYDEncoder {
     int wrote_header;
     int last_tile;
 
+    double stage_ms, batch_t0;   /* HYDRIUM_B200_APITRACE accounting */
+
     /* suggested ICC profile, already in the form the image header codes (libhydrium.c:242-305) */
     uint8_t *icc;
     size_t icc_size;
@@ -445,6 +447,9 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
     enc->stage_cap = (size_t)enc->batch * TILE_STAGE_BYTES;
     if (enc->groups_per_tile > 1 && enc->stage_cap < (size_t)enc->tile_w * enc->tile_h * 16u)
         enc->stage_cap = (size_t)enc->tile_w * enc->tile_h * 16u;   /* one whole tile, RGBA float */
+    HydbEngine *stale_engine = NULL;
+    uint8_t *stale_host = NULL, *stale_dev = NULL, *stale_out = NULL;
+    HydbTile *stale_tiles = NULL;
     if (g_parked.valid && g_parked.device == enc->device && g_parked.batch == enc->batch &&
         g_parked.slots == enc->slots && g_parked.stage_cap == enc->stage_cap) {
         g_parked.valid = 0;
@@ -453,8 +458,24 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
         enc->stage_dev = g_parked.stage_dev;
         enc->out_dev = g_parked.out_dev;
         enc->tiles = g_parked.tiles;
+    } else if (g_parked.valid) {
+        /* a parked set of another shape: drop it, so that the one created now can be parked in turn
+         * (the most recent geometry is the one most likely to come back) and its memory is returned */
+        g_parked.valid = 0;
+        stale_engine = g_parked.engine;
+        stale_host = g_parked.stage_host;
+        stale_dev = g_parked.stage_dev;
+        stale_out = g_parked.out_dev;
+        stale_tiles = g_parked.tiles;
     }
     pthread_mutex_unlock(&g_parked.lock);
+    if (stale_engine) {
+        hydb_host_free(stale_host);
+        hydb_device_free(stale_dev);
+        hydb_device_free(stale_out);
+        hydb_engine_destroy(stale_engine);
+        free(stale_tiles);
+    }
     if (enc->engine)
         return HYD_OK;
     HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->slots);
@@ -495,8 +516,10 @@ static HYDStatusCode emit_icc_header(HYDEncoder *enc) {
 static HYDStatusCode run_batch(HYDEncoder *enc) {
     if (!enc->queued)
         return HYD_OK;
+    const double t0 = now_ms();
     if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
+    const double t1 = now_ms();
     HYDStatusCode rc = hydb_engine_encode_tiles(enc->engine, enc->tiles, enc->queued, enc->out_dev,
                                                 (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
     if (rc < HYD_ERROR_START)
@@ -505,11 +528,18 @@ static HYDStatusCode run_batch(HYDEncoder *enc) {
     rc = hydb_engine_finish(enc->engine, &bytes);
     if (rc != HYD_OK)
         return gpu_error(enc, rc);
+    const double t2 = now_ms();
     rc = pend_reserve(enc, (size_t)bytes);
     if (rc < HYD_ERROR_START)
         return rc;
     if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
+    if (api_trace()) {
+        fprintf(stderr, "[hydrium_b200] batch of %u tiles: staging %.2f (since the previous batch %.2f)  h2d %.2f  gpu %.2f  d2h %.2f ms\n",
+                enc->queued, enc->stage_ms, t0 - enc->batch_t0, t1 - t0, t2 - t1, now_ms() - t2);
+        enc->stage_ms = 0;
+        enc->batch_t0 = now_ms();
+    }
     enc->pend_len += (size_t)bytes;
     enc->queued = 0;
     enc->stage_used = 0;
@@ -855,7 +885,15 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     t->linear_light = enc->metadata.linear_light != 0;
     t->with_image_header = !enc->wrote_header; /* encoder.c:490-494: the image header precedes the first frame */
     enc->wrote_header = 1;
-    stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
+    if (api_trace()) {
+        const double ts = now_ms();
+        if (!enc->queued && enc->batch_t0 == 0)
+            enc->batch_t0 = ts;
+        stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
+        enc->stage_ms += now_ms() - ts;
+    } else {
+        stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
+    }
     enc->queued++;
 
     if (enc->queued == enc->batch || enc->last_tile) {
