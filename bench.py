@@ -158,7 +158,7 @@ def run_ours(args) -> int:
     import torch.distributed as dist
 
     from hydrium_b200.abi import HYD_UINT8
-    from hydrium_b200.dist import gather_spans
+    from hydrium_b200.dist import PeerGather, gather_spans
     from hydrium_b200.engine import Engine, output_bound
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,12 +185,45 @@ def run_ours(args) -> int:
         with torch.cuda.stream(ext):
             flush_buf.fill_(rank & 0xFF)
 
+    # rank 0 receives every rank's codestream here (sized for the synthetic's ~0.35 B/px with head-room)
+    gbuf = torch.empty(world * n_in // 4, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    enc_done = [None]
+    # The gather.  Preferred: every rank's compaction kernel writes its span straight into
+    # rank 0's HBM over NVLink (CUDA IPC peer memory), then one tiny all-reduce as the barrier and one
+    # kernel on rank 0 that closes the gaps.  Fallback: NCCL send/recv of the spans (gather_spans).
+    pg = None
+    gather_kind = None
+    if world > 1:
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            pg = PeerGather(eng, cap)
+        except RuntimeError as e:
+            print(f"[bench] rank {rank}: peer-memory gather unavailable ({e}); using NCCL send/recv", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if pg is not None:
+                pg.close()
+            pg = None
+        gather_kind = ("peer memory: k_gather_frames writes into rank 0's HBM over NVLink (CUDA IPC), all-reduce barrier, "
+                       "k_compact_regions on rank 0") if pg is not None else "NCCL: all-gather of lengths + grouped send/recv"
+
     def step(gather: bool):
+        if gather and pg is not None:
+            n = eng.encode_image_device(d_in.data_ptr(), WIDTH, HEIGHT, CHANNELS, sample_fmt=HYD_UINT8,
+                                        d_out=pg.d_out, d_out_cap=pg.d_out_cap)
+            with torch.cuda.stream(ext):
+                if enc_done[0] is not None:
+                    enc_done[0].record()
+                pg.finish(n, gbuf.data_ptr() if gbuf is not None else 0, gbuf.numel() if gbuf is not None else 0)
+            return n
         n = eng.encode_image_device(d_in.data_ptr(), WIDTH, HEIGHT, CHANNELS, sample_fmt=HYD_UINT8,
                                     d_out=d_out.data_ptr(), d_out_cap=cap)
         if gather and world > 1:
             with torch.cuda.stream(ext):
-                gather_spans(d_out[:n], dst=0)
+                if enc_done[0] is not None:
+                    enc_done[0].record()
+                gather_spans(d_out[:n], dst=0, out=gbuf)
         return n
 
     for _ in range(max(args.warmup, 3)):
@@ -208,10 +241,12 @@ def run_ours(args) -> int:
     wall0 = time.perf_counter()
     total_ms = 0.0
     step_ms = []
+    encode_ms = []
     out_bytes = 0
     for _ in range(args.steps):
         flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        enc_done[0] = torch.cuda.Event(enable_timing=True) if world > 1 else None
         with torch.cuda.stream(ext):
             e0.record()
         out_bytes = step(True)
@@ -220,10 +255,13 @@ def run_ours(args) -> int:
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         total_ms += step_ms[-1]
+        if world > 1:
+            encode_ms.append(e0.elapsed_time(enc_done[0]))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
+    enc_done[0] = None
     launches = eng.launch_count - launches0
     # per-kernel durations: same workload on the plain single-stream sequence (the band pipeline of
     # the timed loop overlaps kernels of different bands, so events could not bracket one kernel)
@@ -398,6 +436,9 @@ def run_ours(args) -> int:
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_in, "d2h_bytes_per_step": e2e_bytes,
                     "ms_per_step": e2e_ms_per_step, "api": "hydb_encode_image_host (C ABI, pinned host buffers)"},
+            "gather": ({"how": gather_kind, "ms_encode_rank0": float(np.mean(encode_ms)), "ms_step_rank0": float(np.mean(step_ms)),
+                        "note": "rank 0's own encode vs its whole step (waiting for the slowest rank + the NCCL gather)"}
+                       if world > 1 else None),
             "smooth_variant": smooth,
             "e2e_hyd_api": hyd_api,
             "e2e_hyd_api_one_frame": one_frame,
@@ -407,6 +448,8 @@ def run_ours(args) -> int:
             "clocks": clocks,
         }
         print(json.dumps(line))
+    if pg is not None:
+        pg.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -904,6 +904,65 @@ int hydb_memcpy_h2d(void *dst, const void *src, size_t bytes) {
 int hydb_memcpy_d2h(void *dst, const void *src, size_t bytes) {
     return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
+// ---- peer-memory gather (one process per GPU): CUDA IPC plumbing + the compaction launch ---------------
+int hydb_ipc_export(const void *d_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)) != cudaSuccess)
+        return -1;
+    memcpy(handle, &h, 64);
+    return 0;
+}
+void *hydb_ipc_open(const uint8_t handle[64]) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void hydb_ipc_close(void *p) {
+    if (p)
+        cudaIpcCloseMemHandle(p);
+}
+
+HYDStatusCode hydb_engine_compact_regions(HydbEngine *eng, const uint8_t *d_regions, uint32_t nregions, uint64_t region_stride,
+                                          uint8_t *d_out, uint64_t d_out_cap, uint64_t *total) {
+    if (!eng || !d_regions || !nregions || nregions > 64 || region_stride < 512 || (region_stride & 15) || !d_out || !total) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_compact_regions";
+        return HYD_API_ERROR;
+    }
+    CK(cudaSetDevice(eng->device));
+    uint64_t *d_total = nullptr;
+    if (cudaMalloc(&d_total, 16) != cudaSuccess) {
+        eng->error = "device allocation failed";
+        return HYD_NOMEM;
+    }
+    uint32_t *d_ovf = reinterpret_cast<uint32_t *>(d_total + 1);
+    uint64_t res[2] = {0, 0};
+    HYDStatusCode rc = HYD_OK;
+    if (cudaMemsetAsync(d_total, 0, 16, eng->st) != cudaSuccess)
+        rc = HYD_INTERNAL_ERROR;
+    if (rc == HYD_OK) {
+        launch_compact_regions(d_regions, nregions, region_stride, d_out, d_out_cap, d_total, d_ovf, eng->st);
+        eng->launches++;
+        if (cudaMemcpyAsync(res, d_total, 16, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
+            cudaStreamSynchronize(eng->st) != cudaSuccess)
+            rc = HYD_INTERNAL_ERROR;
+    }
+    cudaFree(d_total);
+    if (rc == HYD_OK && (uint32_t)res[1]) {
+        eng->error = "gathered codestream does not fit the output buffer";
+        rc = HYD_INTERNAL_ERROR;
+    }
+    if (rc != HYD_OK && eng->error.empty())
+        eng->error = "CUDA failure while compacting the gathered spans";
+    *total = res[0];
+    return rc;
+}
+
 int hydb_device_count(void) {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;

@@ -104,6 +104,62 @@ void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t 
     k_gather_frames<<<ntiles, 256, 0, st>>>(ws.slab, ws.frame_off, ws.frame_len, ws.out_off, out, out_cap, base, d_overflow);
 }
 
+// ---- multi-GPU gather over peer memory ------------------------------------------------------------
+// Every rank's k_gather_frames writes its span straight into its REGION of a buffer that lives on the
+// gathering rank (peer pointer over NVLink, opened with CUDA IPC): region r = [8-byte length, pad to
+// 256][span bytes].  Once all ranks are done this kernel closes the gaps: spans in rank order into one
+// contiguous stream.  grid = (chunks, regions); each CTA re-derives its region's offset from the
+// headers (regions <= 64).
+constexpr uint32_t kRegionHeader = 256;
+__global__ void __launch_bounds__(256)
+k_compact_regions(const uint8_t *__restrict__ regions, uint32_t nregions, uint64_t region_stride, uint8_t *__restrict__ out,
+                  uint64_t out_cap, uint64_t *__restrict__ total_out, uint32_t *overflow) {
+    const uint32_t r = blockIdx.y, tid = threadIdx.x;
+    uint64_t off = 0, len = 0, total = 0;
+    for (uint32_t k = 0; k < nregions; k++) {
+        const uint64_t l = *reinterpret_cast<const uint64_t *>(regions + (uint64_t)k * region_stride);
+        if (k < r)
+            off += l;
+        if (k == r)
+            len = l;
+        total += l;
+    }
+    if (r == 0 && blockIdx.x == 0 && tid == 0)
+        *total_out = total;
+    if (len + 16 > region_stride - kRegionHeader || off + len > out_cap) {
+        if (tid == 0)
+            atomicOr(overflow, 1u);
+        return;
+    }
+    const uint8_t *src = regions + (uint64_t)r * region_stride + kRegionHeader;   // 16-byte aligned
+    uint8_t *dst = out + off;
+    // destination words are stored whole; the source is read as aligned words and funnel-shifted
+    const uint32_t h = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    const uint64_t head = h < len ? h : len;
+    if (blockIdx.x == 0 && tid < head)
+        dst[tid] = src[tid];
+    const uint64_t nw = (len - head) >> 2;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    const uint64_t per = (nw + gridDim.x - 1) / gridDim.x;
+    const uint64_t k0 = (uint64_t)blockIdx.x * per, k1 = k0 + per < nw ? k0 + per : nw;
+    if (h == 0) {
+        for (uint64_t k = k0 + tid; k < k1; k += 256)
+            dw[k] = sw[k];
+    } else {
+        for (uint64_t k = k0 + tid; k < k1; k += 256)   // sw[k + 1] stays inside the region: len + 16 <= its capacity
+            dw[k] = __funnelshift_r(sw[k], sw[k + 1], h * 8);
+    }
+    const uint64_t done = head + nw * 4;
+    if (blockIdx.x == gridDim.x - 1 && tid < len - done)
+        dst[done + tid] = src[done + tid];
+}
+
+void launch_compact_regions(const uint8_t *regions, uint32_t nregions, uint64_t region_stride, uint8_t *out, uint64_t out_cap,
+                            uint64_t *d_total, uint32_t *d_overflow, cudaStream_t st) {
+    k_compact_regions<<<dim3(148, nregions), 256, 0, st>>>(regions, nregions, region_stride, out, out_cap, d_total, d_overflow);
+}
+
 // ---- synthetic input (hydrium_b200/synth.py is the numpy twin) ----------
 __device__ __forceinline__ uint32_t mix32(uint32_t v) {
     v ^= v >> 16;

@@ -19,22 +19,29 @@ def shard_range(n_units: int, world: int, rank: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def gather_spans(local: torch.Tensor, dst: int = 0, group=None) -> tuple[torch.Tensor | None, list[int]]:
+def gather_spans(local: torch.Tensor, dst: int = 0, group=None, out: torch.Tensor | None = None
+                 ) -> tuple[torch.Tensor | None, list[int]]:
     """Concatenate every rank's 1-D uint8 span, in rank order, on rank `dst`.
 
-    Returns (stream on dst / None elsewhere, list of span lengths).  One all_gather of 8-byte
-    lengths plus one grouped send/recv round: the "single NCCL gather" of the codestream.
+    Returns (stream on dst / None elsewhere, list of span lengths).  One all-gather of the 8-byte
+    lengths (read back with a single synchronisation) plus one grouped send/recv round: the "single
+    NCCL gather" of the codestream.  `out`, if given on `dst`, is a reusable receive buffer (the
+    stream is returned as a view of it when it is large enough).
     """
     if local.dtype != torch.uint8 or local.dim() != 1:
         raise ValueError("span must be a 1-D uint8 tensor")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    lens_t = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
-    dist.all_gather(lens_t, n_local, group=group)
-    lens = [int(t.item()) for t in lens_t]
+    lens_t = torch.empty(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(lens_t, n_local, group=group)
+    lens = [int(v) for v in lens_t.tolist()]
     if rank == dst:
-        out = torch.empty(sum(lens), dtype=torch.uint8, device=local.device)
+        total = sum(lens)
+        if out is not None and out.numel() >= total and out.dtype == torch.uint8 and out.device == local.device:
+            out = out[:total]
+        else:
+            out = torch.empty(total, dtype=torch.uint8, device=local.device)
         offs = [0]
         for n in lens:
             offs.append(offs[-1] + n)
@@ -49,3 +56,71 @@ def gather_spans(local: torch.Tensor, dst: int = 0, group=None) -> tuple[torch.T
         for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst, group)]):
             req.wait()
     return None, lens
+
+
+class PeerGather:
+    """The gather of SURVEY 8e over peer memory instead of NCCL send/recv (GPUs of one node, one process
+    each): rank `dst` owns a buffer of world x region_stride bytes, every rank opens it through CUDA
+    IPC and lets its encoder's compaction kernel (k_gather_frames) write its span straight into its
+    region over NVLink.  What is left per step is one tiny all-reduce as the barrier and, on `dst`,
+    one kernel that closes the gaps between the spans (k_compact_regions).
+
+        pg = PeerGather(engine, region_bytes)                    # collective: call on every rank
+        n = engine.encode_image_device(..., d_out=pg.d_out, d_out_cap=pg.d_out_cap)
+        total = pg.finish(n, d_final, d_final_cap)               # collective; bytes on dst, 0 elsewhere
+    """
+
+    HEADER = 256
+
+    def __init__(self, engine, region_bytes: int, dst: int = 0, group=None):
+        import ctypes as C
+        self.eng, self.lib, self.dst, self.group = engine, engine.lib, dst, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.stride = (self.HEADER + region_bytes + 16 + 255) & ~255
+        self._own = self._peer = None
+        handle = [None]
+        if self.rank == dst:
+            self._own = engine.device_alloc(self.world * self.stride)
+            buf = (C.c_uint8 * 64)()
+            if self.lib.hydb_ipc_export(self._own, buf) != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            handle[0] = bytes(buf)
+        dist.broadcast_object_list(handle, src=dst, group=group)
+        if self.rank == dst:
+            self.base = self._own
+        else:
+            buf = (C.c_uint8 * 64).from_buffer_copy(handle[0])
+            self._peer = self.lib.hydb_ipc_open(buf)
+            if not self._peer:
+                raise RuntimeError("cudaIpcOpenMemHandle failed (no peer access between the GPUs?)")
+            self.base = self._peer
+        self.d_out = self.base + self.rank * self.stride + self.HEADER
+        self.d_out_cap = self.stride - self.HEADER - 16
+        self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        self._len = (C.c_uint64 * 1)()
+
+    def finish(self, n_local: int, d_final: int = 0, d_final_cap: int = 0) -> int:
+        """After this rank's encode call has returned (its span is in the region): publish the length,
+        wait for everyone, and on `dst` compact the spans into d_final.  Returns the stream's bytes on
+        `dst`, 0 elsewhere."""
+        import ctypes as C
+        self._len[0] = n_local
+        if self.lib.hydb_memcpy_h2d(self.base + self.rank * self.stride, self._len, 8) != 0:
+            raise RuntimeError("could not publish the span length")
+        dist.all_reduce(self._flag, group=self.group)   # the barrier: every span and length has landed
+        if self.rank != self.dst:
+            return 0
+        total = C.c_uint64(0)
+        self.eng._check(self.lib.hydb_engine_compact_regions(self.eng._h, self.base, self.world, self.stride, d_final,
+                                                             d_final_cap, C.byref(total)))
+        return int(total.value)
+
+    def close(self) -> None:
+        """Collective: peers unmap the buffer before its owner frees it."""
+        if self._peer:
+            self.lib.hydb_ipc_close(self._peer)
+            self._peer = None
+        dist.barrier(group=self.group)
+        if self._own:
+            self.eng.device_free(self._own)
+            self._own = None

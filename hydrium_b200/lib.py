@@ -22,7 +22,8 @@ HYDB_SYMBOLS = (
     "hydb_image_header", "hydb_host_alloc", "hydb_host_free", "hydb_device_alloc", "hydb_device_free",
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
     "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
-    "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header",
+    "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header", "hydb_ipc_export", "hydb_ipc_open", "hydb_ipc_close",
+    "hydb_engine_compact_regions",
 )
 
 
@@ -87,6 +88,14 @@ def load_library() -> C.CDLL:
     lib.hydb_device_alloc.argtypes = [C.c_size_t]
     lib.hydb_device_free.restype = None
     lib.hydb_device_free.argtypes = [vp]
+    lib.hydb_ipc_export.restype = C.c_int
+    lib.hydb_ipc_export.argtypes = [vp, vp]
+    lib.hydb_ipc_open.restype = vp
+    lib.hydb_ipc_open.argtypes = [vp]
+    lib.hydb_ipc_close.restype = None
+    lib.hydb_ipc_close.argtypes = [vp]
+    lib.hydb_engine_compact_regions.restype = C.c_int
+    lib.hydb_engine_compact_regions.argtypes = [vp, vp, u32, u64, vp, u64, C.POINTER(u64)]
     lib.hydb_memcpy_h2d.restype = C.c_int
     lib.hydb_memcpy_h2d.argtypes = [vp, vp, C.c_size_t]
     lib.hydb_memcpy_d2h.restype = C.c_int

@@ -17,3 +17,18 @@ def test_sharded_encode_gathers_to_identical_stream(oracle, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "DIST_OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_peer_memory_gather(oracle):
+    """Two GPUs of one node: spans written into rank 0's HBM by the encoders' own compaction kernels
+    (CUDA IPC peer memory), closed up by k_compact_regions.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIST_GPU_OK" in r.stdout
