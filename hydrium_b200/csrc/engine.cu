@@ -37,6 +37,8 @@ struct HydbEngine {
     std::vector<uint32_t> shapes;   // (vbw << 16) | vbh, index = shape id
     uint32_t *d_shape_dims = nullptr;
     uint32_t *d_overflow = nullptr;
+    uint64_t *d_small = nullptr;    // [4] scratch for single-result kernels (compact_regions)
+    uint64_t *h_small = nullptr;    // pinned twin
     uint32_t *h_err = nullptr;      // pinned [max_batch + 1]; last entry = gather overflow flag
     uint64_t *h_total = nullptr;    // pinned [1]
     uint32_t last_n = 0;
@@ -169,6 +171,8 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(dalloc(&eng->templ.bits, 1 + kMaxShapes));
     A(dalloc(&eng->d_shape_dims, 2 * kMaxShapes));
     A(dalloc(&eng->d_overflow, 1));
+    A(dalloc(&eng->d_small, 4));
+    A(cudaMallocHost((void **)&eng->h_small, 4 * sizeof(uint64_t)));
     A(cudaMallocHost((void **)&eng->h_err, (T + 1) * sizeof(uint32_t)));
     A(cudaMallocHost((void **)&eng->h_total, sizeof(uint64_t)));
     A(cudaMemsetAsync(eng->templ.words, 0, (size_t)(1 + kMaxShapes) * kTemplWords * sizeof(uint32_t), eng->st));
@@ -222,6 +226,8 @@ void hydb_engine_destroy(HydbEngine *eng) {
     for (cudaEvent_t ev : eng->tev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : eng->lev) if (ev) cudaEventDestroy(ev);
     if (eng->h_err) cudaFreeHost(eng->h_err);
+    if (eng->h_small) cudaFreeHost(eng->h_small);
+    cudaFree(eng->d_small);
     if (eng->h_total) cudaFreeHost(eng->h_total);
     if (eng->ev_front) cudaEventDestroy(eng->ev_front);
     if (eng->ev_lf) cudaEventDestroy(eng->ev_lf);
@@ -928,6 +934,19 @@ void hydb_ipc_close(void *p) {
         cudaIpcCloseMemHandle(p);
 }
 
+// Stream-ordered store of one 64-bit word into device (or mapped peer) memory.  A host-side cudaMemcpy
+// from pageable memory may return before the bytes have landed, which is not good enough for a
+// length that another GPU reads right after the barrier.
+HYDStatusCode hydb_engine_store_u64(HydbEngine *eng, void *d_dst, uint64_t value) {
+    if (!eng || !d_dst || ((uintptr_t)d_dst & 7))
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    launch_store_u64(static_cast<uint64_t *>(d_dst), value, eng->st);
+    eng->launches++;
+    CK(cudaGetLastError());
+    return HYD_OK;
+}
+
 HYDStatusCode hydb_engine_compact_regions(HydbEngine *eng, const uint8_t *d_regions, uint32_t nregions, uint64_t region_stride,
                                           uint8_t *d_out, uint64_t d_out_cap, uint64_t *total) {
     if (!eng || !d_regions || !nregions || nregions > 64 || region_stride < 512 || (region_stride & 15) || !d_out || !total) {
@@ -935,31 +954,26 @@ HYDStatusCode hydb_engine_compact_regions(HydbEngine *eng, const uint8_t *d_regi
         return HYD_API_ERROR;
     }
     CK(cudaSetDevice(eng->device));
-    uint64_t *d_total = nullptr;
-    if (cudaMalloc(&d_total, 16) != cudaSuccess) {
-        eng->error = "device allocation failed";
-        return HYD_NOMEM;
-    }
+    uint64_t *d_total = eng->d_small;
     uint32_t *d_ovf = reinterpret_cast<uint32_t *>(d_total + 1);
-    uint64_t res[2] = {0, 0};
+    volatile uint64_t *res = eng->h_small;
     HYDStatusCode rc = HYD_OK;
     if (cudaMemsetAsync(d_total, 0, 16, eng->st) != cudaSuccess)
         rc = HYD_INTERNAL_ERROR;
     if (rc == HYD_OK) {
         launch_compact_regions(d_regions, nregions, region_stride, d_out, d_out_cap, d_total, d_ovf, eng->st);
         eng->launches++;
-        if (cudaMemcpyAsync(res, d_total, 16, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
+        if (cudaMemcpyAsync(eng->h_small, d_total, 16, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
             cudaStreamSynchronize(eng->st) != cudaSuccess)
             rc = HYD_INTERNAL_ERROR;
     }
-    cudaFree(d_total);
     if (rc == HYD_OK && (uint32_t)res[1]) {
         eng->error = "gathered codestream does not fit the output buffer";
         rc = HYD_INTERNAL_ERROR;
     }
     if (rc != HYD_OK && eng->error.empty())
         eng->error = "CUDA failure while compacting the gathered spans";
-    *total = res[0];
+    *total = rc == HYD_OK ? res[0] : 0;
     return rc;
 }
 

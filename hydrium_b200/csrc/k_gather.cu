@@ -155,6 +155,9 @@ k_compact_regions(const uint8_t *__restrict__ regions, uint32_t nregions, uint64
         dst[done + tid] = src[done + tid];
 }
 
+__global__ void k_store_u64(uint64_t *dst, uint64_t v) { *dst = v; }
+void launch_store_u64(uint64_t *dst, uint64_t v, cudaStream_t st) { k_store_u64<<<1, 1, 0, st>>>(dst, v); }
+
 void launch_compact_regions(const uint8_t *regions, uint32_t nregions, uint64_t region_stride, uint8_t *out, uint64_t out_cap,
                             uint64_t *d_total, uint32_t *d_overflow, cudaStream_t st) {
     k_compact_regions<<<dim3(148, nregions), 256, 0, st>>>(regions, nregions, region_stride, out, out_cap, d_total, d_overflow);

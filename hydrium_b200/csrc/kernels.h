@@ -81,6 +81,8 @@ void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t 
 // spans written by every rank into its region of a buffer on the gathering rank -> one contiguous stream
 void launch_compact_regions(const uint8_t *regions, uint32_t nregions, uint64_t region_stride, uint8_t *out, uint64_t out_cap,
                             uint64_t *d_total, uint32_t *d_overflow, cudaStream_t st);
+// one 64-bit word, stream ordered (a span length published to the gathering rank's memory)
+void launch_store_u64(uint64_t *dst, uint64_t v, cudaStream_t st);
 void launch_synth_fill(void *dst, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t full_w,
                        uint32_t full_h, int bits, uint32_t seed, int smooth, cudaStream_t st);
 int ans_encode_smem_bytes();

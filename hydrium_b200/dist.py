@@ -97,17 +97,18 @@ class PeerGather:
         self.d_out = self.base + self.rank * self.stride + self.HEADER
         self.d_out_cap = self.stride - self.HEADER - 16
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
-        self._len = (C.c_uint64 * 1)()
+        self._ext = torch.cuda.ExternalStream(engine.stream, device=self._flag.device)
 
     def finish(self, n_local: int, d_final: int = 0, d_final_cap: int = 0) -> int:
         """After this rank's encode call has returned (its span is in the region): publish the length,
         wait for everyone, and on `dst` compact the spans into d_final.  Returns the stream's bytes on
         `dst`, 0 elsewhere."""
         import ctypes as C
-        self._len[0] = n_local
-        if self.lib.hydb_memcpy_h2d(self.base + self.rank * self.stride, self._len, 8) != 0:
-            raise RuntimeError("could not publish the span length")
-        dist.all_reduce(self._flag, group=self.group)   # the barrier: every span and length has landed
+        # the length goes out on the engine's stream and the barrier is enqueued behind it on the same
+        # stream, so no rank passes the barrier before every span and every length has landed
+        self.eng._check(self.lib.hydb_engine_store_u64(self.eng._h, self.base + self.rank * self.stride, n_local))
+        with torch.cuda.stream(self._ext):
+            dist.all_reduce(self._flag, group=self.group)
         if self.rank != self.dst:
             return 0
         total = C.c_uint64(0)

@@ -23,7 +23,7 @@ HYDB_SYMBOLS = (
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
     "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
     "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header", "hydb_ipc_export", "hydb_ipc_open", "hydb_ipc_close",
-    "hydb_engine_compact_regions",
+    "hydb_engine_compact_regions", "hydb_engine_store_u64",
 )
 
 
@@ -94,6 +94,8 @@ def load_library() -> C.CDLL:
     lib.hydb_ipc_open.argtypes = [vp]
     lib.hydb_ipc_close.restype = None
     lib.hydb_ipc_close.argtypes = [vp]
+    lib.hydb_engine_store_u64.restype = C.c_int
+    lib.hydb_engine_store_u64.argtypes = [vp, vp, u64]
     lib.hydb_engine_compact_regions.restype = C.c_int
     lib.hydb_engine_compact_regions.argtypes = [vp, vp, u32, u64, vp, u64, C.POINTER(u64)]
     lib.hydb_memcpy_h2d.restype = C.c_int

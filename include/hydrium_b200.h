@@ -237,11 +237,13 @@ HYDRIUM_EXPORT int hydb_device_count(void);
  * buffer of `regions` x region_stride bytes (hydb_device_alloc) and exports it; every rank opens it and
  * passes  base + rank * region_stride + 256  as d_out to its encode call, so its frames are written
  * straight into the gathering rank's HBM over NVLink by the compaction kernel itself, then stores the
- * span length (uint64) at  base + rank * region_stride.  After a barrier the gathering rank closes the
+ * span length (uint64) at  base + rank * region_stride  with hydb_engine_store_u64 (stream ordered).  After a barrier the gathering rank closes the
  * gaps with hydb_engine_compact_regions: spans in rank order, contiguous, in d_out; *total = bytes. */
 HYDRIUM_EXPORT int hydb_ipc_export(const void *d_ptr, uint8_t handle[64]);
 HYDRIUM_EXPORT void *hydb_ipc_open(const uint8_t handle[64]);
 HYDRIUM_EXPORT void hydb_ipc_close(void *p);
+/* one 64-bit word written on the engine's stream (the span length in a region header) */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_store_u64(HydbEngine *engine, void *d_dst, uint64_t value);
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_compact_regions(HydbEngine *engine, const uint8_t *d_regions, uint32_t regions,
                                                          uint64_t region_stride, uint8_t *d_out, uint64_t d_out_cap,
                                                          uint64_t *total);

@@ -233,6 +233,19 @@ def test_pfm_reader_against_reference_library(cli_ref, reflib, tmp_path, case):
     assert got == _want_pfm(reflib, img, opts, shift)
 
 
+def test_cli_reads_stdin_and_writes_stdout(cli_ref, tmp_path):
+    samples, color, depth, inter, pal, _ = _png_case("rgb8", 70, 50, seed=5)
+    src = str(tmp_path / "in.png")
+    write_png(src, samples, color, depth, inter, pal)
+    want = _run(cli_ref, [], src, str(tmp_path / "out.jxl"))
+    with open(src, "rb") as f:
+        r = subprocess.run([cli_ref, "-", "-"], stdin=f, capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == want
+    r = subprocess.run([cli_ref, "--", src], capture_output=True, timeout=120)   # output defaults to stdout
+    assert r.returncode == 0 and r.stdout == want
+
+
 def test_cli_option_errors(cli_ref, tmp_path):
     def rc(*args):
         return subprocess.run([cli_ref, *args], capture_output=True, timeout=60)
@@ -252,7 +265,9 @@ def test_cli_option_errors(cli_ref, tmp_path):
 
 
 # ---- the product binary: same files, same bytes as the reference-linked binary ----------------------
-GPU_CASES = [PNG_CASES[0], PNG_CASES[1], PNG_CASES[8], PNG_CASES[11], PNG_CASES[12], PNG_CASES[15], PNG_CASES[19]]
+GPU_CASES = [PNG_CASES[0], PNG_CASES[1], PNG_CASES[8], PNG_CASES[11], PNG_CASES[12], PNG_CASES[15], PNG_CASES[19],
+             ("rgb8", 2100, 300, [], -1),            # one frame over two LF groups
+             ("rgb16", 2060, 40, ["--linear"], -1)]  # ... 16-bit linear, the second LF group 12 px wide
 
 
 @pytest.mark.gpu
