@@ -17,6 +17,9 @@
 //   coefficient, ctx = 458 i + 111 + prev + 2 (n+f) -> 3 + prev + 2 ((i + n + f) mod 3)
 // so the neighbour-predicted count of encoder.c:670-687 never influences the output.
 // Symbol offsets come from one CTA-wide exclusive scan over the <= 3072 (block, channel) counts.
+// Small launches put several CTAs on a tile (gridDim.y parts): each repeats the cheap scan and codes
+// its share of the entries, histograms and residue-bit counts are accumulated in HBM with atomics --
+// the tokeniser of one tile is issue bound on its SM, and a band of 64 tiles leaves half the SMs idle.
 #include "common.cuh"
 #include "kernels.h"
 #include "tables.cuh"
@@ -50,6 +53,7 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
     __shared__ uint32_t s_resbits, s_err;
 
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t part = blockIdx.y, parts = gridDim.y;
     const TileDesc t = tiles[tile];
     if (t.flags & kTilePrefix)   // pseudo-tile of a multi-group frame (k_frame.cu): no pixels
         return;
@@ -102,7 +106,7 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
                 wi += v;
         }
         s_warp[lane] = wi - w;   // exclusive warp base
-        if (lane == 31)
+        if (lane == 31 && part == 0)
             nsyms[tile] = wi;
     }
     __syncthreads();
@@ -141,17 +145,25 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
             }
         }
     };
+    // this CTA's share of the entries: [e_begin, e_end)
+    const uint32_t e_begin = (uint32_t)(((uint64_t)ne * part) / parts), e_end = (uint32_t)(((uint64_t)ne * (part + 1)) / parts);
+    auto fetch_part = [&](uint32_t e, int &lo, int &hi) {
+        if (e < e_end)
+            fetch(e, lo, hi);
+        else
+            lo = hi = 0;
+    };
     int buf_lo[kAhead], buf_hi[kAhead];
 #pragma unroll
     for (int k = 0; k < kAhead; k++)
-        fetch(warp + (uint32_t)k * kStep, buf_lo[k], buf_hi[k]);
-    for (uint32_t e0 = warp; e0 < ne; e0 += kStep * kAhead) {
+        fetch_part(e_begin + warp + (uint32_t)k * kStep, buf_lo[k], buf_hi[k]);
+    for (uint32_t e0 = e_begin + warp; e0 < e_end; e0 += kStep * kAhead) {
 #pragma unroll
         for (int k = 0; k < kAhead; k++) {
             const uint32_t e = e0 + (uint32_t)k * kStep;
             const int q_lo = buf_lo[k], q_hi = buf_hi[k];
-            fetch(e + kStep * kAhead, buf_lo[k], buf_hi[k]);
-            if (e >= ne)
+            fetch_part(e + kStep * kAhead, buf_lo[k], buf_hi[k]);
+            if (e >= e_end)
                 continue;
             const uint32_t blk = e / 3, i = e - blk * 3;
             const uint32_t info = s_info[e], nz = info & 0xFF, last = info >> 8;
@@ -210,19 +222,32 @@ k_hf_tokens(const TileDesc *__restrict__ tiles, const int16_t *__restrict__ coef
             atomicOr(&s_err, my_err);
     }
     __syncthreads();
-    for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)
-        hist[(size_t)tile * kHfClusters * kHfTokens + i] = s_hist[i];
-    if (tid == 0) {
-        resbits[tile] = s_resbits;
-        if (s_err)
-            atomicOr(&tile_err[tile], s_err);
+    if (parts == 1) {
+        for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)
+            hist[(size_t)tile * kHfClusters * kHfTokens + i] = s_hist[i];
+        if (tid == 0)
+            resbits[tile] = s_resbits;
+    } else {   // hist / resbits of the launch were zeroed beforehand (launch_hf_tokens)
+        for (uint32_t i = tid; i < kHfClusters * kHfTokens; i += kTokThreads)
+            if (s_hist[i])
+                atomicAdd(&hist[(size_t)tile * kHfClusters * kHfTokens + i], s_hist[i]);
+        if (tid == 0 && s_resbits)
+            atomicAdd(&resbits[tile], s_resbits);
     }
+    if (tid == 0 && s_err)
+        atomicOr(&tile_err[tile], s_err);
 }
 
 void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
     prefer_max_shared(k_hf_tokens);
-    k_hf_tokens<<<ntiles, kTokThreads, 0, st>>>(ws.tiles, ws.coef, ws.nzinfo, ws.syms, ws.nsyms, ws.resbits, ws.hist,
-                                                ws.tile_err);
+    // CTAs per tile: fill the 148 SMs when the launch has few tiles (one band of the pipeline, one frame, one tile)
+    const uint32_t parts = ntiles <= 37 ? 4u : (ntiles <= 74 ? 2u : 1u);
+    if (parts > 1) {
+        cudaMemsetAsync(ws.hist, 0, (size_t)ntiles * kHfClusters * kHfTokens * sizeof(uint32_t), st);
+        cudaMemsetAsync(ws.resbits, 0, (size_t)ntiles * sizeof(uint32_t), st);
+    }
+    k_hf_tokens<<<dim3(ntiles, parts), kTokThreads, 0, st>>>(ws.tiles, ws.coef, ws.nzinfo, ws.syms, ws.nsyms, ws.resbits,
+                                                             ws.hist, ws.tile_err);
 }
 
 }  // namespace hydb
