@@ -61,9 +61,8 @@ typedef enum HYDSampleFormat {
 } HYDSampleFormat;
 
 /* libhydrium.h:109-155.  tile_size_shift_{x,y}: 0..3 => 256<<shift pixel tiles, -1 => one frame.
- * This library encodes tile mode with shift 0/0 (one 256x256 group per frame), and one-frame
- * mode for images that fit a single group; other values are rejected with HYD_API_ERROR
- * ("tile size not supported by the B200 encoder"), see DESIGN.md. */
+ * Every combination is encoded; the one limit is one-frame mode beyond 256 LF groups of 2048x2048
+ * (more than 1 Gpx), which hyd_set_metadata refuses with HYD_API_ERROR and a message. */
 typedef struct HYDImageMetadata {
     size_t width;
     size_t height;
