@@ -776,7 +776,11 @@ static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t ro
         for (cudaEvent_t &e : tr) cudaEventCreate(&e);
     if (trace) cudaEventRecord(tr[0], eng->st);
     CK(cudaEventRecord(eng->ev_desc, eng->st));
-    const uint32_t nbands = rows < (uint32_t)HydbEngine::kBands ? rows : (uint32_t)HydbEngine::kBands;
+    // HYDRIUM_B200_BANDS=1..4 for experiments (tools/bands_sweep.py: 3.80 / 3.70 / 3.61 / 3.60 ms for 1 / 2 / 3 / 4 bands
+    // on config 2; five and more were slower still)
+    static const uint32_t band_limit = [] { const char *e = getenv("HYDRIUM_B200_BANDS"); int v = e ? atoi(e) : 0;
+                                            return (uint32_t)(v >= 1 && v <= HydbEngine::kBands ? v : HydbEngine::kBands); }();
+    const uint32_t nbands = rows < band_limit ? rows : band_limit;
     if (h_src) {
         // all copies first, on one stream: they reach the device in band order at full PCIe rate, and
         // every band's kernels wait only for their own rows (separate per-band copies were served in
