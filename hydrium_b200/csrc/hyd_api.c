@@ -495,6 +495,20 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
     return HYD_OK;
 }
 
+/* Device output -> the pending-output queue.  The queue is ordinary (pageable, growing) memory, and a
+ * device-to-pageable copy runs at a fraction of PCIe speed; the page-locked staging buffer is idle once
+ * the kernels have consumed the tile pixels, so the bytes take that way when they fit. */
+static int fetch_output(HYDEncoder *enc, size_t bytes) {
+    uint8_t *dst = enc->pend + enc->pend_len;
+    if (bytes <= enc->stage_cap) {
+        if (hydb_memcpy_d2h(enc->stage_host, enc->out_dev, bytes))
+            return -1;
+        memcpy(dst, enc->stage_host, bytes);
+        return 0;
+    }
+    return hydb_memcpy_d2h(dst, enc->out_dev, bytes);
+}
+
 /* encode everything queued and move the frames to the pending-output queue */
 /* ICC-tagged image: the image header (with the entropy-coded profile) goes out ahead of the first
  * frame, from its own kernel; the frame paths then run as if the header had been written already */
@@ -532,7 +546,7 @@ static HYDStatusCode run_batch(HYDEncoder *enc) {
     rc = pend_reserve(enc, (size_t)bytes);
     if (rc < HYD_ERROR_START)
         return rc;
-    if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
+    if (fetch_output(enc, (size_t)bytes))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
     if (api_trace()) {
         fprintf(stderr, "[hydrium_b200] batch of %u tiles: staging %.2f (since the previous batch %.2f)  h2d %.2f  gpu %.2f  d2h %.2f ms\n",
@@ -626,7 +640,7 @@ static HYDStatusCode run_frame(HYDEncoder *enc, HydbFrame *fr) {
     rc = pend_reserve(enc, (size_t)bytes);
     if (rc < HYD_ERROR_START)
         return rc;
-    if (hydb_memcpy_d2h(enc->pend + enc->pend_len, enc->out_dev, (size_t)bytes))
+    if (fetch_output(enc, (size_t)bytes))
         return gpu_error(enc, HYD_INTERNAL_ERROR);
     if (api_trace())
         fprintf(stderr, "[hydrium_b200] frame %ux%u: h2d %.2f  launch %.2f  wait %.2f  d2h %.2f ms (%llu bytes)\n", fr->width,
