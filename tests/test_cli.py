@@ -265,6 +265,12 @@ def test_cli_option_errors(cli_ref, tmp_path):
 
 
 # ---- the product binary: same files, same bytes as the reference-linked binary ----------------------
+@pytest.fixture(scope="module", autouse=True)
+def _product_cli_built():
+    if not os.path.exists(CLI_OURS):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hydrium_b200", "csrc")], check=True, capture_output=True)
+
+
 GPU_CASES = [PNG_CASES[0], PNG_CASES[1], PNG_CASES[8], PNG_CASES[11], PNG_CASES[12], PNG_CASES[15], PNG_CASES[19],
              ("rgb8", 2100, 300, [], -1),            # one frame over two LF groups
              ("rgb16", 2060, 40, ["--linear"], -1)]  # ... 16-bit linear, the second LF group 12 px wide
