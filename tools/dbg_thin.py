@@ -1,5 +1,8 @@
-import sys, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+"""Thin one-frame images (LF groups a few pixels high or wide) against the reference library: the shapes
+that exercised the parallel LFGroup coder's corner cases."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hydrium_b200.encoder import encode_cli_loop
 from hydrium_b200.lib import load_library
 from hydrium_b200.synth import synth_image
