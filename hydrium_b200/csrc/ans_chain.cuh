@@ -128,4 +128,51 @@ HD void ans_step(AnsCarry &c, const AnsSymInfo &own, const AnsSymInfo *next, uin
     s_out = q12 | slot;
 }
 
+// ---- the same step over the COMPACT inverse map (ans_model.cuh) ---------------------------------------
+// Element units instead of table byte addresses: the step yields  g = cum + x % f  and the caller turns
+// g into the slot (a warp-wide search over the cluster's sorted pieces).  Same quotient, same exactness
+// argument; k is 1 / 0 instead of 2 / 0 and c0 = a + cum.
+struct AnsRecC {
+    uint32_t mc;    // ceil(2^32 / f), as AnsSymInfo
+    uint32_t ne;    // -e
+    uint32_t nf;    // -f (mod 2^32)
+    uint32_t cum;   // cumulative frequency of the symbol inside its cluster
+};
+HD AnsRecC ans_rec_c(uint32_t f, uint32_t cum) {
+    const AnsSymInfo s = ans_sym_info(f, 0);
+    AnsRecC r;
+    r.mc = s.mc;
+    r.ne = s.ne;
+    r.nf = f ? 0u - f : 0u;
+    r.cum = cum;
+    return r;
+}
+HD void ans_prepare_c(AnsCarry &c, uint32_t a, bool v_counts, uint32_t mc, uint32_t ne, uint32_t cum) {
+    c.meff = v_counts ? mc : 0u;
+    c.k = v_counts ? 1u : 0u;
+    const uint64_t w = (uint64_t)a * mc;
+    const uint32_t qa = ans_hi32(w) - 1u;
+    c.c0 = a + cum;
+    c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)ne);
+}
+HD void ans_chain_begin_c(AnsCarry &c, const AnsRecC &first) {
+    const uint32_t f = 0u - first.nf;
+    const uint32_t x = ((kAnsInitState >> 20) >= f) ? (kAnsInitState >> 16) : kAnsInitState;
+    c.v = 0;
+    ans_prepare_c(c, x, false, first.mc, first.ne, first.cum);
+}
+// `slot_of(g)` maps g = cum + remainder to the alias slot of the symbol's cluster
+template <typename SlotOf>
+HD void ans_step_c(AnsCarry &c, const AnsRecC &own, const AnsRecC *next, SlotOf slot_of, uint32_t &s_out) {
+    const uint32_t q = ans_hi32((uint64_t)c.v * c.meff + c.R);
+    const uint32_t slot = slot_of(q * own.nf + (c.v * c.k + c.c0));
+    const bool p = next && q >= ((0u - next->nf) << 8);
+    const uint32_t q12 = q << 12;
+    const uint32_t a = p ? (q >> 4) : q12;
+    if (next)
+        ans_prepare_c(c, a, !p, next->mc, next->ne, next->cum);
+    c.v = slot;
+    s_out = q12 | slot;
+}
+
 }  // namespace hydb

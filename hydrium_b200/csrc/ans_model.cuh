@@ -18,15 +18,19 @@
 
 namespace hydb {
 
-struct AnsCluster {
-    uint16_t freq[kHfTokens];   // normalised frequencies (0 for unused)
-    uint16_t cum[kHfTokens];    // exclusive prefix sums
-    uint8_t owner[kHfTokens];   // per bucket: symbol that owns the part above `cut`
-    uint16_t cut[kHfTokens];    // per bucket: size of the bucket's own symbol share
-    int16_t off[kHfTokens];     // per bucket: symbol offset of position 0 of the foreign part
-    uint32_t alpha;             // alphabet size (max token + 1), 0 = cluster unused
-    uint32_t single;            // 1: one symbol with frequency 4096
+template <int NT>
+struct AnsClusterT {
+    static constexpr int kTokens = NT;
+    uint16_t freq[NT];   // normalised frequencies (0 for unused)
+    uint16_t cum[NT];    // exclusive prefix sums
+    uint8_t owner[NT];   // per bucket: symbol that owns the part above `cut`
+    uint16_t cut[NT];    // per bucket: size of the bucket's own symbol share
+    int16_t off[NT];     // per bucket: symbol offset of position 0 of the foreign part
+    uint32_t alpha;      // alphabet size (max token + 1), 0 = cluster unused
+    uint32_t single;     // 1: one symbol with frequency 4096
 };
+using AnsCluster = AnsClusterT<kHfTokens>;   // log_alphabet_size 5 or 6
+using AnsCluster32 = AnsClusterT<32>;        // log_alphabet_size 5 only (k_ans_chain_compact)
 
 // counts -> 12-bit frequencies (reference: entropy.c:267-301).  Returns -1 if all zero, else
 // whether the LAST symbol took everything.
@@ -67,12 +71,13 @@ HDN inline int ans_normalise(uint32_t *f, uint32_t n) {
 
 // Vose-style alias split with the reference's LIFO work lists (entropy.c:184-242).
 // counts[] holds the NORMALISED frequencies.  Returns false where the reference errors out.
-HDN inline bool ans_build_alias(AnsCluster &c, const uint32_t *normalised, uint32_t alpha, int log_alpha, bool single) {
+template <class Cluster>
+HDN inline bool ans_build_alias(Cluster &c, const uint32_t *normalised, uint32_t alpha, int log_alpha, bool single) {
     const uint32_t bucket = 1u << (12 - log_alpha), slots = 1u << log_alpha;
     c.alpha = alpha;
     c.single = single ? 1u : 0u;
     uint32_t run = 0;
-    for (uint32_t s = 0; s < (uint32_t)kHfTokens; s++) {
+    for (uint32_t s = 0; s < (uint32_t)Cluster::kTokens; s++) {
         const uint32_t f = s < alpha ? normalised[s] : 0;
         c.freq[s] = (uint16_t)f;
         c.cum[s] = (uint16_t)run;
@@ -128,7 +133,8 @@ HDN inline bool ans_build_alias(AnsCluster &c, const uint32_t *normalised, uint3
 }
 
 // slot s of the alias table decodes to (symbol, offset) (reference: entropy.c:233-262 read backwards)
-HD void ans_slot_symbol(const AnsCluster &c, uint32_t s, int log_alpha, uint32_t &sym, uint32_t &offset) {
+template <class Cluster>
+HD void ans_slot_symbol(const Cluster &c, uint32_t s, int log_alpha, uint32_t &sym, uint32_t &offset) {
     const uint32_t lb = 12u - (uint32_t)log_alpha;
     const uint32_t i = s >> lb, pos = s & ((1u << lb) - 1u);
     if (c.single) {
@@ -142,6 +148,65 @@ HD void ans_slot_symbol(const AnsCluster &c, uint32_t s, int log_alpha, uint32_t
         sym = c.owner[i];
         offset = (uint32_t)((int32_t)c.off[i] + (int32_t)pos);
     }
+}
+
+// ---- compact form of the inverse alias map (log_alpha 5: 32 buckets of 128 slots) ----------------
+// The alias map is a bijection between g = cum[sym] + offset in [0, 4096) and the slots.  Every
+// bucket i contributes at most two PIECES on which  slot = g + delta  holds:
+//   own share      sym i          offsets [0, own)                 slots [128 i, 128 i + own)
+//   foreign share  sym owner[i]   offsets [off + cut, off + 128)   slots [128 i + cut, 128 i + 128)
+// (reference: entropy.c:233-262 read backwards), so <= 64 pieces partition [0, 4096).  Sorted by their
+// first g they are dealt two per lane; lane L keeps {lo0, lo1, delta0 + (L << 13), delta1 + (L << 13)}
+// and the slot of g is found by the whole warp at once:
+//     cand = g >= lo0 ? g + (g >= lo1 ? e1 : e0) : 0          slot = max over lanes (cand) & 0xFFF
+// The owner is the highest lane with lo0 <= g; lower lanes see g ABOVE their pieces, so their
+// g + delta stays in [0, 8190] and never reaches the lane tag in bits 13+.  4.6 KB per tile instead of
+// the 72 KB direct table: the form k_ans_chain_compact uses when many chains must share an SM.
+constexpr int kAnsPieces = 64;
+constexpr uint32_t kAnsPieceNone = 4096;   // first g of an unused piece: never reached
+// piece p of the cluster: p < 32 own share of bucket p, p >= 32 foreign share of bucket p - 32.
+// Returns its length (0 = unused).
+template <class Cluster>
+HD uint32_t ans_piece(const Cluster &c, uint32_t p, uint32_t &lo, int32_t &delta) {
+    const uint32_t bucket = 128u, i = p & 31u;
+    lo = kAnsPieceNone;
+    delta = 0;
+    if (c.single) {   // one symbol owns everything and slot == offset (entropy.c:195-200)
+        if (p)
+            return 0;
+        lo = 0;
+        return (uint32_t)kAnsTotal;
+    }
+    const bool full = c.cut[i] == 0 && c.owner[i] == i;   // the bucket holds nothing but its own symbol
+    if (p < 32u) {
+        const uint32_t own = full ? bucket : c.cut[i];
+        if (!own || !c.freq[i])
+            return 0;
+        lo = c.cum[i];
+        delta = (int32_t)(i * bucket) - (int32_t)c.cum[i];
+        return own;
+    }
+    if (full)
+        return 0;
+    const uint32_t o = c.owner[i];
+    lo = (uint32_t)((int32_t)c.cum[o] + (int32_t)c.off[i] + (int32_t)c.cut[i]);
+    delta = (int32_t)(i * bucket) - (int32_t)c.off[i] - (int32_t)c.cum[o];
+    return bucket - c.cut[i];
+}
+// position of piece p in the sorted order (used pieces by first g, then the unused ones): O(64)
+HD uint32_t ans_piece_rank(const uint32_t *lo /*[64]*/, uint32_t p) {
+    uint32_t r = 0;
+    const uint32_t mine = lo[p];
+    for (uint32_t q = 0; q < (uint32_t)kAnsPieces; q++)
+        r += (lo[q] < mine || (lo[q] == mine && q < p)) ? 1u : 0u;
+    return r;
+}
+struct AnsPieceLane {
+    uint32_t lo0, lo1, e0, e1;
+};
+// what one lane contributes to the warp-wide maximum
+HD uint32_t ans_piece_candidate(const AnsPieceLane &pl, uint32_t g) {
+    return g >= pl.lo0 ? g + (g >= pl.lo1 ? pl.e1 : pl.e0) : 0u;
 }
 
 HD void ans_put_u8(BitSink &bw, uint32_t b) {   // reference: entropy.c:71-78

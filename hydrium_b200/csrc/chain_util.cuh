@@ -1,0 +1,60 @@
+// hydrium_b200/csrc/chain_util.cuh
+//
+// Inline-PTX helpers shared by the two rANS chain kernels (k_ans.cu, k_ans_compact.cu): named
+// barriers between the chain warp and its helper warp, and shared-memory accesses by 32-bit
+// shared-window address (so that ptxas keeps them in program order around the chain step).
+#pragma once
+
+#include <stdint.h>
+
+namespace hydb {
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// shared-memory barriers (mbarrier): unlike named barriers they do not count against the 64 barrier
+// slots of an SM (16 named barriers per CTA would cap a kernel at 4 CTAs per SM)
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {   // release: the thread's earlier shared stores are visible to waiters
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra MBAR_DONE;\n"
+        " bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint32_t v;
+    // volatile: keeps the table load of a chain step ahead of that step's record prefetch and state
+    // store in program order, so nothing queues in front of it in the shared-memory pipe
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+}  // namespace hydb

@@ -47,6 +47,7 @@ enum TileError : uint32_t {
     kErrAlias = 1u << 5,          // reference would fail: "empty underfull during alias table gen"
     kErrLfAlphabet = 1u << 6,     // more distinct LF tokens than the sparse coder holds
     kErrNonFinite = 1u << 7,      // NaN / Inf float sample (reference: format.c:123-126 "Invalid NaN Float")
+    kErrRange = 1u << 8,          // quantised HF coefficient outside int16 (float samples far outside [0, 1])
 };
 
 // Device-visible tile descriptor (mirrors what hyd_send_tile is given,

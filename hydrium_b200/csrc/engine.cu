@@ -62,6 +62,21 @@ struct HydbEngine {
     bool timing = false, timed_pending = false;
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, lev[2] = {nullptr, nullptr};
     double stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};   // xyb_dct, hf_tokens, ans_chain, ans_pack(+LF wait), gather, lf_group, batches
+    // asynchronous jobs (hydb_engine_submit_*): each owns a stream pair, a range of workspace slots
+    // and a page-locked result record the last kernel of the job writes directly
+    struct Job {
+        cudaStream_t st = nullptr, st2 = nullptr;
+        cudaEvent_t ev_front = nullptr, ev_lf = nullptr, ev_done = nullptr;
+        uint32_t slot0 = 0, n = 0;
+        bool busy = false;
+        uint64_t *h_res = nullptr;   // page-locked [2]: bytes gathered, error bits | overflow << 31
+        uint32_t *d_ovf = nullptr;
+    };
+    static constexpr int kJobs = 16;
+    Job jobs[kJobs];
+    uint64_t *h_job_res = nullptr;   // page-locked [kJobs][2]
+    uint32_t *d_job_ovf = nullptr;   // [kJobs]
+    TileDesc *h_job_tiles = nullptr; // page-locked [max_batch]: descriptors of asynchronous jobs, by slot
 };
 
 #define CK(call)                                                                        \
@@ -82,6 +97,7 @@ static size_t sample_item_bytes(int sample_fmt) {
 
 static const char *tile_error_text(uint32_t bits) {
     if (bits & kErrNonFinite) return "Invalid NaN Float";                 // reference: format.c:124
+    if (bits & kErrRange) return "HF coefficient exceeds the 16-bit range of the B200 encoder (float samples far outside [0, 1])";
     if (bits & kErrAlphabet) return "HF token alphabet exceeds 64 symbols";
     if (bits & kErrHuffman) return "couldn't find target";               // reference: entropy.c:635
     if (bits & kErrAlias) return "empty underfull during alias table gen";   // reference: entropy.c:219
@@ -158,10 +174,12 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(dalloc(&w.slab, T * kSlabBytes));
     A(dalloc(&w.frame_off, T));
     A(dalloc(&w.frame_len, T));
-    A(dalloc(&w.out_off, T + 1));
+    A(dalloc(&w.out_off, 2 * T + 2));   // a view starting at slot f uses entries [2 f, 2 f + n]
     A(dalloc(&w.tile_err, T));
     A(dalloc(&w.sm_ticket, 256));
     A(cudaMemsetAsync(w.sm_ticket, 0, 256 * sizeof(uint32_t), eng->st));
+    A(dalloc(&w.sm_load, 1024));
+    A(cudaMemsetAsync(w.sm_load, 0, 1024 * sizeof(uint32_t), eng->st));
     A(dalloc(&eng->lut8_srgb, 256));
     A(dalloc(&eng->lut8_lin, 256));
     A(dalloc(&eng->lut16_srgb, 65536));
@@ -175,6 +193,19 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(cudaMallocHost((void **)&eng->h_small, 4 * sizeof(uint64_t)));
     A(cudaMallocHost((void **)&eng->h_err, (T + 1) * sizeof(uint32_t)));
     A(cudaMallocHost((void **)&eng->h_total, sizeof(uint64_t)));
+    A(cudaMallocHost((void **)&eng->h_job_res, HydbEngine::kJobs * 2 * sizeof(uint64_t)));
+    A(dalloc(&eng->d_job_ovf, HydbEngine::kJobs));
+    A(cudaMallocHost((void **)&eng->h_job_tiles, T * sizeof(TileDesc)));
+    for (int j = 0; j < HydbEngine::kJobs && e == cudaSuccess; j++) {
+        HydbEngine::Job &jb = eng->jobs[j];
+        A(cudaStreamCreateWithFlags(&jb.st, cudaStreamNonBlocking));
+        A(cudaStreamCreateWithFlags(&jb.st2, cudaStreamNonBlocking));
+        A(cudaEventCreateWithFlags(&jb.ev_front, cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&jb.ev_lf, cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&jb.ev_done, cudaEventDisableTiming));
+        jb.h_res = eng->h_job_res + 2 * j;
+        jb.d_ovf = eng->d_job_ovf + j;
+    }
     A(cudaMemsetAsync(eng->templ.words, 0, (size_t)(1 + kMaxShapes) * kTemplWords * sizeof(uint32_t), eng->st));
     A(cudaMemsetAsync(w.lfbits, 0, T * kLfBitsWords * sizeof(uint32_t), eng->st));
     A(cudaMemsetAsync(w.slab, 0, T * kSlabBytes, eng->st));
@@ -206,7 +237,7 @@ void hydb_engine_destroy(HydbEngine *eng) {
     if (eng->st2) cudaStreamSynchronize(eng->st2);
     Workspace &w = eng->ws;
     void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags, w.dbits, w.chain_out,
-                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.sm_ticket, w.dbg_xyb, w.dbg_dct,
+                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.sm_ticket, w.sm_load, w.dbg_xyb, w.dbg_dct,
                    w.dbg_freqs, w.dbg_sect, w.dbg_clk, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
     for (void *p : dev)
@@ -220,6 +251,16 @@ void hydb_engine_destroy(HydbEngine *eng) {
         if (eng->band_done[b]) cudaEventDestroy(eng->band_done[b]);
         if (eng->band_h2d[b]) cudaEventDestroy(eng->band_h2d[b]);
     }
+    for (HydbEngine::Job &jb : eng->jobs) {
+        if (jb.st) { cudaStreamSynchronize(jb.st); cudaStreamDestroy(jb.st); }
+        if (jb.st2) { cudaStreamSynchronize(jb.st2); cudaStreamDestroy(jb.st2); }
+        if (jb.ev_front) cudaEventDestroy(jb.ev_front);
+        if (jb.ev_lf) cudaEventDestroy(jb.ev_lf);
+        if (jb.ev_done) cudaEventDestroy(jb.ev_done);
+    }
+    if (eng->h_job_res) cudaFreeHost(eng->h_job_res);
+    if (eng->d_job_ovf) cudaFree(eng->d_job_ovf);
+    if (eng->h_job_tiles) cudaFreeHost(eng->h_job_tiles);
     if (eng->ev_desc) cudaEventDestroy(eng->ev_desc);
     if (eng->host_in) cudaFree(eng->host_in);
     if (eng->host_out) cudaFree(eng->host_out);
@@ -240,6 +281,13 @@ const char *hydb_engine_error(const HydbEngine *eng) { return eng ? eng->error.c
 uint32_t hydb_engine_max_batch(const HydbEngine *eng) { return eng ? eng->max_batch : 0; }
 uint64_t hydb_engine_stream(const HydbEngine *eng) { return eng ? (uint64_t)(uintptr_t)eng->st : 0; }
 uint64_t hydb_engine_launch_count(const HydbEngine *eng) { return eng ? eng->launches : 0; }
+
+HYDStatusCode hydb_engine_set_chain_kernel(HydbEngine *eng, int mode) {
+    if (!eng || mode < 0 || mode > 2)
+        return HYD_API_ERROR;
+    eng->ws.chain_mode = (uint32_t)mode;
+    return HYD_OK;
+}
 
 HYDStatusCode hydb_engine_enable_taps(HydbEngine *eng, int enable) {
     if (!eng)
@@ -300,6 +348,7 @@ static Workspace ws_view(const Workspace &w, uint32_t first) {
     v.slab += f * kSlabBytes;
     v.frame_off += f;
     v.frame_len += f;
+    v.out_off += 2 * f;
     v.tile_err += f;
     if (v.dbg_xyb) v.dbg_xyb += f * 65536 * 3;
     if (v.dbg_dct) v.dbg_dct += f * 65536 * 3;
@@ -317,10 +366,16 @@ struct SlotExtra {
 };
 
 static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, cudaStream_t st,
-                                   const SlotExtra *extra = nullptr) {
+                                   const SlotExtra *extra = nullptr, uint32_t slot0 = 0, uint32_t *d_ovf = nullptr,
+                                   bool *any_float = nullptr, bool job = false) {
     std::vector<uint32_t> fresh;
+    if (any_float)
+        *any_float = false;
     const uint32_t first_fresh = (uint32_t)eng->shapes.size();
-    eng->h_tiles.resize(n);
+    // jobs keep their descriptors in page-locked memory (by slot) so that the upload is asynchronous
+    if (!job)
+        eng->h_tiles.resize(n);
+    TileDesc *h_tiles = job ? eng->h_job_tiles + slot0 : eng->h_tiles.data();
     for (uint32_t i = 0; i < n; i++) {
         const HydbTile &s = tiles[i];
         if (!s.width || !s.height || s.width > 256 || s.height > 256 || (s.x0 & 255) || (s.y0 & 255) ||
@@ -328,12 +383,14 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
             eng->error = "invalid tile descriptor";
             return HYD_API_ERROR;
         }
+        if (any_float && s.sample_fmt == HYD_FLOAT32)
+            *any_float = true;
         const int shape = shape_of(eng, (s.width + 7) >> 3, (s.height + 7) >> 3, fresh);
         if (shape < 0) {
             eng->error = "too many distinct tile shapes in one engine";
             return HYD_API_ERROR;
         }
-        TileDesc &d = eng->h_tiles[i];
+        TileDesc &d = h_tiles[i];
         d.plane[0] = s.plane[0];
         d.plane[1] = s.plane[1];
         d.plane[2] = s.plane[2];
@@ -376,9 +433,9 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
         CK(cudaStreamSynchronize(st));   // dims is a stack-lifetime buffer
     }
     // pageable source: the runtime stages it before returning, so h_tiles may be reused immediately
-    CK(cudaMemcpyAsync(eng->ws.tiles, eng->h_tiles.data(), n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(eng->ws.tile_err, 0, n * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(eng->d_overflow, 0, sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(eng->ws.tiles + slot0, h_tiles, n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(eng->ws.tile_err + slot0, 0, n * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d_ovf ? d_ovf : eng->d_overflow, 0, sizeof(uint32_t), st));
     return HYD_OK;
 }
 
@@ -394,6 +451,33 @@ static HYDStatusCode queue_readback(HydbEngine *eng, uint32_t n, uint64_t d_out_
     return HYD_OK;
 }
 
+// the kernel sequence of a batch of classic (one-group) tiles whose descriptors are in place:
+// `v` = workspace view of the batch, st / st2 = its stream pair
+static HYDStatusCode enqueue_tile_kernels(HydbEngine *eng, const Workspace &v, uint32_t n, cudaStream_t st, cudaStream_t st2,
+                                          cudaEvent_t ev_front, cudaEvent_t ev_lf, bool allow_compact, uint8_t *out,
+                                          uint64_t out_cap, uint64_t out_pos, uint32_t *d_ovf, bool tm) {
+    if (tm) CK(cudaEventRecord(eng->tev[0], st));
+    launch_xyb_dct_quant(v, eng->luts, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[1], st));
+    CK(cudaEventRecord(ev_front, st));
+    CK(cudaStreamWaitEvent(st2, ev_front, 0));
+    if (tm) CK(cudaEventRecord(eng->lev[0], st2));
+    launch_lf_group(v, n, st2);
+    if (tm) CK(cudaEventRecord(eng->lev[1], st2));
+    CK(cudaEventRecord(ev_lf, st2));
+    launch_hf_tokens(v, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[2], st));
+    launch_ans_chain(v, n, st, allow_compact);
+    if (tm) CK(cudaEventRecord(eng->tev[3], st));
+    CK(cudaStreamWaitEvent(st, ev_lf, 0));   // the LF stream is first needed by the packer
+    launch_ans_pack(v, eng->templ, n, st);
+    if (tm) CK(cudaEventRecord(eng->tev[4], st));
+    launch_gather(v, n, out, out_cap, out_pos, d_ovf, st);
+    if (tm) CK(cudaEventRecord(eng->tev[5], st));
+    eng->launches += 7;
+    return HYD_OK;
+}
+
 HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, uint32_t n, uint8_t *d_out,
                                        uint64_t d_out_cap, uint64_t d_out_pos) {
     if (!eng || !tiles || !n || n > eng->max_batch || !d_out) {
@@ -402,46 +486,27 @@ HYDStatusCode hydb_engine_encode_tiles(HydbEngine *eng, const HydbTile *tiles, u
     }
     CK(cudaSetDevice(eng->device));
     cudaStream_t st = eng->st;
+    bool any_float = false;
     {
-        const HYDStatusCode rc = prepare_tiles(eng, tiles, n, st);
+        const HYDStatusCode rc = prepare_tiles(eng, tiles, n, st, nullptr, 0, nullptr, &any_float);
         if (rc != HYD_OK)
             return rc;
     }
     const bool tm = eng->timing;
-    if (tm) CK(cudaEventRecord(eng->tev[0], st));
-    launch_xyb_dct_quant(eng->ws, eng->luts, n, st);
-    if (tm) CK(cudaEventRecord(eng->tev[1], st));
-    CK(cudaEventRecord(eng->ev_front, st));
-    CK(cudaStreamWaitEvent(eng->st2, eng->ev_front, 0));
-    if (tm) CK(cudaEventRecord(eng->lev[0], eng->st2));
-    launch_lf_group(eng->ws, n, eng->st2);
-    if (tm) CK(cudaEventRecord(eng->lev[1], eng->st2));
-    CK(cudaEventRecord(eng->ev_lf, eng->st2));
-    launch_hf_tokens(eng->ws, n, st);
-    if (tm) CK(cudaEventRecord(eng->tev[2], st));
-    launch_ans_chain(eng->ws, n, st);
-    if (tm) CK(cudaEventRecord(eng->tev[3], st));
-    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));   // the LF stream is first needed by the packer
-    launch_ans_pack(eng->ws, eng->templ, n, st);
-    if (tm) CK(cudaEventRecord(eng->tev[4], st));
-    launch_gather(eng->ws, n, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
-    if (tm) CK(cudaEventRecord(eng->tev[5], st));
+    const HYDStatusCode rc = enqueue_tile_kernels(eng, eng->ws, n, st, eng->st2, eng->ev_front, eng->ev_lf, !any_float, d_out,
+                                                  d_out_cap, d_out_pos, eng->d_overflow, tm);
+    if (rc != HYD_OK)
+        return rc;
     eng->timed_pending = tm;
-    eng->launches += 7;
     return queue_readback(eng, n, d_out_pos);
 }
 
 // Frames of up to 8 x 8 groups.  A frame of one group is an ordinary tile; a larger one becomes a
 // prefix pseudo-tile plus its groups (k_frame.cu).
-HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames, uint32_t n, uint8_t *d_out,
-                                        uint64_t d_out_cap, uint64_t d_out_pos) {
-    if (!eng || !frames || !n || !d_out) {
-        if (eng) eng->error = "invalid arguments to hydb_engine_encode_frames";
-        return HYD_API_ERROR;
-    }
-    std::vector<HydbTile> tiles;
-    std::vector<SlotExtra> extra;
-    bool any_multi = false;
+// frames -> workspace slots (a frame of several groups = one prefix pseudo-tile + its groups)
+static HYDStatusCode expand_frames(HydbEngine *eng, const HydbFrame *frames, uint32_t n, std::vector<HydbTile> &tiles,
+                                   std::vector<SlotExtra> &extra, bool &any_multi) {
+    any_multi = false;
     for (uint32_t f = 0; f < n; f++) {
         const HydbFrame &fr = frames[f];
         if (!fr.width || !fr.height || fr.width > 2048 || fr.height > 2048 || (fr.x0 & 255) || (fr.y0 & 255) ||
@@ -517,6 +582,44 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
             extra.push_back(ge);
         }
     }
+    return HYD_OK;
+}
+
+// the kernel sequence of a batch that holds multi-group frames (k_frame.cu), descriptors in place
+static HYDStatusCode enqueue_frame_kernels(HydbEngine *eng, const Workspace &v, uint32_t slots, cudaStream_t st,
+                                           cudaStream_t st2, cudaEvent_t ev_front, cudaEvent_t ev_lf, bool allow_compact,
+                                           uint8_t *out, uint64_t out_cap, uint64_t out_pos, uint32_t *d_ovf) {
+    launch_xyb_dct_quant(v, eng->luts, slots, st);
+    CK(cudaEventRecord(ev_front, st));
+    CK(cudaStreamWaitEvent(st2, ev_front, 0));
+    launch_lf_group(v, slots, st2);   // classic single-group frames in the same batch
+    launch_frame_lf(v, slots, st2);
+    CK(cudaEventRecord(ev_lf, st2));
+    launch_hf_tokens(v, slots, st);
+    launch_frame_hist_sum(v, slots, st);
+    launch_ans_chain(v, slots, st, allow_compact);
+    CK(cudaStreamWaitEvent(st, ev_lf, 0));
+    launch_ans_pack(v, eng->templ, slots, st);
+    launch_frame_finish(v, slots, st);
+    launch_gather(v, slots, out, out_cap, out_pos, d_ovf, st);
+    eng->launches += 10;
+    return HYD_OK;
+}
+
+HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames, uint32_t n, uint8_t *d_out,
+                                        uint64_t d_out_cap, uint64_t d_out_pos) {
+    if (!eng || !frames || !n || !d_out) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_encode_frames";
+        return HYD_API_ERROR;
+    }
+    std::vector<HydbTile> tiles;
+    std::vector<SlotExtra> extra;
+    bool any_multi = false;
+    {
+        const HYDStatusCode rc = expand_frames(eng, frames, n, tiles, extra, any_multi);
+        if (rc != HYD_OK)
+            return rc;
+    }
     const uint32_t slots = (uint32_t)tiles.size();
     if (slots > eng->max_batch) {
         eng->error = "frames need more workspace slots than the engine's batch size";
@@ -526,35 +629,146 @@ HYDStatusCode hydb_engine_encode_frames(HydbEngine *eng, const HydbFrame *frames
         return hydb_engine_encode_tiles(eng, tiles.data(), slots, d_out, d_out_cap, d_out_pos);
     CK(cudaSetDevice(eng->device));
     cudaStream_t st = eng->st;
+    bool any_float = false;
     {
-        const HYDStatusCode rc = prepare_tiles(eng, tiles.data(), slots, st, extra.data());
+        const HYDStatusCode rc = prepare_tiles(eng, tiles.data(), slots, st, extra.data(), 0, nullptr, &any_float);
         if (rc != HYD_OK)
             return rc;
     }
-    launch_xyb_dct_quant(eng->ws, eng->luts, slots, st);
-    CK(cudaEventRecord(eng->ev_front, st));
-    CK(cudaStreamWaitEvent(eng->st2, eng->ev_front, 0));
-    launch_lf_group(eng->ws, slots, eng->st2);   // classic single-group frames in the same batch
-    launch_frame_lf(eng->ws, slots, eng->st2);
-    CK(cudaEventRecord(eng->ev_lf, eng->st2));
-    launch_hf_tokens(eng->ws, slots, st);
-    launch_frame_hist_sum(eng->ws, slots, st);
-    launch_ans_chain(eng->ws, slots, st);
-    CK(cudaStreamWaitEvent(st, eng->ev_lf, 0));
-    launch_ans_pack(eng->ws, eng->templ, slots, st);
-    launch_frame_finish(eng->ws, slots, st);
-    launch_gather(eng->ws, slots, d_out, d_out_cap, d_out_pos, eng->d_overflow, st);
+    const HYDStatusCode rc = enqueue_frame_kernels(eng, eng->ws, slots, st, eng->st2, eng->ev_front, eng->ev_lf, !any_float,
+                                                   d_out, d_out_cap, d_out_pos, eng->d_overflow);
+    if (rc != HYD_OK)
+        return rc;
     eng->timed_pending = false;
-    eng->launches += 10;
     return queue_readback(eng, slots, d_out_pos);
+}
+
+// ---- asynchronous jobs ---------------------------------------------------------------------------------
+// A job = n frames (or tiles) on workspace slots [slot0, slot0 + slots) with its own stream pair:
+// [h2d copy of the staged pixels] -> kernels -> gather straight into `out`, which may be page-locked
+// HOST memory (the compaction kernel then writes the codestream across PCIe itself and nothing is
+// copied back afterwards) -> k_job_result writes {bytes, error bits} into the job's page-locked record.
+// Several jobs run concurrently; the caller owns the slot ranges and polls jobs in any order.
+HYDStatusCode hydb_engine_submit_frames(HydbEngine *eng, const HydbFrame *frames, uint32_t n, uint32_t slot0,
+                                        const void *h_src, void *d_dst, size_t h2d_bytes, uint8_t *out, uint64_t out_cap,
+                                        uint32_t *job_out, uint32_t *slots_out) {
+    if (!eng || !frames || !n || !out || !job_out) {
+        if (eng) eng->error = "invalid arguments to hydb_engine_submit_frames";
+        return HYD_API_ERROR;
+    }
+    int j = -1;
+    for (int k = 0; k < HydbEngine::kJobs; k++)
+        if (!eng->jobs[k].busy) {
+            j = k;
+            break;
+        }
+    if (j < 0) {
+        eng->error = "no free job: poll and release a finished one first";
+        return HYD_API_ERROR;
+    }
+    std::vector<HydbTile> tiles;
+    std::vector<SlotExtra> extra;
+    bool any_multi = false;
+    {
+        const HYDStatusCode rc = expand_frames(eng, frames, n, tiles, extra, any_multi);
+        if (rc != HYD_OK)
+            return rc;
+    }
+    const uint32_t slots = (uint32_t)tiles.size();
+    if ((uint64_t)slot0 + slots > eng->max_batch) {
+        eng->error = "job exceeds the engine's workspace slots";
+        return HYD_API_ERROR;
+    }
+    CK(cudaSetDevice(eng->device));
+    HydbEngine::Job &jb = eng->jobs[j];
+    if (h_src && h2d_bytes)
+        CK(cudaMemcpyAsync(d_dst, h_src, h2d_bytes, cudaMemcpyHostToDevice, jb.st));
+    bool any_float = false;
+    {
+        const HYDStatusCode rc = prepare_tiles(eng, tiles.data(), slots, jb.st, extra.data(), slot0, jb.d_ovf, &any_float, true);
+        if (rc != HYD_OK)
+            return rc;
+    }
+    const Workspace v = ws_view(eng->ws, slot0);
+    const HYDStatusCode rc =
+        any_multi ? enqueue_frame_kernels(eng, v, slots, jb.st, jb.st2, jb.ev_front, jb.ev_lf, !any_float, out, out_cap, 0, jb.d_ovf)
+                  : enqueue_tile_kernels(eng, v, slots, jb.st, jb.st2, jb.ev_front, jb.ev_lf, !any_float, out, out_cap, 0, jb.d_ovf,
+                                         false);
+    if (rc != HYD_OK)
+        return rc;
+    launch_job_result(v.tile_err, slots, v.out_off + slots, jb.d_ovf, jb.h_res, jb.st);
+    eng->launches++;
+    CK(cudaEventRecord(jb.ev_done, jb.st));
+    CK(cudaGetLastError());
+    jb.busy = true;
+    jb.slot0 = slot0;
+    jb.n = slots;
+    *job_out = (uint32_t)j;
+    if (slots_out)
+        *slots_out = slots;
+    return HYD_OK;
+}
+
+// wait = 0: HYD_DEFAULT while the job is still running.  HYD_OK: *bytes were gathered.
+// HYD_NEED_MORE_OUTPUT: the frames did not fit `out` (hydb_engine_job_regather them into a larger buffer).
+// Errors of the job's tiles come back as HYD_INTERNAL_ERROR / HYD_API_ERROR with hydb_engine_error set.
+HYDStatusCode hydb_engine_job_poll(HydbEngine *eng, uint32_t job, int wait, uint64_t *bytes) {
+    if (!eng || job >= (uint32_t)HydbEngine::kJobs || !eng->jobs[job].busy)
+        return HYD_API_ERROR;
+    HydbEngine::Job &jb = eng->jobs[job];
+    if (wait) {
+        CK(cudaEventSynchronize(jb.ev_done));
+    } else {
+        const cudaError_t q = cudaEventQuery(jb.ev_done);
+        if (q == cudaErrorNotReady)
+            return HYD_DEFAULT;
+        CK(q);
+    }
+    const uint64_t res = reinterpret_cast<volatile uint64_t *>(jb.h_res)[1];
+    if (bytes)
+        *bytes = reinterpret_cast<volatile uint64_t *>(jb.h_res)[0];
+    const uint32_t err = (uint32_t)res & 0x7FFFFFFFu;
+    if (err) {
+        eng->error = tile_error_text(err);
+        return (err & kErrNonFinite) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
+    }
+    return (res >> 31) & 1u ? HYD_NEED_MORE_OUTPUT : HYD_OK;
+}
+
+// gather a finished job's frames again, into device memory, synchronously (after HYD_NEED_MORE_OUTPUT)
+HYDStatusCode hydb_engine_job_regather(HydbEngine *eng, uint32_t job, uint8_t *d_out, uint64_t d_out_cap, uint64_t *bytes) {
+    if (!eng || job >= (uint32_t)HydbEngine::kJobs || !eng->jobs[job].busy || !d_out || !bytes)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    HydbEngine::Job &jb = eng->jobs[job];
+    const Workspace v = ws_view(eng->ws, jb.slot0);
+    CK(cudaMemsetAsync(jb.d_ovf, 0, sizeof(uint32_t), jb.st));
+    launch_gather(v, jb.n, d_out, d_out_cap, 0, jb.d_ovf, jb.st);
+    launch_job_result(v.tile_err, jb.n, v.out_off + jb.n, jb.d_ovf, jb.h_res, jb.st);
+    eng->launches += 3;
+    CK(cudaStreamSynchronize(jb.st));
+    const uint64_t res = reinterpret_cast<volatile uint64_t *>(jb.h_res)[1];
+    *bytes = reinterpret_cast<volatile uint64_t *>(jb.h_res)[0];
+    if ((res >> 31) & 1u) {
+        eng->error = "device output buffer too small";
+        return HYD_NEED_MORE_OUTPUT;
+    }
+    return HYD_OK;
+}
+
+HYDStatusCode hydb_engine_job_release(HydbEngine *eng, uint32_t job) {
+    if (!eng || job >= (uint32_t)HydbEngine::kJobs)
+        return HYD_API_ERROR;
+    eng->jobs[job].busy = false;
+    return HYD_OK;
 }
 
 HYDStatusCode hydb_engine_read_model(HydbEngine *eng, uint32_t slot, uint32_t *bits_out, uint32_t *nbits,
                                      uint32_t *max_alphabet) {
-    if (!eng || !bits_out || !nbits || !max_alphabet || slot >= eng->last_n)
+    if (!eng || !bits_out || !nbits || !max_alphabet || slot >= eng->max_batch)
         return HYD_API_ERROR;
     CK(cudaSetDevice(eng->device));
-    CK(cudaStreamSynchronize(eng->st));
+    CK(cudaStreamSynchronize(eng->st));   // (jobs: the caller has polled the job that owns the slot)
     uint32_t meta = 0;
     std::vector<uint32_t> d(kDBitsWords);
     CK(cudaMemcpy(&meta, eng->ws.chain_out + (size_t)slot * 4 + 2, sizeof(meta), cudaMemcpyDeviceToHost));
@@ -707,6 +921,14 @@ HYDStatusCode hydb_engine_frame_lengths(HydbEngine *eng, uint32_t *dst, uint32_t
     CK(cudaSetDevice(eng->device));
     CK(cudaStreamSynchronize(eng->st));
     CK(cudaMemcpy(dst, eng->ws.frame_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return HYD_OK;
+}
+// the same for the slots of a finished job
+HYDStatusCode hydb_engine_slot_frame_lengths(HydbEngine *eng, uint32_t slot0, uint32_t *dst, uint32_t n) {
+    if (!eng || !dst || (uint64_t)slot0 + n > eng->max_batch)
+        return HYD_API_ERROR;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaMemcpy(dst, eng->ws.frame_len + slot0, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return HYD_OK;
 }
 

@@ -26,6 +26,7 @@
 // the step is bound by in-order issue of those instructions -- wide integer multiplies occupy the
 // multiply pipe for ~8 cycles each -- rather than by the load latency.
 #include "ans_chain.cuh"
+#include "chain_util.cuh"
 #include "headers.cuh"
 #include "kernels.h"
 #include "prefix_coder.cuh"
@@ -36,13 +37,6 @@ constexpr int kAnsThreads = 256;    // k_ans_chain
 constexpr int kPackThreads = 1024;  // k_ans_pack: one thread per ~3 chunks of 32 symbols, so its global loads overlap
 constexpr int kRing = 4;                 // batches in flight between the helper and the chain warp
 constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;   // named barrier ids (0 is __syncthreads)
-
-__device__ __forceinline__ void bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 struct AnsShared {
     uint16_t inv[kHfClusters * kAnsTotal];              // 73,728 B inverse alias table
@@ -142,27 +136,6 @@ __device__ __forceinline__ void block_scan2(uint32_t &a, uint32_t &b, uint32_t *
     a = ea;
     b = eb;
     __syncthreads();
-}
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
-    uint32_t v;
-    // volatile: keeps the table load of a chain step ahead of that step's record prefetch and state
-    // store in program order, so nothing queues in front of it in the shared-memory pipe
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
 }
 
 __global__ void __launch_bounds__(kAnsThreads)
@@ -692,7 +665,37 @@ k_ans_pack(Workspace ws, Templates tp) {
     }
 }
 
-void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st) {
+// HYDRIUM_B200_CHAIN=table|compact forces one kernel (tests, measurements).  Otherwise by launch size:
+// the table kernel runs 2 chains per SM at ~55 cycles per symbol, the compact kernel 16 per SM at
+// ~150 under full load (~90 when an SM holds few), i.e. twice the throughput but a longer critical
+// path.  With chain lengths spread by ~1.3x around their mean the two meet near 4.3 tiles per SM
+// (profiles/r02_config_shares_*.txt: 512 tiles 9.5 ms table / 10.9 ms compact, 8192 tiles 85 / 50 ms).
+static int chain_mode_override() {
+    static const int mode = [] {
+        const char *e = getenv("HYDRIUM_B200_CHAIN");
+        return !e ? 0 : (e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : 0));
+    }();
+    return mode;
+}
+static uint32_t chain_table_limit() {
+    static const uint32_t lim = [] {
+        const char *e = getenv("HYDRIUM_B200_CHAIN_TABLE_MAX");
+        if (e && atoi(e) > 0)
+            return (uint32_t)atoi(e);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return (uint32_t)(sms * 13 / 3);   // 641 tiles on a B200
+    }();
+    return lim;
+}
+
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact) {
+    const int mode = ws.chain_mode ? (int)ws.chain_mode : chain_mode_override();
+    if (allow_compact && (mode == 2 || (mode == 0 && ntiles > chain_table_limit()))) {
+        launch_ans_chain_compact(ws, ntiles, st);
+        return;
+    }
     cudaFuncSetAttribute(k_ans_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
     prefer_max_shared(k_ans_chain);
     k_ans_chain<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws);

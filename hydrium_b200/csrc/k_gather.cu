@@ -104,6 +104,31 @@ void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t 
     k_gather_frames<<<ntiles, 256, 0, st>>>(ws.slab, ws.frame_off, ws.frame_len, ws.out_off, out, out_cap, base, d_overflow);
 }
 
+// last kernel of an asynchronous job: {bytes gathered, OR of the tiles' error bits | overflow << 31} into
+// the job's page-locked host record (written by the device, read by the host once the job's event fired)
+__global__ void __launch_bounds__(256)
+k_job_result(const uint32_t *__restrict__ tile_err, uint32_t n, const uint64_t *__restrict__ total,
+             const uint32_t *__restrict__ overflow, uint64_t *__restrict__ h_res) {
+    __shared__ uint32_t s_err;
+    if (threadIdx.x == 0)
+        s_err = 0;
+    __syncthreads();
+    uint32_t e = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256)
+        e |= tile_err[i];
+    if (e)
+        atomicOr(&s_err, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        h_res[0] = *total;
+        h_res[1] = (uint64_t)((s_err & 0x7FFFFFFFu) | (*overflow ? 0x80000000u : 0u));
+    }
+}
+void launch_job_result(const uint32_t *tile_err, uint32_t n, const uint64_t *total, const uint32_t *overflow, uint64_t *h_res,
+                       cudaStream_t st) {
+    k_job_result<<<1, 256, 0, st>>>(tile_err, n, total, overflow, h_res);
+}
+
 // ---- multi-GPU gather over peer memory ------------------------------------------------------------
 // Every rank's k_gather_frames writes its span straight into its REGION of a buffer that lives on the
 // gathering rank (peer pointer over NVLink, opened with CUDA IPC): region r = [8-byte length, pad to

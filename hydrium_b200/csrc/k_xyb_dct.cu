@@ -255,6 +255,7 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     // thread (b, t): horizontal frequency kh = t, produces vertical frequencies kv = 0..7
     if (b < vbw) {
         const uint32_t kh = r;
+        bool in_range = true;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             float v[8], o[8];
@@ -277,17 +278,25 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
                 if (j == 0) {
                     // LF: trunc(dc * {8192, 1024, 512}) (encoder.c:573, 582)
                     const float scale = c == 0 ? 8192.f : (c == 1 ? 1024.f : 512.f);
-                    lfq[((size_t)tile * 3 + c) * kMaxBlocks + by * kBlocksPerRow + b] = __float2int_rz(__fmul_rn(o[kv], scale));
+                    const float lf = __fmul_rn(o[kv], scale);
+                    in_range = in_range && fabsf(lf) < 2147483648.0f;   // beyond it the reference's cast is undefined
+                    lfq[((size_t)tile * 3 + c) * kMaxBlocks + by * kBlocksPerRow + b] = __float2int_rz(lf);
                     qd[0] = 0;
                 } else {
                     // HF: trunc((f * w) * 5), dead zone |q| < 2 -> 0 (encoder.c:808-810)
                     int q = __float2int_rz(__fmul_rn(__fmul_rn(o[kv], s_w[c * 64 + j]), 5.0f));
                     if (q > -2 && q < 2)
                         q = 0;
+                    // the reference keeps 32 bits here (encoder.c:808); coefficients, residues and tokens
+                    // downstream are sized for 16 (every u8 / u16 image, floats within a few thousand of
+                    // [0, 1]).  Anything larger is refused loudly instead of wrapping.
+                    in_range = in_range && q >= -32768 && q <= 32767;
                     qd[j] = (int16_t)q;
                 }
             }
         }
+        if (!in_range)
+            atomicOr(&tile_err[tile], (uint32_t)kErrRange);
     } else {
         // blocks beyond the tile edge: keep the staging buffer defined
         for (int i = r; i < 3 * 64; i += 8)

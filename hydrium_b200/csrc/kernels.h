@@ -20,6 +20,7 @@ struct LutSet {
 // never need a global scan except for the final compaction.
 struct Workspace {
     uint32_t capacity;        // tiles
+    uint32_t chain_mode;      // 0 choose by launch size, 1 table kernel, 2 compact kernel (hydb_engine_set_chain_kernel)
     TileDesc *tiles;          // [T]
     int16_t *coef;            // [T][1024 blocks (row stride 32)][3 channels X,Y,B][64 scan order]
     uint16_t *nzinfo;         // [T][1024][3]  nz count | last scan index << 8
@@ -40,6 +41,7 @@ struct Workspace {
     uint64_t *out_off;        // [T+1] exclusive scan of frame_len (compaction offsets)
     uint32_t *tile_err;       // [T] TileError bits
     uint32_t *sm_ticket;      // [256] per-SM ticket counter (spreads chain warps over sub-partitions)
+    uint32_t *sm_load;        // [256][4] chain warps currently running per SM sub-partition (k_ans_chain_compact)
     // optional stage taps for the parity tests (NULL in production)
     float *dbg_xyb, *dbg_dct; // [T][256][256][3]
     uint32_t *dbg_freqs;      // [T][9][64] normalised frequencies
@@ -61,7 +63,11 @@ void launch_build_templates(const Templates &t, const uint32_t *d_shape_dims /*[
 void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st);
 void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
-void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
+// allow_compact: no HYD_FLOAT32 tile in the launch (tokens stay below 32); large launches then take
+// k_ans_chain_compact (sixteen chains per SM), small ones the table kernel (two per SM, shorter steps)
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact = true);
+void launch_ans_chain_compact(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
+int ans_compact_smem_bytes();
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
 // frames with several groups (k_frame.cu): shared ANS model, LFGroup section, frame prefix
 void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st);
@@ -78,6 +84,8 @@ void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H,
 // compaction: out[prefix_len + out_off[i] ...] = frame i ; total written to ws.out_off[ntiles]
 void launch_gather(const Workspace &ws, uint32_t ntiles, uint8_t *out, uint64_t out_cap, uint64_t base,
                    uint32_t *d_overflow, cudaStream_t st);
+void launch_job_result(const uint32_t *tile_err, uint32_t n, const uint64_t *total, const uint32_t *overflow, uint64_t *h_res,
+                       cudaStream_t st);
 // spans written by every rank into its region of a buffer on the gathering rank -> one contiguous stream
 void launch_compact_regions(const uint8_t *regions, uint32_t nregions, uint64_t region_stride, uint8_t *out, uint64_t out_cap,
                             uint64_t *d_total, uint32_t *d_overflow, cudaStream_t st);

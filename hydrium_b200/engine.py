@@ -94,6 +94,13 @@ class Engine:
             raise RuntimeError("D2H copy failed")
         return out.tobytes()
 
+    CHAIN_AUTO, CHAIN_TABLE, CHAIN_COMPACT = 0, 1, 2
+
+    def set_chain_kernel(self, mode: int) -> None:
+        """Which rANS chain kernel runs (hydb_engine_set_chain_kernel): by launch size, the table kernel,
+        or the compact-pieces kernel.  The bytes are the same."""
+        self._check(self.lib.hydb_engine_set_chain_kernel(self._h, mode))
+
     # -- encoding ------------------------------------------------------------------------
     def encode_image_device(self, d_pixels: int, width: int, height: int, channels: int = 3, *,
                             row_stride: int | None = None, sample_fmt: int = HYD_UINT8, linear_light: int = 0,

@@ -23,7 +23,7 @@ HYDB_SYMBOLS = (
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
     "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
     "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header", "hydb_ipc_export", "hydb_ipc_open", "hydb_ipc_close",
-    "hydb_engine_compact_regions", "hydb_engine_store_u64",
+    "hydb_engine_compact_regions", "hydb_engine_store_u64", "hydb_engine_set_chain_kernel",
 )
 
 
@@ -116,5 +116,7 @@ def load_library() -> C.CDLL:
     lib.hydb_engine_enable_timing.argtypes = [vp, C.c_int]
     lib.hydb_engine_stage_ms.restype = C.c_int
     lib.hydb_engine_stage_ms.argtypes = [vp, C.POINTER(C.c_double * 7)]
+    lib.hydb_engine_set_chain_kernel.restype = C.c_int
+    lib.hydb_engine_set_chain_kernel.argtypes = [vp, C.c_int]
     _lib = lib
     return lib

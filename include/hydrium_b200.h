@@ -137,6 +137,12 @@ HYDRIUM_EXPORT uint64_t hydb_engine_stream(const HydbEngine *engine);
 /* number of kernel launches issued by the engine so far */
 HYDRIUM_EXPORT uint64_t hydb_engine_launch_count(const HydbEngine *engine);
 
+/* Which rANS chain kernel the engine launches: 0 (default) = by launch size -- the table kernel (72 KB
+ * inverse alias table per tile, two chains per SM, shortest step) up to 2 x SM-count tiles per launch,
+ * the compact kernel (sorted alias pieces, sixteen chains per SM) beyond; 1 = always the table kernel;
+ * 2 = the compact kernel wherever it applies (integer sample formats).  Same bytes either way. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_set_chain_kernel(HydbEngine *engine, int mode);
+
 /* Encode n tiles (n <= max batch) and append their frames, in order, to d_out (device memory)
  * starting at byte d_out_pos.  Asynchronous on the engine stream; call hydb_engine_finish to
  * synchronise, collect per-tile errors and learn how many bytes the batch appended. */

@@ -86,6 +86,11 @@ uint32_t hh_lf_stream(const int32_t *lfq, uint32_t vbw, uint32_t vbh, uint32_t *
     return err;
 }
 
+// 1: hh_ans_encode runs the chain over the COMPACT inverse alias map (sorted pieces, 32 emulated lanes,
+// maximum of the lane candidates) the way k_ans_chain_compact does; 0: the direct table of k_ans_chain
+static int g_compact = 0;
+void hh_set_compact(int on) { g_compact = on; }
+
 // HF symbols (packed hf_pack records) -> normalised frequencies, section D bits, section E bits.
 // Mirrors what k_ans.cu does per tile, sequentially.
 uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[9][64]*/, uint32_t *alpha_out /*[9]*/,
@@ -154,12 +159,66 @@ uint32_t hh_ans_encode(const uint32_t *syms, uint32_t n, uint32_t *freqs_out /*[
         const uint8_t *inv_bytes = (const uint8_t *)&inv[0][0];
         auto info_of = [&](uint32_t p) -> const AnsSymInfo & { return info[hf_cluster(syms[p])][hf_token(syms[p])]; };
         AnsCarry carry;
+        if (g_compact) {
+            if (log_alpha != 5)
+                return kErrAlphabet;
+            static AnsPieceLane lanes[kHfClusters][32];
+            for (int c = 0; c < kHfClusters; c++) {
+                uint32_t lo[kAnsPieces];
+                int32_t delta[kAnsPieces];
+                uint64_t covered = 0;
+                for (uint32_t p = 0; p < (uint32_t)kAnsPieces; p++) {
+                    const uint32_t len = alpha[c] ? ans_piece(cl[c], p, lo[p], delta[p]) : 0u;
+                    if (!len)
+                        lo[p] = kAnsPieceNone;
+                    covered += len;
+                }
+                if (alpha[c] && covered != (uint64_t)kAnsTotal)
+                    return kErrAlias;
+                for (uint32_t p = 0; p < (uint32_t)kAnsPieces; p++) {
+                    const uint32_t rank = ans_piece_rank(lo, p), L = rank >> 1;
+                    uint32_t *pl = reinterpret_cast<uint32_t *>(&lanes[c][L]);
+                    pl[rank & 1u] = lo[p];
+                    pl[2u + (rank & 1u)] = (uint32_t)delta[p] + (L << 13);
+                }
+                // the pieces must reproduce the direct table everywhere
+                for (uint32_t g = 0; alpha[c] && g < (uint32_t)kAnsTotal; g++) {
+                    uint32_t best = 0;
+                    for (int L = 0; L < 32; L++) {
+                        const uint32_t cand = ans_piece_candidate(lanes[c][L], g);
+                        best = cand > best ? cand : best;
+                    }
+                    if ((best & 0xFFFu) != inv[c][g])
+                        return kErrAlias | 0x80000000u;
+                }
+            }
+            auto rec_of = [&](uint32_t p) {
+                const uint32_t c = hf_cluster(syms[p]), k = hf_token(syms[p]);
+                return ans_rec_c(cl[c].freq[k], cl[c].cum[k]);
+            };
+            ans_chain_begin_c(carry, rec_of(n - 1));
+            for (uint32_t r = 0; r < n; r++) {
+                const uint32_t p = n - 1 - r, c = hf_cluster(syms[p]);
+                const AnsRecC own = rec_of(p), nx = p ? rec_of(p - 1) : own;
+                ans_step_c(carry, own, p ? &nx : nullptr,
+                           [&](uint32_t g) {
+                               uint32_t best = 0;
+                               for (int L = 0; L < 32; L++) {
+                                   const uint32_t cand = ans_piece_candidate(lanes[c][L], g);
+                                   best = cand > best ? cand : best;
+                               }
+                               return best & 0xFFFu;
+                           },
+                           sprime[p]);
+            }
+        } else {
         ans_chain_begin(carry, info_of(n - 1), 0u);
         for (uint32_t r = 0; r < n; r++) {
             const uint32_t p = n - 1 - r;
             ans_step(carry, info_of(p), p ? &info_of(p - 1) : nullptr, 0u,
                      [inv_bytes](uint32_t off) { uint16_t v; memcpy(&v, inv_bytes + off, 2); return (uint32_t)v; },
                      sprime[p]);
+        }
         }
         x = sprime[0];   // the state left by the last step is final (no renormalisation follows)
         for (uint32_t p = n; p-- > 0;) {   // descending, like the chain emits them

@@ -112,6 +112,50 @@ def test_whole_images_device_and_host_paths(engine, oracle):
         assert engine.encode_image_host(img, linear_light=lin) == want, (name, "host path")
 
 
+def test_compact_chain_kernel(product_lib, oracle):
+    """k_ans_chain_compact (sorted alias pieces + warp-wide search, sixteen chains per SM) against the
+    oracle and against the table kernel: frequencies, section lengths and bytes, over the image set
+    (edge tiles, flat tiles, 16-bit linear), and on a launch large enough to fill every SM several times."""
+    rng = np.random.default_rng(5)
+    with E.Engine(device=0, max_batch_tiles=64) as eng:
+        eng.set_chain_kernel(E.Engine.CHAIN_COMPACT)
+        eng.enable_taps(True)
+        for name, img, lin in image_set(rng):
+            if img.dtype == np.float32:
+                continue   # float tiles always take the table kernel (tokens may pass 32)
+            want = oracle.encode_image(img, linear_light=lin)
+            assert eng.encode_image(img, linear_light=lin) == want, (name, "compact kernel")
+            st = Stages()
+            oracle.encode_tile(img, 0, 0, linear_light=lin, stages=st)
+            d_img, d_out = eng.upload(img), eng.device_alloc(1 << 20)
+            try:
+                eng.encode_tiles([_tile_desc(d_img, img, 0, 0, lin)], d_out, 1 << 20)
+                assert np.array_equal(eng.read_tap(E.TAP_FREQS, 0, np.uint32).reshape(9, 64), st.freqs[:, :64]), (name, "freqs")
+                sect = eng.read_tap(E.TAP_SECT, 0, np.uint32)
+                assert int(sect[0] + sect[1]) == st.pre_bitlen and int(sect[2]) == st.ans_bitlen, (name, "section lengths")
+            finally:
+                eng.device_free(d_img)
+                eng.device_free(d_out)
+    # 1280 tiles in one launch (four times what the table kernel keeps resident): both kernels and
+    # the automatic choice give the same bytes, and those are the oracle's
+    w, h = 8192, 10 * 256
+    outs = []
+    img = None
+    for mode in (E.Engine.CHAIN_TABLE, E.Engine.CHAIN_COMPACT, E.Engine.CHAIN_AUTO):
+        with E.Engine(device=0, max_batch_tiles=(w // 256) * (h // 256)) as eng:
+            eng.set_chain_kernel(mode)
+            d_in, cap = eng.device_alloc(w * h * 3), E.output_bound(w, h)
+            d_out = eng.device_alloc(cap)
+            eng.synth_fill(d_in, w, h, bits=8, seed=7)
+            outs.append(eng.download(d_out, eng.encode_image_device(d_in, w, h, 3, d_out=d_out, d_out_cap=cap)))
+            if img is None:
+                img = np.frombuffer(eng.download(d_in, w * h * 3), np.uint8).reshape(h, w, 3)
+            eng.device_free(d_in)
+            eng.device_free(d_out)
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[1] == oracle.encode_image(img)
+
+
 def test_batches_larger_than_the_workspace(product_lib, oracle):
     """An image with more tiles than max_batch_tiles goes through several launches."""
     img = synth_image(1300, 1100, 8, seed=2)   # 6 x 5 = 30 tiles

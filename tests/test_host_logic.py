@@ -96,7 +96,11 @@ def _encode_like_device(hh, st: Stages):
     return A, L, B, bits_of_words(d, dl.value), bits_of_words(e, el.value), fr
 
 
-def test_device_formulation_reproduces_oracle_payload(host_harness, oracle):
+@pytest.mark.parametrize("compact", [0, 1], ids=["table", "compact_pieces"])
+def test_device_formulation_reproduces_oracle_payload(host_harness, oracle, compact):
+    """compact = 1: the rANS chain runs over the sorted-piece form of the inverse alias map
+    (k_ans_chain_compact); the harness also checks the pieces against the direct table slot by slot."""
+    host_harness.hh_set_compact(compact)
     rng = np.random.default_rng(3)
     for name, img, lin in image_set(rng):
         h, w, _ = img.shape

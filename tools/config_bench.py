@@ -94,7 +94,9 @@ def config4(eng):
 
 
 which = sys.argv[1:] or ["3", "4", "5"]
-for batch in (256, 1024, 4096):
+batches = [int(b) for b in os.environ.get("CONFIG_BENCH_BATCHES", "256,1024,4096").split(",")]
+print(f"chain kernel: {os.environ.get('HYDRIUM_B200_CHAIN', 'auto')}", flush=True)
+for batch in batches:
     with E.Engine(device=0, max_batch_tiles=batch) as eng:
         for name, fn in (("3", config3), ("4", config4), ("5", config5)):
             if name not in which:
