@@ -291,10 +291,8 @@ int main(int argc, const char *argv[]) {
         fprintf(stderr, "%s: png error: %s\n", argv[0], error_msg);
         goto done;
     }
-    /* Tile mode: libhydrium_b200 encodes queued tiles in one GPU launch when asked to (the bytes still
-     * come out in send order through the same flush loop); other libhydrium builds ignore the variable */
-    if (!opt.one_frame)
-        setenv("HYDRIUM_B200_BATCH", "256", 0);
+    /* (libhydrium_b200 pipelines the tiles behind this loop by itself: hyd_send_tile stages and returns,
+     * finished bytes come out of the flush loops in send order, all of them by the one after the last tile) */
     enc = hyd_encoder_new();
     if (!enc) {
         fprintf(stderr, "%s: error allocating encoder\n", argv[0]);

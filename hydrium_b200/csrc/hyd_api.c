@@ -14,8 +14,13 @@
  *   - every byte (image header, frame header, TOC, payload) surfaces through hyd_flush, in send
  *     order; the reference writes the header fields straight into the lent buffer during
  *     hyd_send_tile.  The concatenation of all surfaced bytes is identical.
- *   - with hydb_encoder_set_batch(n > 1) tiles are encoded n at a time; hyd_flush then returns
- *     HYD_OK with nothing written until a batch completes.
+ *   - hyd_send_tile is asynchronous by default: it copies the tile into page-locked staging memory and
+ *     returns; tiles are encoded a chunk (32 tiles, or one multi-group frame) at a time by engine jobs
+ *     that run while the caller stages the next ones, and hyd_flush hands out whatever has finished, in
+ *     send order.  Everything is delivered by the end of the flush loop that follows the last tile
+ *     (libhydrium.c:147-166), or by a second consecutive hyd_flush.  hydb_encoder_set_batch(1) /
+ *     HYDRIUM_B200_BATCH=1 restores the reference's timing: every tile's bytes are ready when its
+ *     hyd_send_tile returns.  Float tiles are always encoded synchronously (error timing, format.c:123-126).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
@@ -27,10 +32,41 @@
 #include "../../include/hydrium_b200.h"
 
 #define TILE 256u
-/* worst-case staged bytes of one tile: 256 rows x 256 px x 4 samples x 2 bytes */
-#define TILE_STAGE_BYTES (256u * 256u * 4u * 4u) /* worst case: RGBA float */
-/* device output bytes reserved per queued tile (the engine reports overflow, never overruns) */
+/* device bytes reserved per workspace slot when a job's frames have to be gathered again (worst case) */
 #define TILE_OUT_BYTES (768u * 1024u)
+#define MAX_CHUNKS 8
+
+enum { CH_FREE = 0, CH_FILLING, CH_INFLIGHT, CH_DONE };
+
+typedef struct Chunk {
+    uint8_t *stage_host, *stage_dev, *out_host;
+    HydbFrame *frames;       /* [units] descriptors of what is staged (a classic tile = a frame of one group) */
+    uint32_t nframes;
+    size_t used;             /* staged bytes */
+    uint32_t slot0;          /* first engine workspace slot of this chunk */
+    int state;
+    uint32_t job, job_slots;
+    double t_submit;
+    /* one-frame mode over several LF groups: the chunk holds one LF group (frame part) */
+    int is_lf_part, closes_image;
+    uint32_t lfid, groups;
+} Chunk;
+
+typedef struct Seg {
+    uint8_t *heap;           /* owned block, or NULL when p points into a chunk's output area */
+    const uint8_t *p;
+    size_t len, pos;
+    int chunk;               /* chunk to recycle once consumed, -1 for heap blocks */
+} Seg;
+
+typedef struct Gpu {
+    int device;
+    uint32_t nchunks, units, slots_per_chunk;
+    size_t chunk_cap, out_cap;
+    HydbEngine *engine;
+    uint8_t *stage_host, *stage_dev, *out_host;
+    HydbFrame *frames;
+} Gpu;
 
 struct HYDEncoder {
     HYDImageMetadata metadata;
@@ -44,14 +80,15 @@ struct HYDEncoder {
     uint8_t *out;
     size_t out_len, out_pos;
 
-    /* bytes produced but not yet handed to the caller */
-    uint8_t *pend;
-    size_t pend_len, pend_cap, pend_pos;
+    /* bytes produced but not yet handed to the caller, in send order */
+    Seg *segs;
+    size_t seg_head, seg_tail, seg_cap;
 
     int wrote_header;
     int last_tile;
-
-    double stage_ms, batch_t0;   /* HYDRIUM_B200_APITRACE accounting */
+    int flush_idle;                 /* the previous call was a hyd_flush that had nothing more to give */
+    uint64_t tiles_sent, tiles_total;
+    HYDStatusCode async_rc;         /* first error of an asynchronous job: sticky */
 
     /* suggested ICC profile, already in the form the image header codes (libhydrium.c:242-305) */
     uint8_t *icc;
@@ -59,22 +96,19 @@ struct HYDEncoder {
 
     /* GPU side */
     int device;
-    uint32_t batch;
-    HydbEngine *engine;
-    uint32_t slots;        /* engine workspace slots: max(batch, 1 + groups_per_tile) */
-    size_t stage_cap;      /* bytes of each staging buffer */
-    uint8_t *stage_host;   /* page-locked */
-    uint8_t *stage_dev;
-    uint8_t *out_dev;      /* batch * TILE_OUT_BYTES */
-    HydbTile *tiles;
-    uint32_t queued;
-    size_t stage_used;
+    uint32_t batch;                 /* 0 = automatic chunks, 1 = synchronous per tile, n = chunks of n tiles */
+    uint32_t depth;                 /* chunks in flight (0 = default) */
+    uint32_t outcap_kb;             /* HYDRIUM_B200_OUTCAP_KB: output area per chunk (tests: forces the re-gather path) */
+    Gpu gpu;
+    Chunk chunks[MAX_CHUNKS];
+    int cur;                        /* chunk being filled, -1 = none */
+    uint64_t ring_head, ring_next;  /* oldest chunk not yet retired / next chunk to open (counters, index = % nchunks) */
     char errbuf[256];
 
     /* one-frame mode over several LF groups (encoder.c:752-1011): every hyd_send_tile encodes one
      * 2048x2048 LF group as a frame part; nothing surfaces until the last one (libhydrium.c:147-166) */
     uint32_t of_n, of_cx;           /* LF groups of the image, per row */
-    uint32_t of_nsent;
+    uint32_t of_nsent, of_nqueued;  /* parts collected / parts sent */
     uint32_t *of_sent;              /* raster id of the k-th LF group sent */
     uint8_t *of_seen;
     uint32_t *of_len1;              /* byte length of the k-th sent LFGroup section */
@@ -87,19 +121,9 @@ struct HYDEncoder {
     uint32_t of_max_alpha;
 };
 
-/* One engine + staging set is kept alive across encoders (creating the CUDA workspace and the
- * page-locked staging costs far more than encoding an image): hyd_encoder_destroy parks it here,
- * the next encoder with the same device / batch takes it back.  Distinct encoders may live on
- * different threads, hence the mutex. */
-static struct {
-    pthread_mutex_t lock;
-    int valid, device;
-    uint32_t batch, slots;
-    size_t stage_cap;
-    HydbEngine *engine;
-    uint8_t *stage_host, *stage_dev, *out_dev;
-    HydbTile *tiles;
-} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
+static HYDStatusCode chunk_submit(HYDEncoder *enc);
+static void release_gpu(HYDEncoder *enc);
+static void segs_clear(HYDEncoder *enc);
 
 static uint32_t env_u32(const char *name, uint32_t fallback) {
     const char *v = getenv(name);
@@ -118,40 +142,11 @@ HYDRIUM_EXPORT HYDEncoder *hyd_encoder_new(void) { /* libhydrium.c:16-19 */
     const char *dev = getenv("HYDRIUM_B200_DEVICE");
     if (dev && *dev)
         enc->device = atoi(dev);
-    enc->batch = env_u32("HYDRIUM_B200_BATCH", 1);
+    enc->batch = env_u32("HYDRIUM_B200_BATCH", 0);
+    enc->depth = env_u32("HYDRIUM_B200_DEPTH", 0);
+    enc->outcap_kb = env_u32("HYDRIUM_B200_OUTCAP_KB", 0);
+    enc->cur = -1;
     return enc;
-}
-
-static void release_gpu(HYDEncoder *enc) {
-    if (enc->engine && enc->stage_host && enc->stage_dev && enc->out_dev && enc->tiles) {
-        pthread_mutex_lock(&g_parked.lock);
-        if (!g_parked.valid) {
-            g_parked.valid = 1;
-            g_parked.device = enc->device;
-            g_parked.batch = enc->batch;
-            g_parked.slots = enc->slots;
-            g_parked.stage_cap = enc->stage_cap;
-            g_parked.engine = enc->engine;
-            g_parked.stage_host = enc->stage_host;
-            g_parked.stage_dev = enc->stage_dev;
-            g_parked.out_dev = enc->out_dev;
-            g_parked.tiles = enc->tiles;
-            enc->engine = NULL;
-            enc->stage_host = enc->stage_dev = enc->out_dev = NULL;
-            enc->tiles = NULL;
-        }
-        pthread_mutex_unlock(&g_parked.lock);
-    }
-    if (enc->stage_host) hydb_host_free(enc->stage_host);
-    if (enc->stage_dev) hydb_device_free(enc->stage_dev);
-    if (enc->out_dev) hydb_device_free(enc->out_dev);
-    if (enc->engine) hydb_engine_destroy(enc->engine);
-    free(enc->tiles);
-    enc->stage_host = enc->stage_dev = enc->out_dev = NULL;
-    enc->engine = NULL;
-    enc->tiles = NULL;
-    enc->queued = 0;
-    enc->stage_used = 0;
 }
 
 static void of_reset(HYDEncoder *enc) {
@@ -168,7 +163,7 @@ static void of_reset(HYDEncoder *enc) {
     enc->of_lf = NULL;
     enc->of_sent = enc->of_len1 = enc->of_elen = enc->of_hist = NULL;
     enc->of_seen = enc->of_e = NULL;
-    enc->of_n = enc->of_nsent = enc->of_ngroups = enc->of_elen_cap = enc->of_max_alpha = 0;
+    enc->of_n = enc->of_nsent = enc->of_nqueued = enc->of_ngroups = enc->of_elen_cap = enc->of_max_alpha = 0;
     enc->of_e_len = enc->of_e_cap = 0;
 }
 
@@ -176,7 +171,8 @@ HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydriu
     if (!enc)
         return HYD_OK;
     release_gpu(enc);
-    free(enc->pend);
+    segs_clear(enc);
+    free(enc->segs);
     free(enc->icc);
     of_reset(enc);
     free(enc);
@@ -184,7 +180,7 @@ HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydriu
 }
 
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *enc, uint32_t tiles) {
-    if (!enc || !tiles || tiles > 65536 || enc->engine) {
+    if (!enc || !tiles || tiles > 65536 || enc->tiles_sent) {
         if (enc)
             enc->error = "batch size must be set before the first tile";
         return HYD_API_ERROR;
@@ -194,7 +190,7 @@ HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *enc, uint32_t ti
 }
 
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_device(HYDEncoder *enc, int device) {
-    if (!enc || enc->engine) {
+    if (!enc || enc->tiles_sent) {
         if (enc)
             enc->error = "device must be set before the first tile";
         return HYD_API_ERROR;
@@ -252,6 +248,8 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_metadata(HYDEncoder *enc, const HYDImageMet
             return HYD_NOMEM;
         }
     }
+    enc->tiles_total = ((w + enc->tile_w - 1) / enc->tile_w) * ((h + enc->tile_h - 1) / enc->tile_h);
+    enc->tiles_sent = 0;
     enc->have_metadata = 1;
     return HYD_OK;
 }
@@ -284,26 +282,6 @@ HYDRIUM_EXPORT HYDStatusCode hyd_release_output_buffer(HYDEncoder *enc, size_t *
     *written = enc->out_pos;
     enc->out = NULL;
     return HYD_OK;
-}
-
-HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-166 */
-    if (enc->one_frame && !enc->last_tile)
-        return HYD_OK;
-    if (!enc->out) {
-        enc->error = "buffer was never provided";
-        return HYD_API_ERROR;
-    }
-    size_t n = enc->out_len - enc->out_pos;
-    if (n > enc->pend_len - enc->pend_pos)
-        n = enc->pend_len - enc->pend_pos;
-    memcpy(enc->out + enc->out_pos, enc->pend + enc->pend_pos, n);
-    enc->out_pos += n;
-    enc->pend_pos += n;
-    if (enc->pend_pos >= enc->pend_len) {
-        enc->pend_pos = enc->pend_len = 0;
-        return HYD_OK;
-    }
-    return HYD_NEED_MORE_OUTPUT;
 }
 
 HYDRIUM_EXPORT const char *hyd_error_message_get(HYDEncoder *enc) { return enc->error; } /* libhydrium.c:168-170 */
@@ -402,7 +380,7 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *enc, cons
     return HYD_OK;
 }
 
-/* HYDRIUM_B200_APITRACE=1: where a hyd_send_tile spends its time (stderr, milliseconds) */
+/* HYDRIUM_B200_APITRACE=1: what each retired chunk did (stderr, milliseconds) */
 static int api_trace(void) {
     static int on = -1;
     if (on < 0) {
@@ -417,239 +395,231 @@ static double now_ms(void) {
     return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
 }
 
-static HYDStatusCode pend_reserve(HYDEncoder *enc, size_t extra) {
-    if (enc->pend_len + extra <= enc->pend_cap)
-        return HYD_OK;
-    size_t cap = enc->pend_cap ? enc->pend_cap : 4096;
-    while (cap < enc->pend_len + extra)
-        cap *= 2;
-    uint8_t *p = realloc(enc->pend, cap);
-    if (!p)
-        return HYD_NOMEM;
-    enc->pend = p;
-    enc->pend_cap = cap;
+/* ---- the queue of produced bytes --------------------------------------------------------------------
+ * A segment is either a heap block (ICC image header, an assembled one-frame image, spilled or re-gathered
+ * output) or the page-locked output area of a finished chunk, which the GPU's compaction kernel filled
+ * directly; hyd_flush copies from the head of the queue into the caller's buffer. */
+static HYDStatusCode seg_push(HYDEncoder *enc, uint8_t *heap, const uint8_t *p, size_t len, int chunk) {
+    if (enc->seg_head == enc->seg_tail)
+        enc->seg_head = enc->seg_tail = 0;
+    if (enc->seg_tail == enc->seg_cap) {
+        if (enc->seg_head) {   /* slide down */
+            memmove(enc->segs, enc->segs + enc->seg_head, (enc->seg_tail - enc->seg_head) * sizeof(Seg));
+            enc->seg_tail -= enc->seg_head;
+            enc->seg_head = 0;
+        } else {
+            const size_t cap = enc->seg_cap ? enc->seg_cap * 2 : 32;
+            Seg *q = realloc(enc->segs, cap * sizeof(Seg));
+            if (!q) {
+                free(heap);
+                return HYD_NOMEM;
+            }
+            enc->segs = q;
+            enc->seg_cap = cap;
+        }
+    }
+    Seg *sg = &enc->segs[enc->seg_tail++];
+    sg->heap = heap;
+    sg->p = heap ? heap : p;
+    sg->len = len;
+    sg->pos = 0;
+    sg->chunk = chunk;
     return HYD_OK;
 }
 
+static void segs_clear(HYDEncoder *enc) {
+    for (size_t i = enc->seg_head; i < enc->seg_tail; i++)
+        free(enc->segs[i].heap);
+    enc->seg_head = enc->seg_tail = 0;
+}
+
 static HYDStatusCode gpu_error(HYDEncoder *enc, HYDStatusCode rc) {
-    const char *msg = enc->engine ? hydb_engine_error(enc->engine) : "CUDA engine unavailable";
+    const char *msg = enc->gpu.engine ? hydb_engine_error(enc->gpu.engine) : "CUDA engine unavailable";
     strncpy(enc->errbuf, msg, sizeof(enc->errbuf) - 1);
     enc->errbuf[sizeof(enc->errbuf) - 1] = 0;
     enc->error = enc->errbuf;
     return rc < HYD_ERROR_START ? rc : HYD_INTERNAL_ERROR;
 }
 
-static HYDStatusCode ensure_gpu(HYDEncoder *enc) {
-    if (enc->engine)
+/* ---- GPU resources: engine + chunk ring ---------------------------------------------------------------
+ * A chunk is what one asynchronous engine job works on: page-locked staging for the caller's pixels, its
+ * device twin, a page-locked output area and a range of workspace slots.  hyd_send_tile fills the current
+ * chunk and submits it when it is full (or holds the last tile); up to `nchunks` are in flight, so the
+ * staging copy of later tiles runs while the GPU encodes earlier ones, and hyd_flush only ever copies
+ * finished bytes.  One set is kept alive across encoders (creating the CUDA workspace and the page-locked
+ * memory costs far more than encoding an image): hyd_encoder_destroy parks it, the next encoder with the
+ * same geometry takes it back.  Distinct encoders may live on different threads, hence the mutex. */
+static struct {
+    pthread_mutex_t lock;
+    int valid;
+    Gpu gpu;
+} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, {0}};
+
+static void gpu_free(Gpu *g) {
+    if (g->stage_host) hydb_host_free(g->stage_host);
+    if (g->out_host) hydb_host_free(g->out_host);
+    if (g->stage_dev) hydb_device_free(g->stage_dev);
+    if (g->engine) hydb_engine_destroy(g->engine);
+    free(g->frames);
+    memset(g, 0, sizeof(*g));
+}
+
+static int gpu_same_shape(const Gpu *a, const Gpu *b) {
+    return a->device == b->device && a->nchunks == b->nchunks && a->units == b->units &&
+           a->slots_per_chunk == b->slots_per_chunk && a->chunk_cap == b->chunk_cap && a->out_cap == b->out_cap;
+}
+
+static HYDStatusCode retire(HYDEncoder *enc, int wait, int all);
+
+/* wait for everything in flight and move finished output out of the chunks (the ring may go away) */
+static HYDStatusCode drain_chunks(HYDEncoder *enc) {
+    if (!enc->gpu.engine)
         return HYD_OK;
+    HYDStatusCode rc = retire(enc, 1, 1);
+    for (size_t i = enc->seg_head; i < enc->seg_tail; i++) {
+        Seg *sg = &enc->segs[i];
+        if (sg->chunk >= 0) {
+            uint8_t *h = malloc(sg->len - sg->pos ? sg->len - sg->pos : 1);
+            if (!h)
+                return HYD_NOMEM;
+            memcpy(h, sg->p + sg->pos, sg->len - sg->pos);
+            enc->chunks[sg->chunk].state = CH_FREE;
+            sg->heap = h;
+            sg->p = h;
+            sg->len -= sg->pos;
+            sg->pos = 0;
+            sg->chunk = -1;
+        }
+    }
+    return rc;
+}
+
+static void release_gpu(HYDEncoder *enc) {
+    if (!enc->gpu.engine)
+        return;
+    /* kernels may still be reading the staging memory: let them finish; output nobody fetched is dropped */
+    for (uint32_t i = 0; i < enc->gpu.nchunks; i++) {
+        Chunk *c = &enc->chunks[i];
+        if (c->state == CH_INFLIGHT) {
+            uint64_t bytes = 0;
+            hydb_engine_job_poll(enc->gpu.engine, c->job, 1, &bytes);
+            hydb_engine_job_release(enc->gpu.engine, c->job);
+        }
+        c->state = CH_FREE;
+    }
     pthread_mutex_lock(&g_parked.lock);
-    enc->slots = enc->groups_per_tile > 1 && enc->batch < 1 + enc->groups_per_tile ? 1 + enc->groups_per_tile : enc->batch;
-    enc->stage_cap = (size_t)enc->batch * TILE_STAGE_BYTES;
-    if (enc->groups_per_tile > 1 && enc->stage_cap < (size_t)enc->tile_w * enc->tile_h * 16u)
-        enc->stage_cap = (size_t)enc->tile_w * enc->tile_h * 16u;   /* one whole tile, RGBA float */
-    HydbEngine *stale_engine = NULL;
-    uint8_t *stale_host = NULL, *stale_dev = NULL, *stale_out = NULL;
-    HydbTile *stale_tiles = NULL;
-    if (g_parked.valid && g_parked.device == enc->device && g_parked.batch == enc->batch &&
-        g_parked.slots == enc->slots && g_parked.stage_cap == enc->stage_cap) {
+    Gpu stale;
+    memset(&stale, 0, sizeof(stale));
+    if (g_parked.valid)
+        stale = g_parked.gpu;   /* the most recent geometry is the one most likely to come back */
+    g_parked.gpu = enc->gpu;
+    g_parked.valid = 1;
+    pthread_mutex_unlock(&g_parked.lock);
+    memset(&enc->gpu, 0, sizeof(enc->gpu));
+    gpu_free(&stale);
+    enc->cur = -1;
+    enc->ring_head = enc->ring_next = 0;
+}
+
+/* geometry for this encoder's tile shape and sample size */
+static void gpu_plan(const HYDEncoder *enc, size_t item, Gpu *g) {
+    memset(g, 0, sizeof(*g));
+    g->device = enc->device;
+    const uint32_t depth = enc->depth;
+    if (enc->groups_per_tile > 1 || enc->of_n) {
+        /* one frame of several groups per chunk */
+        const uint64_t W = enc->metadata.width, H = enc->metadata.height;
+        const uint64_t fw = W < enc->tile_w ? W : enc->tile_w, fh = H < enc->tile_h ? H : enc->tile_h;
+        g->units = 1;
+        g->slots_per_chunk = 1 + enc->groups_per_tile;
+        g->chunk_cap = (size_t)(fw * fh) * 4u * item + 4096;
+        g->out_cap = (size_t)g->slots_per_chunk * (128u << 10) + (256u << 10);
+        g->nchunks = enc->batch == 1 ? 1 : (depth ? depth : (g->chunk_cap > ((size_t)40 << 20) ? 2 : 4));
+    } else {
+        const uint32_t units = enc->batch ? enc->batch : 32u;
+        g->units = units;
+        g->slots_per_chunk = units;
+        g->chunk_cap = (size_t)units * TILE * TILE * 4u * item + 4096;
+        g->out_cap = (size_t)units * (160u << 10) + (64u << 10);
+        uint32_t n = enc->batch == 1 ? 1 : (depth ? depth : 8);
+        while (n > 2 && (uint64_t)n * units > 4096)
+            n--;
+        g->nchunks = n;
+    }
+    if (g->nchunks > MAX_CHUNKS)
+        g->nchunks = MAX_CHUNKS;
+    if (enc->outcap_kb)
+        g->out_cap = (size_t)enc->outcap_kb << 10;
+}
+
+static HYDStatusCode ensure_gpu(HYDEncoder *enc, size_t item) {
+    Gpu want;
+    gpu_plan(enc, item, &want);
+    if (enc->gpu.engine) {
+        /* hyd_set_metadata may be called again on a used encoder (the reference reallocates its group
+         * state then, libhydrium.c:79-100), and a caller may switch sample formats between tiles: when
+         * the live ring is too small in any dimension, finish what is in flight and rebuild it */
+        if (enc->gpu.device == want.device && enc->gpu.nchunks == want.nchunks && enc->gpu.units == want.units &&
+            enc->gpu.slots_per_chunk == want.slots_per_chunk && enc->gpu.chunk_cap >= want.chunk_cap &&
+            enc->gpu.out_cap >= want.out_cap)
+            return HYD_OK;
+        if (enc->cur >= 0 && enc->chunks[enc->cur].nframes) {
+            HYDStatusCode rc = chunk_submit(enc);
+            if (rc < HYD_ERROR_START)
+                return rc;
+        }
+        HYDStatusCode rc = drain_chunks(enc);
+        if (rc < HYD_ERROR_START)
+            return rc;
+        release_gpu(enc);
+    }
+    pthread_mutex_lock(&g_parked.lock);
+    Gpu stale;
+    memset(&stale, 0, sizeof(stale));
+    if (g_parked.valid) {
         g_parked.valid = 0;
-        enc->engine = g_parked.engine;
-        enc->stage_host = g_parked.stage_host;
-        enc->stage_dev = g_parked.stage_dev;
-        enc->out_dev = g_parked.out_dev;
-        enc->tiles = g_parked.tiles;
-    } else if (g_parked.valid) {
-        /* a parked set of another shape: drop it, so that the one created now can be parked in turn
-         * (the most recent geometry is the one most likely to come back) and its memory is returned */
-        g_parked.valid = 0;
-        stale_engine = g_parked.engine;
-        stale_host = g_parked.stage_host;
-        stale_dev = g_parked.stage_dev;
-        stale_out = g_parked.out_dev;
-        stale_tiles = g_parked.tiles;
+        if (gpu_same_shape(&g_parked.gpu, &want))
+            enc->gpu = g_parked.gpu;
+        else
+            stale = g_parked.gpu;
     }
     pthread_mutex_unlock(&g_parked.lock);
-    if (stale_engine) {
-        hydb_host_free(stale_host);
-        hydb_device_free(stale_dev);
-        hydb_device_free(stale_out);
-        hydb_engine_destroy(stale_engine);
-        free(stale_tiles);
-    }
-    if (enc->engine)
-        return HYD_OK;
-    HYDStatusCode rc = hydb_engine_create(&enc->engine, enc->device, enc->slots);
-    if (rc < HYD_ERROR_START) {
-        enc->error = "could not create the CUDA engine (no usable GPU? this encoder has no CPU path)";
-        return rc;
-    }
-    enc->stage_host = hydb_host_alloc(enc->stage_cap);
-    enc->stage_dev = hydb_device_alloc(enc->stage_cap);
-    enc->out_dev = hydb_device_alloc((size_t)enc->slots * TILE_OUT_BYTES);
-    enc->tiles = calloc(enc->slots, sizeof(HydbTile));
-    if (!enc->stage_host || !enc->stage_dev || !enc->out_dev || !enc->tiles) {
-        release_gpu(enc);
-        enc->error = "out of memory allocating tile staging";
-        return HYD_NOMEM;
-    }
-    return HYD_OK;
-}
-
-/* Device output -> the pending-output queue.  The queue is ordinary (pageable, growing) memory, and a
- * device-to-pageable copy runs at a fraction of PCIe speed; the page-locked staging buffer is idle once
- * the kernels have consumed the tile pixels, so the bytes take that way when they fit. */
-static int fetch_output(HYDEncoder *enc, size_t bytes) {
-    uint8_t *dst = enc->pend + enc->pend_len;
-    if (bytes <= enc->stage_cap) {
-        if (hydb_memcpy_d2h(enc->stage_host, enc->out_dev, bytes))
-            return -1;
-        memcpy(dst, enc->stage_host, bytes);
-        return 0;
-    }
-    return hydb_memcpy_d2h(dst, enc->out_dev, bytes);
-}
-
-/* encode everything queued and move the frames to the pending-output queue */
-/* ICC-tagged image: the image header (with the entropy-coded profile) goes out ahead of the first
- * frame, from its own kernel; the frame paths then run as if the header had been written already */
-static HYDStatusCode emit_icc_header(HYDEncoder *enc) {
-    const size_t cap = enc->icc_size * 3 + 16384;
-    HYDStatusCode rc = pend_reserve(enc, cap);
-    if (rc < HYD_ERROR_START)
-        return rc;
-    uint64_t len = 0;
-    rc = hydb_engine_icc_header(enc->engine, (uint32_t)enc->metadata.width, (uint32_t)enc->metadata.height, enc->icc,
-                                (uint32_t)enc->icc_size, enc->pend + enc->pend_len, cap, &len);
-    if (rc != HYD_OK)
-        return gpu_error(enc, rc);
-    enc->pend_len += (size_t)len;
-    enc->wrote_header = 1;
-    return HYD_OK;
-}
-
-static HYDStatusCode run_batch(HYDEncoder *enc) {
-    if (!enc->queued)
-        return HYD_OK;
-    const double t0 = now_ms();
-    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    const double t1 = now_ms();
-    HYDStatusCode rc = hydb_engine_encode_tiles(enc->engine, enc->tiles, enc->queued, enc->out_dev,
-                                                (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
-    if (rc < HYD_ERROR_START)
-        return gpu_error(enc, rc);
-    uint64_t bytes = 0;
-    rc = hydb_engine_finish(enc->engine, &bytes);
-    if (rc != HYD_OK)
-        return gpu_error(enc, rc);
-    const double t2 = now_ms();
-    rc = pend_reserve(enc, (size_t)bytes);
-    if (rc < HYD_ERROR_START)
-        return rc;
-    if (fetch_output(enc, (size_t)bytes))
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    if (api_trace()) {
-        fprintf(stderr, "[hydrium_b200] batch of %u tiles: staging %.2f (since the previous batch %.2f)  h2d %.2f  gpu %.2f  d2h %.2f ms\n",
-                enc->queued, enc->stage_ms, t0 - enc->batch_t0, t1 - t0, t2 - t1, now_ms() - t2);
-        enc->stage_ms = 0;
-        enc->batch_t0 = now_ms();
-    }
-    enc->pend_len += (size_t)bytes;
-    enc->queued = 0;
-    enc->stage_used = 0;
-    return HYD_OK;
-}
-
-/* copy one tile's samples into staging and fill its device-side descriptor */
-static void stage_pixels(HYDEncoder *enc, uint32_t w, uint32_t h, const void **plane, int64_t *out_row_stride,
-                         int64_t *out_pixel_stride, const void *const buffer[3], ptrdiff_t row_stride,
-                         ptrdiff_t pixel_stride, size_t item) {
-    struct { const void *plane[3]; int64_t row_stride, pixel_stride; } tt, *t = &tt;
-    uint8_t *dst = enc->stage_host + enc->stage_used;
-    uint8_t *ddst = enc->stage_dev + enc->stage_used;
-    const uint8_t *p[3] = {buffer[0], buffer[1], buffer[2]};
-    const uint8_t *lo = p[0] < p[1] ? (p[0] < p[2] ? p[0] : p[2]) : (p[1] < p[2] ? p[1] : p[2]);
-    const uint8_t *hi = p[0] > p[1] ? (p[0] > p[2] ? p[0] : p[2]) : (p[1] > p[2] ? p[1] : p[2]);
-    size_t used;
-    if (pixel_stride > 0 && pixel_stride <= 4 && (size_t)(hi - lo) < (size_t)pixel_stride * item) {
-        /* interleaved (RGB / RGBA ...): copy whole row spans, keep the caller's sample offsets */
-        const size_t span = (size_t)w * (size_t)pixel_stride * item;
-        for (uint32_t y = 0; y < h; y++)
-            memcpy(dst + (size_t)y * span, lo + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
-        for (int k = 0; k < 3; k++)
-            t->plane[k] = ddst + (p[k] - lo);
-        t->row_stride = (int64_t)w * pixel_stride;
-        t->pixel_stride = pixel_stride;
-        used = span * h;
-    } else if (pixel_stride == 1) {
-        /* planar: three contiguous planes */
-        const size_t span = (size_t)w * item;
-        for (int k = 0; k < 3; k++) {
-            uint8_t *pd = dst + (size_t)k * span * h;
-            for (uint32_t y = 0; y < h; y++)
-                memcpy(pd + (size_t)y * span, p[k] + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
-            t->plane[k] = ddst + (size_t)k * span * h;
+    gpu_free(&stale);
+    if (!enc->gpu.engine) {
+        enc->gpu = want;
+        Gpu *g = &enc->gpu;
+        HYDStatusCode rc = hydb_engine_create(&g->engine, g->device, g->nchunks * g->slots_per_chunk);
+        if (rc < HYD_ERROR_START) {
+            memset(g, 0, sizeof(*g));
+            enc->error = "could not create the CUDA engine (no usable GPU? this encoder has no CPU path)";
+            return rc;
         }
-        t->row_stride = w;
-        t->pixel_stride = 1;
-        used = 3 * span * h;
-    } else {
-        /* anything else: gather to packed RGB */
-        for (uint32_t y = 0; y < h; y++)
-            for (uint32_t x = 0; x < w; x++) {
-                const ptrdiff_t o = ((ptrdiff_t)y * row_stride + (ptrdiff_t)x * pixel_stride) * (ptrdiff_t)item;
-                uint8_t *q = dst + ((size_t)y * w + x) * 3 * item;
-                for (int k = 0; k < 3; k++)
-                    memcpy(q + k * item, p[k] + o, item);
-            }
-        for (int k = 0; k < 3; k++)
-            t->plane[k] = ddst + k * item;
-        t->row_stride = (int64_t)w * 3;
-        t->pixel_stride = 3;
-        used = (size_t)w * h * 3 * item;
+        g->stage_host = hydb_host_alloc(g->chunk_cap * g->nchunks);
+        g->stage_dev = hydb_device_alloc(g->chunk_cap * g->nchunks);
+        g->out_host = hydb_host_alloc(g->out_cap * g->nchunks);
+        g->frames = calloc((size_t)g->units * g->nchunks, sizeof(HydbFrame));
+        if (!g->stage_host || !g->stage_dev || !g->out_host || !g->frames) {
+            gpu_free(g);
+            enc->error = "out of memory allocating tile staging";
+            return HYD_NOMEM;
+        }
     }
-    enc->stage_used += (used + 255) & ~(size_t)255;
-    for (int k = 0; k < 3; k++)
-        plane[k] = tt.plane[k];
-    *out_row_stride = tt.row_stride;
-    *out_pixel_stride = tt.pixel_stride;
-}
-
-static void stage_tile(HYDEncoder *enc, HydbTile *t, const void *const buffer[3], ptrdiff_t row_stride,
-                       ptrdiff_t pixel_stride, size_t item) {
-    stage_pixels(enc, t->width, t->height, t->plane, &t->row_stride, &t->pixel_stride, buffer, row_stride, pixel_stride,
-                 item);
-}
-
-/* a tile of several 256x256 groups: one frame with shared sections (k_frame.cu), encoded at once */
-static HYDStatusCode run_frame(HYDEncoder *enc, HydbFrame *fr) {
-    const double t0 = now_ms();
-    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    const double t1 = now_ms();
-    HYDStatusCode rc = hydb_engine_encode_frames(enc->engine, fr, 1, enc->out_dev,
-                                                 (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
-    if (rc < HYD_ERROR_START)
-        return gpu_error(enc, rc);
-    const double t2 = now_ms();
-    uint64_t bytes = 0;
-    rc = hydb_engine_finish(enc->engine, &bytes);
-    if (rc != HYD_OK)
-        return gpu_error(enc, rc);
-    const double t3 = now_ms();
-    rc = pend_reserve(enc, (size_t)bytes);
-    if (rc < HYD_ERROR_START)
-        return rc;
-    if (fetch_output(enc, (size_t)bytes))
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    if (api_trace())
-        fprintf(stderr, "[hydrium_b200] frame %ux%u: h2d %.2f  launch %.2f  wait %.2f  d2h %.2f ms (%llu bytes)\n", fr->width,
-                fr->height, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, (unsigned long long)bytes);
-    enc->pend_len += (size_t)bytes;
-    enc->stage_used = 0;
+    for (uint32_t i = 0; i < enc->gpu.nchunks; i++) {
+        Chunk *c = &enc->chunks[i];
+        memset(c, 0, sizeof(*c));
+        c->stage_host = enc->gpu.stage_host + (size_t)i * enc->gpu.chunk_cap;
+        c->stage_dev = enc->gpu.stage_dev + (size_t)i * enc->gpu.chunk_cap;
+        c->out_host = enc->gpu.out_host + (size_t)i * enc->gpu.out_cap;
+        c->frames = enc->gpu.frames + (size_t)i * enc->gpu.units;
+        c->slot0 = i * enc->gpu.slots_per_chunk;
+        c->state = CH_FREE;
+    }
+    enc->cur = -1;
+    enc->ring_head = enc->ring_next = 0;
     return HYD_OK;
 }
 
+/* ---- one-frame mode over several LF groups: what a finished frame part leaves behind ------------------ */
 static uint32_t cllog2_u32(uint32_t v) {
     uint32_t n = 0;
     while ((1u << n) < v)
@@ -657,32 +627,10 @@ static uint32_t cllog2_u32(uint32_t v) {
     return n;
 }
 
-/* one LF group of a one-frame image with several of them: encode it as a frame part and keep what it
- * produced; when it is the last one, assemble the whole frame into the pending-output queue */
-static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) {
-    if (enc->of_seen[lfid] || enc->of_nsent >= enc->of_n) {
-        enc->error = "LF group sent twice in one-frame mode";
-        return HYD_API_ERROR;
-    }
-    const uint32_t G = ((fr->width + TILE - 1) / TILE) * ((fr->height + TILE - 1) / TILE);
-    fr->lf_part = 1;
-    fr->preset = lfid;
-    fr->preset_bits = cllog2_u32(enc->of_n);
-    fr->alpha_floor = enc->of_max_alpha;
-    fr->clusters_per_preset = enc->of_n * 9 <= 256 ? 9 : (enc->of_n * 3 <= 256 ? 3 : (enc->of_n * 2 <= 256 ? 2 : 1)); /* encoder.c:862-899 */
-    fr->with_image_header = 0;
-    if (hydb_memcpy_h2d(enc->stage_dev, enc->stage_host, enc->stage_used))
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    enc->stage_used = 0;
-    HYDStatusCode rc = hydb_engine_encode_frames(enc->engine, fr, 1, enc->out_dev, (uint64_t)enc->slots * TILE_OUT_BYTES, 0);
-    if (rc < HYD_ERROR_START)
-        return gpu_error(enc, rc);
-    uint64_t bytes = 0;
-    rc = hydb_engine_finish(enc->engine, &bytes);
-    if (rc != HYD_OK)
-        return gpu_error(enc, rc);
+static HYDStatusCode of_collect_part(HYDEncoder *enc, Chunk *c, const uint8_t *data, uint64_t bytes) {
+    const uint32_t G = c->groups, lfid = c->lfid;
     uint32_t lens[65];
-    rc = hydb_engine_frame_lengths(enc->engine, lens, 1 + G);
+    HYDStatusCode rc = hydb_engine_slot_frame_lengths(enc->gpu.engine, c->slot0, lens, 1 + G);
     if (rc != HYD_OK)
         return gpu_error(enc, rc);
     uint64_t sum = 0;
@@ -720,11 +668,8 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
         enc->of_elen = p;
         enc->of_elen_cap = cap;
     }
-    if (hydb_memcpy_d2h(lf, enc->out_dev, lens[0]) ||
-        hydb_memcpy_d2h(enc->of_e + enc->of_e_len, enc->out_dev + lens[0], (size_t)(bytes - lens[0]))) {
-        free(lf);
-        return gpu_error(enc, HYD_INTERNAL_ERROR);
-    }
+    memcpy(lf, data, lens[0]);
+    memcpy(enc->of_e + enc->of_e_len, data + lens[0], (size_t)(bytes - lens[0]));
     enc->of_lf[k] = lf;
     enc->of_len1[k] = lens[0];
     enc->of_e_len += (size_t)(bytes - lens[0]);
@@ -733,18 +678,18 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
     enc->of_ngroups += G;
     uint32_t *hist = enc->of_hist + (size_t)lfid * 385;
     uint32_t alpha = 0;
-    rc = hydb_engine_read_model(enc->engine, 1, hist + 1, &hist[0], &alpha);
+    rc = hydb_engine_read_model(enc->gpu.engine, c->slot0 + 1, hist + 1, &hist[0], &alpha);
     if (rc != HYD_OK)
         return gpu_error(enc, rc);
     if (alpha > enc->of_max_alpha)
         enc->of_max_alpha = alpha;
     enc->of_sent[k] = lfid;
-    enc->of_seen[lfid] = 1;
     enc->of_nsent = k + 1;
-    if (!enc->last_tile)
-        return HYD_OK;
+    return HYD_OK;
+}
 
-    /* last LF group: head and HFGlobal from the device, then  head | LFGroups | HFGlobal | PassGroups */
+/* every LF group is in: head and HFGlobal from the device, then  head | LFGroups | HFGlobal | PassGroups */
+static HYDStatusCode of_assemble(HYDEncoder *enc) {
     if (enc->of_nsent != enc->of_n) {
         enc->error = "one-frame mode: the last tile arrived before every LF group was sent";
         return HYD_API_ERROR;
@@ -780,7 +725,7 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
         }
     }
     uint32_t head_len = 0, hf_len = 0;
-    rc = hydb_oneframe_finish(enc->engine, info, (uint32_t)words, head, head_cap, &head_len, hf, hf_cap, &hf_len);
+    HYDStatusCode rc = hydb_oneframe_finish(enc->gpu.engine, info, (uint32_t)words, head, head_cap, &head_len, hf, hf_cap, &hf_len);
     free(info);
     if (rc != HYD_OK) {
         free(head); free(hf);
@@ -789,12 +734,12 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
     size_t total = (size_t)head_len + hf_len + enc->of_e_len;
     for (uint32_t i = 0; i < n; i++)
         total += enc->of_len1[i];
-    rc = pend_reserve(enc, total);
-    if (rc < HYD_ERROR_START) {
+    uint8_t *blk = malloc(total ? total : 1);
+    if (!blk) {
         free(head); free(hf);
-        return rc;
+        return HYD_NOMEM;
     }
-    uint8_t *d = enc->pend + enc->pend_len;
+    uint8_t *d = blk;
     memcpy(d, head, head_len);
     d += head_len;
     for (uint32_t i = 0; i < n; i++) {
@@ -804,10 +749,294 @@ static HYDStatusCode run_lf_part(HYDEncoder *enc, HydbFrame *fr, uint32_t lfid) 
     memcpy(d, hf, hf_len);
     d += hf_len;
     memcpy(d, enc->of_e, enc->of_e_len);
-    enc->pend_len += total;
     enc->wrote_header = 1;
     free(head);
     free(hf);
+    return seg_push(enc, blk, NULL, total, -1);
+}
+
+/* ---- chunk life cycle ------------------------------------------------------------------------------------ */
+static HYDStatusCode chunk_submit(HYDEncoder *enc) {
+    Chunk *c = &enc->chunks[enc->cur];
+    uint32_t job = 0, slots = 0;
+    c->t_submit = now_ms();
+    HYDStatusCode rc = hydb_engine_submit_frames(enc->gpu.engine, c->frames, c->nframes, c->slot0, c->stage_host, c->stage_dev,
+                                                 c->used, c->out_host, enc->gpu.out_cap, &job, &slots);
+    if (rc != HYD_OK)
+        return gpu_error(enc, rc);
+    c->job = job;
+    c->job_slots = slots;
+    c->state = CH_INFLIGHT;
+    enc->cur = -1;
+    return HYD_OK;
+}
+
+/* frames that did not fit the chunk's output area: gather them again into a device buffer sized for the
+ * worst case and fetch that (never seen with integer samples: the area holds 128+ KB per group) */
+static HYDStatusCode chunk_regather(HYDEncoder *enc, Chunk *c, uint8_t **blk, uint64_t *len) {
+    const size_t cap = (size_t)c->job_slots * TILE_OUT_BYTES;
+    uint8_t *d = hydb_device_alloc(cap);
+    if (!d)
+        return HYD_NOMEM;
+    uint64_t bytes = 0;
+    HYDStatusCode rc = hydb_engine_job_regather(enc->gpu.engine, c->job, d, cap, &bytes);
+    uint8_t *h = rc == HYD_OK ? malloc(bytes ? (size_t)bytes : 1) : NULL;
+    if (rc == HYD_OK && !h)
+        rc = HYD_NOMEM;
+    if (rc == HYD_OK && hydb_memcpy_d2h(h, d, (size_t)bytes))
+        rc = HYD_INTERNAL_ERROR;
+    hydb_device_free(d);
+    if (rc != HYD_OK) {
+        free(h);
+        return rc == HYD_NOMEM ? rc : gpu_error(enc, rc);
+    }
+    *blk = h;
+    *len = bytes;
+    return HYD_OK;
+}
+
+/* move finished chunks, oldest first, to the output queue.  wait: block for the oldest one in flight;
+ * all: keep going (and blocking, if wait) until nothing is in flight */
+static HYDStatusCode retire(HYDEncoder *enc, int wait, int all) {
+    while (enc->ring_head != enc->ring_next) {
+        Chunk *c = &enc->chunks[enc->ring_head % enc->gpu.nchunks];
+        if (c->state == CH_FILLING)
+            break;   /* the newest chunk, not submitted yet */
+        if (c->state != CH_INFLIGHT) {   /* done and queued (or consumed): nothing to do for it here */
+            enc->ring_head++;
+            continue;
+        }
+        uint64_t bytes = 0;
+        HYDStatusCode rc = hydb_engine_job_poll(enc->gpu.engine, c->job, wait, &bytes);
+        if (rc == HYD_DEFAULT)
+            return HYD_OK;   /* still running */
+        if (api_trace())
+            fprintf(stderr, "[hydrium_b200] chunk %u: %u frame(s), %zu bytes staged, %.2f ms from submit to retire, %llu bytes out\n",
+                    (unsigned)(enc->ring_head % enc->gpu.nchunks), c->nframes, c->used, now_ms() - c->t_submit, (unsigned long long)bytes);
+        uint8_t *blk = NULL;
+        if (rc < HYD_ERROR_START)
+            rc = gpu_error(enc, rc);   /* a tile of the job failed on the device: take the engine's message */
+        if (rc == HYD_NEED_MORE_OUTPUT) {
+            rc = chunk_regather(enc, c, &blk, &bytes);
+            if (rc == HYD_OK && !c->is_lf_part) {
+                rc = seg_push(enc, blk, NULL, (size_t)bytes, -1);
+                blk = NULL;
+                hydb_engine_job_release(enc->gpu.engine, c->job);
+                c->state = CH_FREE;
+                enc->ring_head++;
+                if (rc < HYD_ERROR_START) {
+                    enc->async_rc = rc;
+                    return rc;
+                }
+                if (!all)
+                    wait = 0;
+                continue;
+            }
+        }
+        if (rc == HYD_OK && c->is_lf_part) {
+            rc = of_collect_part(enc, c, blk ? blk : c->out_host, bytes);
+            free(blk);
+            hydb_engine_job_release(enc->gpu.engine, c->job);
+            c->state = CH_FREE;
+            if (rc == HYD_OK && c->closes_image)
+                rc = of_assemble(enc);
+        } else if (rc == HYD_OK) {
+            hydb_engine_job_release(enc->gpu.engine, c->job);
+            c->state = CH_DONE;
+            rc = seg_push(enc, NULL, c->out_host, (size_t)bytes, (int)(enc->ring_head % enc->gpu.nchunks));
+        } else {
+            free(blk);
+            hydb_engine_job_release(enc->gpu.engine, c->job);
+            c->state = CH_FREE;
+            if (rc >= HYD_ERROR_START) {
+                enc->error = "internal: unexpected job status";
+                rc = HYD_INTERNAL_ERROR;
+            }
+        }
+        enc->ring_head++;
+        if (rc < HYD_ERROR_START) {
+            enc->async_rc = rc;
+            return rc;
+        }
+        if (!all)
+            wait = 0;   /* one blocking retirement was asked for; take whatever else is ready */
+    }
+    return HYD_OK;
+}
+
+/* the chunk tiles are staged into; NULL with *rc set on failure */
+static Chunk *chunk_current(HYDEncoder *enc, HYDStatusCode *rc) {
+    *rc = HYD_OK;
+    if (enc->cur >= 0)
+        return &enc->chunks[enc->cur];
+    const uint32_t idx = enc->ring_next % enc->gpu.nchunks;
+    Chunk *c = &enc->chunks[idx];
+    if (c->state == CH_INFLIGHT) {   /* the ring is full: wait for the oldest job */
+        *rc = retire(enc, 1, 0);
+        if (*rc < HYD_ERROR_START)
+            return NULL;
+    }
+    if (c->state == CH_DONE) {
+        /* finished but not yet fetched by the caller: move its bytes to the heap so the chunk can go round */
+        for (size_t i = enc->seg_head; i < enc->seg_tail; i++) {
+            Seg *sg = &enc->segs[i];
+            if (sg->chunk == (int)idx) {
+                uint8_t *h = malloc(sg->len - sg->pos ? sg->len - sg->pos : 1);
+                if (!h) {
+                    *rc = HYD_NOMEM;
+                    return NULL;
+                }
+                memcpy(h, sg->p + sg->pos, sg->len - sg->pos);
+                sg->heap = h;
+                sg->p = h;
+                sg->len -= sg->pos;
+                sg->pos = 0;
+                sg->chunk = -1;
+            }
+        }
+        c->state = CH_FREE;
+    }
+    if (c->state != CH_FREE) {
+        enc->error = "internal: chunk ring out of order";
+        *rc = HYD_INTERNAL_ERROR;
+        return NULL;
+    }
+    uint8_t *sh = c->stage_host, *sd = c->stage_dev, *oh = c->out_host;
+    HydbFrame *fr = c->frames;
+    const uint32_t slot0 = c->slot0;
+    memset(c, 0, sizeof(*c));
+    c->stage_host = sh;
+    c->stage_dev = sd;
+    c->out_host = oh;
+    c->frames = fr;
+    c->slot0 = slot0;
+    c->state = CH_FILLING;
+    enc->cur = (int)idx;
+    enc->ring_next++;
+    return c;
+}
+
+/* copy one tile's samples into the chunk's staging memory; plane[] / strides describe the staged copy in
+ * DEVICE memory.  Returns 0 when the tile does not fit the chunk. */
+static int stage_pixels(HYDEncoder *enc, Chunk *c, uint32_t w, uint32_t h, const void **plane, int64_t *out_row_stride,
+                        int64_t *out_pixel_stride, const void *const buffer[3], ptrdiff_t row_stride,
+                        ptrdiff_t pixel_stride, size_t item) {
+    uint8_t *dst = c->stage_host + c->used;
+    uint8_t *ddst = c->stage_dev + c->used;
+    const size_t room = enc->gpu.chunk_cap - c->used;
+    const uint8_t *p[3] = {buffer[0], buffer[1], buffer[2]};
+    const uint8_t *lo = p[0] < p[1] ? (p[0] < p[2] ? p[0] : p[2]) : (p[1] < p[2] ? p[1] : p[2]);
+    const uint8_t *hi = p[0] > p[1] ? (p[0] > p[2] ? p[0] : p[2]) : (p[1] > p[2] ? p[1] : p[2]);
+    size_t used;
+    if (pixel_stride > 0 && pixel_stride <= 4 && (size_t)(hi - lo) < (size_t)pixel_stride * item) {
+        /* interleaved (RGB / RGBA / ARGB ...): copy row spans from the lowest addressed sample to the
+         * highest one of the row's last pixel -- never past it, the caller's buffer may end there */
+        const size_t span = (size_t)w * (size_t)pixel_stride * item;
+        const size_t need = (size_t)(w - 1) * (size_t)pixel_stride * item + (size_t)(hi - lo) + item;
+        if (span * h > room)
+            return 0;
+        for (uint32_t y = 0; y < h; y++)
+            memcpy(dst + (size_t)y * span, lo + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, need);
+        for (int k = 0; k < 3; k++)
+            plane[k] = ddst + (p[k] - lo);
+        *out_row_stride = (int64_t)w * pixel_stride;
+        *out_pixel_stride = pixel_stride;
+        used = span * h;
+    } else if (pixel_stride == 1) {
+        /* planar: three contiguous planes */
+        const size_t span = (size_t)w * item;
+        if (3 * span * h > room)
+            return 0;
+        for (int k = 0; k < 3; k++) {
+            uint8_t *pd = dst + (size_t)k * span * h;
+            for (uint32_t y = 0; y < h; y++)
+                memcpy(pd + (size_t)y * span, p[k] + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
+            plane[k] = ddst + (size_t)k * span * h;
+        }
+        *out_row_stride = w;
+        *out_pixel_stride = 1;
+        used = 3 * span * h;
+    } else {
+        /* anything else: gather to packed RGB */
+        if ((size_t)w * h * 3 * item > room)
+            return 0;
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                const ptrdiff_t o = ((ptrdiff_t)y * row_stride + (ptrdiff_t)x * pixel_stride) * (ptrdiff_t)item;
+                uint8_t *q = dst + ((size_t)y * w + x) * 3 * item;
+                for (int k = 0; k < 3; k++)
+                    memcpy(q + k * item, p[k] + o, item);
+            }
+        for (int k = 0; k < 3; k++)
+            plane[k] = ddst + k * item;
+        *out_row_stride = (int64_t)w * 3;
+        *out_pixel_stride = 3;
+        used = (size_t)w * h * 3 * item;
+    }
+    c->used += (used + 255) & ~(size_t)255;
+    return 1;
+}
+
+/* ICC-tagged image: the image header (with the entropy-coded profile) goes out ahead of the first
+ * frame, from its own kernel; the frame paths then run as if the header had been written already */
+static HYDStatusCode emit_icc_header(HYDEncoder *enc) {
+    const size_t cap = enc->icc_size * 3 + 16384;
+    uint8_t *blk = malloc(cap);
+    if (!blk)
+        return HYD_NOMEM;
+    uint64_t len = 0;
+    HYDStatusCode rc = hydb_engine_icc_header(enc->gpu.engine, (uint32_t)enc->metadata.width, (uint32_t)enc->metadata.height,
+                                              enc->icc, (uint32_t)enc->icc_size, blk, cap, &len);
+    if (rc != HYD_OK) {
+        free(blk);
+        return gpu_error(enc, rc);
+    }
+    enc->wrote_header = 1;
+    return seg_push(enc, blk, NULL, (size_t)len, -1);
+}
+
+HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-166 */
+    if (enc->one_frame && !enc->last_tile)
+        return HYD_OK;
+    if (!enc->out) {
+        enc->error = "buffer was never provided";
+        return HYD_API_ERROR;
+    }
+    if (enc->async_rc < HYD_ERROR_START)
+        return enc->async_rc;
+    if (enc->gpu.engine) {
+        /* Everything is due once the last tile is in (libhydrium.c:147-166: the caller's flush loop after
+         * the last tile must surface the whole image), or when the caller asks again right after a flush
+         * that had nothing more to give: no reference caller does that while it is still sending tiles, so
+         * it means "I am done" -- tile subsets without an is_last are legal (libhydrium.h:235-240). */
+        const int drain = enc->last_tile || enc->flush_idle;
+        if (drain && enc->cur >= 0 && enc->chunks[enc->cur].nframes) {
+            HYDStatusCode rc = chunk_submit(enc);
+            if (rc < HYD_ERROR_START)
+                return rc;
+        }
+        HYDStatusCode rc = retire(enc, drain, drain);
+        if (rc < HYD_ERROR_START)
+            return rc;
+    }
+    while (enc->seg_head < enc->seg_tail && enc->out_pos < enc->out_len) {
+        Seg *sg = &enc->segs[enc->seg_head];
+        size_t n = enc->out_len - enc->out_pos;
+        if (n > sg->len - sg->pos)
+            n = sg->len - sg->pos;
+        memcpy(enc->out + enc->out_pos, sg->p + sg->pos, n);
+        enc->out_pos += n;
+        sg->pos += n;
+        if (sg->pos < sg->len)
+            break;
+        free(sg->heap);
+        if (sg->chunk >= 0)
+            enc->chunks[sg->chunk].state = CH_FREE;
+        enc->seg_head++;
+    }
+    if (enc->seg_head < enc->seg_tail)
+        return HYD_NEED_MORE_OUTPUT;
+    enc->flush_idle = 1;
     return HYD_OK;
 }
 
@@ -830,9 +1059,13 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
         enc->error = "tile out of bounds";
         return HYD_API_ERROR;
     }
-    HYDStatusCode rc = ensure_gpu(enc);
+    if (enc->async_rc < HYD_ERROR_START)
+        return enc->async_rc;   /* a tile sent earlier failed on the device: the encoder is unusable, like the reference's */
+    const size_t item = sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4);
+    HYDStatusCode rc = ensure_gpu(enc, item);
     if (rc < HYD_ERROR_START)
         return rc;
+    enc->flush_idle = 0;
     if (enc->icc && !enc->wrote_header) { /* encoder.c:490-494 with encoder.c:203-236 */
         rc = emit_icc_header(enc);
         if (rc < HYD_ERROR_START)
@@ -842,78 +1075,88 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
     const uint32_t th = (uint32_t)(((uint64_t)tile_y + 1) * span_y > H ? H - (uint64_t)tile_y * span_y : span_y);
     /* encoder.c:482-485 */
     enc->last_tile = is_last < 0 ? (((uint64_t)tile_x + 1) * span_x >= W && ((uint64_t)tile_y + 1) * span_y >= H) : !!is_last;
-    const size_t item = sample_fmt == HYD_UINT8 ? 1 : (sample_fmt == HYD_UINT16 ? 2 : 4);
+    const uint32_t lfid = enc->of_n ? tile_y * enc->of_cx + tile_x : 0;
+    if (enc->of_n && (enc->of_seen[lfid] || enc->of_nqueued >= enc->of_n)) {
+        enc->error = "LF group sent twice in one-frame mode";
+        return HYD_API_ERROR;
+    }
+
+    Chunk *c = chunk_current(enc, &rc);
+    if (!c)
+        return rc;
+    HydbFrame *fr = &c->frames[c->nframes];
+    memset(fr, 0, sizeof(*fr));
+    if (!stage_pixels(enc, c, tw, th, fr->plane, &fr->row_stride, &fr->pixel_stride, buffer, row_stride, pixel_stride, item)) {
+        /* the chunk is full in bytes before it is full in tiles (wider samples than it was sized for are
+         * handled by ensure_gpu; this is a mix of layouts): send it off and start the next one */
+        if (!c->nframes) {
+            enc->error = "internal: tile does not fit an empty staging chunk";
+            return HYD_INTERNAL_ERROR;
+        }
+        rc = chunk_submit(enc);
+        if (rc < HYD_ERROR_START)
+            return rc;
+        c = chunk_current(enc, &rc);
+        if (!c)
+            return rc;
+        fr = &c->frames[c->nframes];
+        memset(fr, 0, sizeof(*fr));
+        if (!stage_pixels(enc, c, tw, th, fr->plane, &fr->row_stride, &fr->pixel_stride, buffer, row_stride, pixel_stride, item)) {
+            enc->error = "internal: tile does not fit an empty staging chunk";
+            return HYD_INTERNAL_ERROR;
+        }
+    }
+    fr->width = tw;
+    fr->height = th;
+    fr->x0 = tile_x * enc->tile_w;
+    fr->y0 = tile_y * enc->tile_h;
+    fr->image_width = (uint32_t)W;
+    fr->image_height = (uint32_t)H;
+    fr->sample_fmt = sample_fmt;
+    fr->linear_light = enc->metadata.linear_light != 0;
+    fr->one_frame = enc->one_frame;
     if (enc->of_n) {
-        /* one-frame mode over several LF groups: this tile is LF group (tile_x, tile_y) */
-        HydbFrame fr;
-        memset(&fr, 0, sizeof(fr));
-        fr.width = tw;
-        fr.height = th;
-        fr.x0 = tile_x * enc->tile_w;
-        fr.y0 = tile_y * enc->tile_h;
-        fr.image_width = (uint32_t)W;
-        fr.image_height = (uint32_t)H;
-        fr.is_last = 1;
-        fr.sample_fmt = sample_fmt;
-        fr.linear_light = enc->metadata.linear_light != 0;
-        fr.one_frame = 1;
-        stage_pixels(enc, tw, th, fr.plane, &fr.row_stride, &fr.pixel_stride, buffer, row_stride, pixel_stride, item);
-        return run_lf_part(enc, &fr, tile_y * enc->of_cx + tile_x);
-    }
-    if (tw > TILE || th > TILE) {
-        /* several groups in this frame: everything queued so far goes first, then the frame at once */
-        rc = run_batch(enc);
-        if (rc < HYD_ERROR_START)
-            return rc;
-        HydbFrame fr;
-        memset(&fr, 0, sizeof(fr));
-        fr.width = tw;
-        fr.height = th;
-        fr.x0 = tile_x * enc->tile_w;
-        fr.y0 = tile_y * enc->tile_h;
-        fr.image_width = (uint32_t)W;
-        fr.image_height = (uint32_t)H;
-        fr.is_last = enc->one_frame || enc->last_tile;
-        fr.sample_fmt = sample_fmt;
-        fr.linear_light = enc->metadata.linear_light != 0;
-        fr.with_image_header = !enc->wrote_header;
-        fr.one_frame = enc->one_frame;
-        enc->wrote_header = 1;
-        const double ts = now_ms();
-        stage_pixels(enc, tw, th, fr.plane, &fr.row_stride, &fr.pixel_stride, buffer, row_stride, pixel_stride, item);
-        if (api_trace())
-            fprintf(stderr, "[hydrium_b200] staging %.2f ms\n", now_ms() - ts);
-        return run_frame(enc, &fr);
-    }
-
-    HydbTile *t = &enc->tiles[enc->queued];
-    memset(t, 0, sizeof(*t));
-    t->width = tw;
-    t->height = th;
-    t->x0 = tile_x * enc->tile_w;
-    t->y0 = tile_y * enc->tile_h;
-    t->image_width = (uint32_t)W;
-    t->image_height = (uint32_t)H;
-    t->is_last = enc->one_frame || enc->last_tile; /* encoder.c:339 */
-    t->sample_fmt = sample_fmt;
-    t->linear_light = enc->metadata.linear_light != 0;
-    t->with_image_header = !enc->wrote_header; /* encoder.c:490-494: the image header precedes the first frame */
-    enc->wrote_header = 1;
-    if (api_trace()) {
-        const double ts = now_ms();
-        if (!enc->queued && enc->batch_t0 == 0)
-            enc->batch_t0 = ts;
-        stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
-        enc->stage_ms += now_ms() - ts;
+        /* one-frame mode over several LF groups: this tile is LF group (tile_x, tile_y), encoded as a
+         * frame part; nothing surfaces until the last one (libhydrium.c:147-166) */
+        fr->is_last = 1;
+        fr->lf_part = 1;
+        fr->preset = lfid;
+        fr->preset_bits = cllog2_u32(enc->of_n);
+        /* the running maximum of the token alphabets (entropy.c:459, 952) only matters beyond 32 tokens,
+         * which integer samples never reach; float parts are encoded one at a time (below), so the value
+         * is exact whenever it can matter */
+        fr->alpha_floor = enc->of_max_alpha;
+        fr->clusters_per_preset = enc->of_n * 9 <= 256 ? 9 : (enc->of_n * 3 <= 256 ? 3 : (enc->of_n * 2 <= 256 ? 2 : 1)); /* encoder.c:862-899 */
+        c->is_lf_part = 1;
+        c->lfid = lfid;
+        c->groups = ((tw + TILE - 1) / TILE) * ((th + TILE - 1) / TILE);
+        c->closes_image = enc->last_tile;
+        enc->of_seen[lfid] = 1;
+        enc->of_nqueued++;
     } else {
-        stage_tile(enc, t, buffer, row_stride, pixel_stride, item);
+        fr->is_last = enc->one_frame || enc->last_tile; /* encoder.c:339 */
+        fr->with_image_header = !enc->wrote_header;     /* encoder.c:490-494: the image header precedes the first frame */
+        enc->wrote_header = 1;
     }
-    enc->queued++;
+    c->nframes++;
+    enc->tiles_sent++;
+    /* every tile of the image has been sent once: whatever is_last said, nothing more can follow */
+    const int image_complete = !enc->one_frame && enc->tiles_sent >= enc->tiles_total;
+    if (image_complete)
+        enc->last_tile = enc->last_tile || 1;
 
-    if (enc->queued == enc->batch || enc->last_tile) {
-        rc = run_batch(enc);
+    const int sync = enc->batch == 1 || sample_fmt == HYD_FLOAT32;
+    if (c->nframes == enc->gpu.units || enc->last_tile || sync) {
+        rc = chunk_submit(enc);
         if (rc < HYD_ERROR_START)
             return rc;
+        if (sync) {
+            /* strict mode (hydb_encoder_set_batch(1)) and float samples: the tile is encoded before the call
+             * returns, errors included ("Invalid NaN Float", format.c:123-126), exactly like the reference */
+            rc = retire(enc, 1, 1);
+            if (rc < HYD_ERROR_START)
+                return rc;
+        }
     }
     return HYD_OK; /* never HYD_NEED_MORE_OUTPUT, like the reference (libhydrium.c:195-202) */
 }

@@ -115,7 +115,8 @@ def tile_grid(width: int, height: int, shift_x: int, shift_y: int) -> tuple[int,
 
 def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, shift_x: int = 0,
                     shift_y: int = 0, out_buf_size: int = 1 << 20, pixel_stride: int | None = None,
-                    tiles=None, is_last=-1, per_tile: list | None = None, icc: bytes | None = None) -> bytes:
+                    tiles=None, is_last=-1, per_tile: list | None = None, icc: bytes | None = None,
+                    batch: int | None = None) -> bytes:
     """Encode `image` (H, W, C>=3 interleaved; uint8/uint16/float32) exactly the way the reference
     CLI drives the library: one output buffer, and after every tile the
     flush / release / consume / provide loop (hydrium.c:402-480).
@@ -124,6 +125,11 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
     libhydrium.h:240); `per_tile`, if a list, receives the bytes surfaced after each tile; `icc` is a
     suggested ICC profile (one-frame mode only, hydrium.c:288-296); `is_last` may be a function of
     (tile_x, tile_y), as the CLI's PFM path sets it explicitly (hydrium.c:459).
+    `batch` (libhydrium_b200 only): hydb_encoder_set_batch -- 1 = every tile's bytes surface in the flush
+    loop right after it, like the reference; default = the library's asynchronous pipeline.
+    After the last tile the flush loop is run once more: a no-op for the reference, and for
+    libhydrium_b200 the documented way to collect everything when no tile was marked last
+    (tile subsets without is_last are legal).
     """
     if image.ndim != 3 or image.shape[2] < 3:
         raise ValueError("image must be (H, W, C>=3)")
@@ -140,6 +146,10 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
     obuf = np.empty(out_buf_size, dtype=np.uint8)
     enc = HYDEncoder(lib)
     try:
+        if batch is not None:
+            lib.hydb_encoder_set_batch.restype = C.c_int
+            lib.hydb_encoder_set_batch.argtypes = [C.c_void_p, C.c_uint32]
+            enc.check(lib.hydb_encoder_set_batch(enc._enc, batch))
         enc.check(enc.set_metadata(w, h, linear_light, shift_x, shift_y))
         if icc is not None:
             enc.check(enc.set_suggested_icc_profile(icc))
@@ -163,6 +173,17 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
             out += got
             if per_tile is not None:
                 per_tile.append(bytes(got))
+        while True:   # final poll
+            ret = enc.flush()
+            r2, written = enc.release_output_buffer()
+            enc.check(r2)
+            out += obuf[:written].tobytes()
+            if per_tile and written:
+                per_tile[-1] += obuf[:written].tobytes()
+            enc.check(enc.provide_output_buffer(obuf))
+            if ret != HYD_NEED_MORE_OUTPUT:
+                enc.check(ret)
+                break
     finally:
         enc.destroy()
     return bytes(out)

@@ -24,6 +24,8 @@ HYDB_SYMBOLS = (
     "hydb_engine_read_tap", "hydb_engine_enable_timing", "hydb_engine_stage_ms", "hydb_engine_frame_lengths",
     "hydb_engine_encode_frames", "hydb_engine_read_model", "hydb_oneframe_finish", "hydb_engine_icc_header", "hydb_ipc_export", "hydb_ipc_open", "hydb_ipc_close",
     "hydb_engine_compact_regions", "hydb_engine_store_u64", "hydb_engine_set_chain_kernel",
+    "hydb_engine_submit_frames", "hydb_engine_job_poll", "hydb_engine_job_regather", "hydb_engine_job_release",
+    "hydb_engine_slot_frame_lengths",
 )
 
 

@@ -100,11 +100,14 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *encoder, 
 
 /* ===================================================================== part 2: additive API */
 
-/* How many tiles hyd_send_tile may queue before it launches the GPU pipeline.  1 = every
- * hyd_send_tile encodes synchronously and the following hyd_flush returns that tile's bytes,
- * exactly like the reference.  N > 1 = tiles are staged and encoded N at a time (or when the last
- * tile arrives); hyd_flush then returns bytes in send order as batches complete, and the
- * concatenation of everything surfaced is byte-identical.  Default: env HYDRIUM_B200_BATCH, else 1.
+/* How hyd_send_tile feeds the GPU.  By default (no call, HYDRIUM_B200_BATCH unset) it is asynchronous: the
+ * tile is copied into page-locked staging memory and the call returns; tiles are encoded a chunk (32 tiles,
+ * or one multi-group frame) at a time by engine jobs that overlap the staging of later tiles, several
+ * chunks in flight (HYDRIUM_B200_DEPTH, default 8 / 4); hyd_flush returns bytes in send order as chunks
+ * finish, everything by the end of the flush loop after the last tile (or on a second consecutive
+ * hyd_flush), and the concatenation of everything surfaced is byte-identical to the reference's.
+ * 1 = every hyd_send_tile encodes synchronously and the following hyd_flush returns that tile's bytes,
+ * exactly like the reference.  N > 1 = asynchronous with chunks of N tiles.
  * Must be called before the first hyd_send_tile. */
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *encoder, uint32_t tiles);
 /* CUDA device ordinal for this encoder.  Default: env HYDRIUM_B200_DEVICE, else the current device. */
@@ -189,6 +192,28 @@ HYDRIUM_EXPORT HYDStatusCode hydb_oneframe_finish(HydbEngine *engine, const uint
  * hydb_engine_encode_tiles; finish with hydb_engine_finish). */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_encode_frames(HydbEngine *engine, const HydbFrame *frames, uint32_t n,
                                                        uint8_t *d_out, uint64_t d_out_cap, uint64_t d_out_pos);
+/* ---- asynchronous jobs: what the nine-symbol API runs on -------------------------------------------------
+ * hydb_engine_submit_frames enqueues, on a stream pair of its own,
+ *     [copy of h2d_bytes from h_src (page-locked) to d_dst] -> the kernels for n frames on workspace slots
+ *     slot0 .. -> the compaction of their bytes into `out` -> a 16-byte result record
+ * and returns at once with a job id (at most 16 jobs at a time).  `out` may be DEVICE memory or PAGE-LOCKED
+ * HOST memory (hydb_host_alloc): in the second case the compaction kernel writes the codestream across PCIe
+ * itself and no copy follows.  The frames' plane pointers are device pointers (normally into d_dst).  The
+ * caller owns the slot ranges: concurrent jobs must not overlap, and a job's slots stay untouched until it
+ * is released.  *slots = workspace slots the job took (1 per single-group frame, 1 + groups otherwise).
+ * hydb_engine_job_poll: HYD_DEFAULT while running (wait = 0), HYD_OK with *bytes, HYD_NEED_MORE_OUTPUT when
+ * `out` was too small (hydb_engine_job_regather gathers again, synchronously, into a device buffer), or the
+ * error of the job's tiles.  hydb_engine_job_release frees the job id. */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_submit_frames(HydbEngine *engine, const HydbFrame *frames, uint32_t n,
+                                                       uint32_t slot0, const void *h_src, void *d_dst, size_t h2d_bytes,
+                                                       uint8_t *out, uint64_t out_cap, uint32_t *job, uint32_t *slots);
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_job_poll(HydbEngine *engine, uint32_t job, int wait, uint64_t *bytes);
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_job_regather(HydbEngine *engine, uint32_t job, uint8_t *d_out, uint64_t d_out_cap,
+                                                      uint64_t *bytes);
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_job_release(HydbEngine *engine, uint32_t job);
+/* frame byte lengths of n slots starting at slot0 (of a finished job) */
+HYDRIUM_EXPORT HYDStatusCode hydb_engine_slot_frame_lengths(HydbEngine *engine, uint32_t slot0, uint32_t *dst, uint32_t n);
+
 /* Synchronise, check per-tile error flags of the last batch, return total bytes appended by it. */
 HYDRIUM_EXPORT HYDStatusCode hydb_engine_finish(HydbEngine *engine, uint64_t *batch_bytes);
 

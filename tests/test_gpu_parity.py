@@ -164,11 +164,13 @@ def test_batches_larger_than_the_workspace(product_lib, oracle):
 
 
 def test_nine_symbol_api_cli_loop(product_lib, oracle):
-    """The reference CLI's call sequence (hydrium.c:402-480) against our library, per-tile
-    synchronous mode: every tile's bytes surface in the flush loop that follows it."""
+    """The reference CLI's call sequence (hydrium.c:402-480) against our library.  Default
+    (asynchronous) mode: the concatenation is the reference's.  hydb_encoder_set_batch(1): every
+    tile's bytes surface in the flush loop that follows it, like the reference."""
     for img, lin in [(synth_image(700, 600, 8), 0), (synth_image(300, 520, 16, seed=3), 1)]:
+        assert encode_cli_loop(product_lib, img, linear_light=lin) == oracle.encode_image(img, linear_light=lin)
         per = []
-        out = encode_cli_loop(product_lib, img, linear_light=lin, per_tile=per)
+        out = encode_cli_loop(product_lib, img, linear_light=lin, per_tile=per, batch=1)
         assert out == oracle.encode_image(img, linear_light=lin)
         h, w, _ = img.shape
         hdr = oracle.image_header(w, h)
@@ -222,6 +224,150 @@ def test_nine_symbol_api_batched_mode(product_lib, oracle):
                 enc.check(ret)
         enc.destroy()
         assert bytes(out) == want, batch
+
+
+def _send_all(lib, img, calls, *, shift=0, lin=0, flush_every=1, env=None, remeta=None, pixel_stride=None, planes=None):
+    """Drive a libhydrium build with an explicit list of (tile_x, tile_y, is_last) calls; the output buffer is
+    drained after every `flush_every`-th tile (0 = only at the end) and once more at the end."""
+    import os
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        h, w, ch = img.shape
+        item = img.dtype.itemsize
+        enc = HYDEncoder(lib)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    out = bytearray()
+    obuf = np.empty(1 << 20, np.uint8)   # like the CLI; the reference writes headers straight into it (SURVEY Appendix D)
+
+    def drain():
+        while True:
+            ret = enc.flush()
+            _, n = enc.release_output_buffer()
+            out.extend(obuf[:n].tobytes())
+            enc.check(enc.provide_output_buffer(obuf))
+            if ret != HYD_NEED_MORE_OUTPUT:
+                enc.check(ret)
+                return
+    enc.check(enc.set_metadata(w, h, lin, shift, shift))
+    enc.check(enc.provide_output_buffer(obuf))
+    tw = 256 << shift
+    for i, (tx, ty, last) in enumerate(calls):
+        if remeta is not None and i == remeta[0]:
+            shift = remeta[1]
+            tw = 256 << shift
+            enc.check(enc.set_metadata(w, h, lin, shift, shift))
+        p = img.ctypes.data + (ty * tw * w * ch + tx * tw * ch) * item
+        pl = (p, p + item, p + 2 * item) if planes is None else tuple(p + o * item for o in planes)
+        enc.check(enc.send_tile(pl, tx, ty, w * ch, ch if pixel_stride is None else pixel_stride, last, E._fmt_of(img)))
+        if flush_every and (i + 1) % flush_every == 0:
+            drain()
+    drain()
+    drain()   # a second poll in a row: whatever is left (no tile was marked last) must come out now
+    enc.destroy()
+    return bytes(out)
+
+
+def test_async_pipeline_orders_gaps_and_backpressure(product_lib, reflib):
+    """The default (asynchronous) nine-symbol path against the reference library driven with the very same
+    calls: raster, reversed and shuffled send orders, the lower-right tile first with is_last = -1, tile
+    subsets that never mark a last tile (libhydrium.h:235-240), a caller that never drains until the end
+    (finished chunks spill to the heap), tiny chunks, and an output area too small for a chunk (re-gather)."""
+    img = synth_image(1100, 800, 8, seed=6)   # 5 x 4 tiles
+    tiles = [(x, y) for y in range(4) for x in range(5)]
+    rng = np.random.default_rng(11)
+    shuffled = [tiles[i] for i in rng.permutation(len(tiles))]
+    cases = {
+        "raster": [(x, y, -1) for x, y in tiles],
+        "reversed": [(x, y, -1) for x, y in reversed(tiles)],           # the lower-right tile comes first
+        "shuffled": [(x, y, -1) for x, y in shuffled],
+        "subset, no last tile": [(x, y, 0) for x, y in shuffled[:7]],
+        "subset, explicit last in the middle": [(x, y, int(i == 3)) for i, (x, y) in enumerate(shuffled[:9])],
+    }
+    for name, calls in cases.items():
+        want = _send_all(reflib, img, calls)
+        assert _send_all(product_lib, img, calls) == want, name
+        assert _send_all(product_lib, img, calls, flush_every=0) == want, (name, "drained only at the end")
+        assert _send_all(product_lib, img, calls, env={"HYDRIUM_B200_BATCH": "3", "HYDRIUM_B200_DEPTH": "2"}, flush_every=0) == want, (name, "chunks of 3, 2 in flight")
+        assert _send_all(product_lib, img, calls, env={"HYDRIUM_B200_BATCH": "1"}) == want, (name, "synchronous")
+    calls = cases["raster"]
+    want = _send_all(reflib, img, calls)
+    assert _send_all(product_lib, img, calls, env={"HYDRIUM_B200_OUTCAP_KB": "64"}) == want, "re-gather path"
+    # larger tiles and 16-bit samples through the same machinery (one multi-group frame per chunk)
+    img16 = synth_image(1100, 800, 16, seed=2)
+    calls = [(x, y, -1) for y in range(2) for x in range(3)]
+    # (a full-size tile first: the reference sizes its per-group arrays by the first tile it sees and
+    # corrupts its heap when a later one has more groups)
+    order = [calls[0]] + calls[:0:-1]
+    want = _send_all(reflib, img16, order, shift=1, lin=1)
+    assert _send_all(product_lib, img16, order, shift=1, lin=1) == want
+    assert _send_all(product_lib, img16, order, shift=1, lin=1, env={"HYDRIUM_B200_OUTCAP_KB": "64"}, flush_every=0) == want
+
+
+def test_metadata_changed_on_a_live_encoder(product_lib, reflib, oracle):
+    """hyd_set_metadata again on a used encoder with a larger tile geometry: the staging ring is rebuilt,
+    nothing overflows, and the stream continues without a second image header.  (The reference itself
+    corrupts its heap on this sequence -- it sizes its group arrays once -- so the expectation is put
+    together from two of its encoders.)"""
+    img = synth_image(1100, 800, 8, seed=9)
+    h, w, _ = img.shape
+    first = [(0, 0, 0), (1, 0, 0)]            # two 256-tiles
+    second = [(0, 0, 0), (0, 0, 1)]           # then shift 2: 1024-tiles
+    hdr = oracle.image_header(w, h)
+    part_b = _send_all(reflib, img, second, shift=2)
+    assert part_b.startswith(hdr)
+    want = _send_all(reflib, img, first) + part_b[len(hdr):]
+    assert _send_all(product_lib, img, first + second, remeta=(2, 2)) == want
+    assert _send_all(product_lib, img, first + second, remeta=(2, 2), env={"HYDRIUM_B200_BATCH": "1"}) == want
+
+
+def test_interleaved_layout_at_the_end_of_the_callers_buffer(product_lib, oracle):
+    """ARGB: the three planes start one sample into each pixel.  The staging copy must not read past the
+    last addressed sample -- the image here ends exactly at an inaccessible page."""
+    import ctypes
+    import mmap
+    w, h = 300, 270
+    rgb = synth_image(w, h, 8, seed=12)
+    argb = np.concatenate([np.full((h, w, 1), 9, np.uint8), rgb], axis=2)
+    nbytes = argb.nbytes - 0   # A R G B per pixel; the last B is the last byte
+    page = mmap.PAGESIZE
+    total = (nbytes + page - 1) // page * page + page
+    m = mmap.mmap(-1, total)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(m))
+    libc = ctypes.CDLL(None, use_errno=True)
+    assert libc.mprotect(ctypes.c_void_p(base + total - page), page, 0) == 0   # PROT_NONE guard page
+    start = total - page - nbytes
+    view = np.frombuffer(m, np.uint8, count=nbytes, offset=start).reshape(h, w, 4)
+    view[:] = argb
+    got = _send_all(product_lib, view, [(x, y, -1) for y in range(2) for x in range(2)], pixel_stride=4, planes=(1, 2, 3))
+    assert got == oracle.encode_image(rgb)
+    del view
+    libc.mprotect(ctypes.c_void_p(base + total - page), page, 3)
+    m.close()
+
+
+def test_float_samples_beyond_the_16_bit_coefficient_range(product_lib, reflib):
+    """HYD_FLOAT32 samples scaled far outside [0, 1]: quantised coefficients leave int16, which the B200
+    encoder's records are sized for (the reference keeps int32, encoder.c:808).  Either the bytes are the
+    reference's or the call fails loudly -- never different bytes."""
+    base = (synth_image(300, 260, 16, seed=4).astype(np.float32) / np.float32(65535))
+    for scale in (8.0, 300.0, 1e6):
+        img = (base * np.float32(scale)).astype(np.float32)
+        try:
+            want = encode_cli_loop(reflib, img)
+        except HydriumError:
+            want = None   # the reference gives up on its own (token alphabet beyond its tables)
+        try:
+            got = encode_cli_loop(product_lib, img)
+        except HydriumError as e:
+            assert e.code < -10 and ("16-bit range" in (e.message or "") or "alphabet" in (e.message or "")), (scale, e.message)
+            continue
+        assert want is not None and got == want, scale
 
 
 def test_sample_layouts(product_lib, oracle):
