@@ -68,6 +68,10 @@ class PeerGather:
         pg = PeerGather(engine, region_bytes)                    # collective: call on every rank
         n = engine.encode_image_device(..., d_out=pg.d_out, d_out_cap=pg.d_out_cap)
         total = pg.finish(n, d_final, d_final_cap)               # collective; bytes on dst, 0 elsewhere
+
+    The regions are double-buffered: `d_out` alternates between two sets from one finish() to the next, so
+    a fast rank's next step never writes into a region `dst` is still compacting (`dst` cannot pass the
+    barrier of step k + 1 before its own compaction of step k has run: both are on its engine stream).
     """
 
     HEADER = 256
@@ -78,9 +82,10 @@ class PeerGather:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.stride = (self.HEADER + region_bytes + 16 + 255) & ~255
         self._own = self._peer = None
+        self.parity = 0
         handle = [None]
         if self.rank == dst:
-            self._own = engine.device_alloc(self.world * self.stride)
+            self._own = engine.device_alloc(2 * self.world * self.stride)
             buf = (C.c_uint8 * 64)()
             if self.lib.hydb_ipc_export(self._own, buf) != 0:
                 raise RuntimeError("cudaIpcGetMemHandle failed")
@@ -94,10 +99,19 @@ class PeerGather:
             if not self._peer:
                 raise RuntimeError("cudaIpcOpenMemHandle failed (no peer access between the GPUs?)")
             self.base = self._peer
-        self.d_out = self.base + self.rank * self.stride + self.HEADER
         self.d_out_cap = self.stride - self.HEADER - 16
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
         self._ext = torch.cuda.ExternalStream(engine.stream, device=self._flag.device)
+
+    @property
+    def set_base(self) -> int:
+        """first byte of the region set this step writes into"""
+        return self.base + self.parity * self.world * self.stride
+
+    @property
+    def d_out(self) -> int:
+        """where this rank's encode call of the current step writes (its region of the current set)"""
+        return self.set_base + self.rank * self.stride + self.HEADER
 
     def finish(self, n_local: int, d_final: int = 0, d_final_cap: int = 0) -> int:
         """After this rank's encode call has returned (its span is in the region): publish the length,
@@ -106,13 +120,15 @@ class PeerGather:
         import ctypes as C
         # the length goes out on the engine's stream and the barrier is enqueued behind it on the same
         # stream, so no rank passes the barrier before every span and every length has landed
-        self.eng._check(self.lib.hydb_engine_store_u64(self.eng._h, self.base + self.rank * self.stride, n_local))
+        set_base = self.set_base
+        self.eng._check(self.lib.hydb_engine_store_u64(self.eng._h, set_base + self.rank * self.stride, n_local))
         with torch.cuda.stream(self._ext):
             dist.all_reduce(self._flag, group=self.group)
+        self.parity ^= 1
         if self.rank != self.dst:
             return 0
         total = C.c_uint64(0)
-        self.eng._check(self.lib.hydb_engine_compact_regions(self.eng._h, self.base, self.world, self.stride, d_final,
+        self.eng._check(self.lib.hydb_engine_compact_regions(self.eng._h, set_base, self.world, self.stride, d_final,
                                                              d_final_cap, C.byref(total)))
         return int(total.value)
 
