@@ -990,7 +990,7 @@ static void image_tiles(std::vector<HydbTile> &tiles, const void *base, uint32_t
 // band's rows to `d_dst` on the band's stream first).  Frames are position- but not
 // order-dependent; the caller gathers all tiles afterwards on eng->st, which waits for every band.
 static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t rows, const void *h_src, void *d_dst,
-                                  size_t row_bytes, uint32_t pixel_rows) {
+                                  size_t row_bytes, uint32_t pixel_rows, bool any_float) {
     // HYDRIUM_B200_BANDTRACE=1: print when each band's stages started / ended (development aid; synchronises)
     static const bool trace = [] { const char *e = getenv("HYDRIUM_B200_BANDTRACE"); return e && e[0] == '1'; }();
     static cudaEvent_t tr[1 + HydbEngine::kBands * 5];
@@ -1033,7 +1033,7 @@ static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t ro
         CK(cudaEventRecord(eng->band_lf[b], sb2));
         launch_hf_tokens(v, n, sb);
         if (trace) cudaEventRecord(tr[1 + b * 5 + 2], sb);
-        launch_ans_chain(v, n, sb);
+        launch_ans_chain(v, n, sb, !any_float, rows * tiles_x);
         if (trace) cudaEventRecord(tr[1 + b * 5 + 3], sb);
         CK(cudaStreamWaitEvent(sb, eng->band_lf[b], 0));
         launch_ans_pack(v, eng->templ, n, sb);
@@ -1081,7 +1081,7 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
                     tile_row_end, with_header);
         HYDStatusCode rc = prepare_tiles(eng, tiles.data(), (uint32_t)ntiles, eng->st);
         if (rc == HYD_OK)
-            rc = launch_bands(eng, tiles_x, tile_row_end - tile_row_begin, nullptr, nullptr, 0, 0);
+            rc = launch_bands(eng, tiles_x, tile_row_end - tile_row_begin, nullptr, nullptr, 0, 0, sample_fmt == HYD_FLOAT32);
         if (rc != HYD_OK)
             return rc;
         launch_gather(eng->ws, (uint32_t)ntiles, d_out, d_out_cap, 0, eng->d_overflow, eng->st);
@@ -1225,9 +1225,15 @@ static HYDStatusCode grow_device(HydbEngine *eng, void **p, size_t *cap, size_t 
 HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint32_t width, uint32_t height,
                                      uint32_t channels, int sample_fmt, int linear_light, uint8_t *h_out,
                                      uint64_t h_out_cap, uint64_t *out_len) {
-    if (!eng || !h_pixels || !h_out || !out_len ||
-        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16 && sample_fmt != HYD_FLOAT32))
+    if (!eng || !h_pixels || !h_out || !out_len || !width || !height || channels < 3 ||
+        (sample_fmt != HYD_UINT8 && sample_fmt != HYD_UINT16 && sample_fmt != HYD_FLOAT32)) {
+        if (eng) eng->error = "invalid arguments to hydb_encode_image_host";
         return HYD_API_ERROR;
+    }
+    if ((uint64_t)width * height > (UINT64_C(1) << 40) / channels) {
+        eng->error = "image too large";
+        return HYD_API_ERROR;
+    }
     CK(cudaSetDevice(eng->device));
     const size_t item = sample_item_bytes(sample_fmt);
     const size_t in_bytes = (size_t)width * height * channels * item;
@@ -1255,7 +1261,7 @@ HYDStatusCode hydb_encode_image_host(HydbEngine *eng, const void *h_pixels, uint
     rc = prepare_tiles(eng, tiles.data(), (uint32_t)ntiles, eng->st);
     if (rc != HYD_OK)
         return rc;
-    rc = launch_bands(eng, tiles_x, tiles_y, h_pixels, eng->host_in, (size_t)width * channels * item, height);
+    rc = launch_bands(eng, tiles_x, tiles_y, h_pixels, eng->host_in, (size_t)width * channels * item, height, sample_fmt == HYD_FLOAT32);
     if (rc != HYD_OK)
         return rc;
     launch_gather(eng->ws, (uint32_t)ntiles, eng->host_out, h_out_cap, 0, eng->d_overflow, eng->st);

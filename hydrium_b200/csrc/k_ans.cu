@@ -690,9 +690,12 @@ static uint32_t chain_table_limit() {
     return lim;
 }
 
-void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact) {
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact, uint32_t concurrent_tiles) {
     const int mode = ws.chain_mode ? (int)ws.chain_mode : chain_mode_override();
-    if (allow_compact && (mode == 2 || (mode == 0 && ntiles > chain_table_limit()))) {
+    // what counts is how many chains compete for the GPU at once: a band of a larger batch is launched next
+    // to its sibling bands on other streams
+    const uint32_t competing = concurrent_tiles > ntiles ? concurrent_tiles : ntiles;
+    if (allow_compact && (mode == 2 || (mode == 0 && competing > chain_table_limit()))) {
         launch_ans_chain_compact(ws, ntiles, st);
         return;
     }

@@ -11,6 +11,7 @@
 // order with coalesced 16-byte stores.  Nothing is a dense contraction that could use tensor
 // cores without changing the result: the summation ORDER is part of the format (SURVEY.md
 // Appendix B), every product and sum is a separate IEEE round-to-nearest op (no FMA).
+#include "chain_util.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "tables.cuh"
@@ -154,6 +155,60 @@ __device__ __forceinline__ void load_xyb(const TileDesc &t, const uint16_t *in_l
     }
 }
 
+// ---- bulk-asynchronous staging of the CTA's 8 pixel rows (TMA, cp.async.bulk -> SASS UBLKCP) -------------
+// One thread arms an mbarrier with the byte count and issues one bulk copy per pixel row (global -> shared,
+// completion counted on the mbarrier); the copy engine moves the rows while the CTA loads its tables, and
+// every thread then picks its samples out of shared memory with one LDS each (no packed-word unpacking).
+// Applies to interleaved u8 / u16 tiles whose rows are 16-byte aligned and a multiple of 16 bytes long
+// (every tile of an image whose row pitch is a multiple of 16 bytes: 768 / 1536 / 2048-byte tile rows);
+// everything else takes the direct-load path above.
+constexpr int kStageRowMax = 2048;                 // RGBA16
+constexpr int kStagePitch = kStageRowMax + 16;     // rows start on different banks
+
+__device__ __forceinline__ bool stage_applicable(const TileDesc &t, uint32_t item, uint32_t &row_bytes) {
+    const uint8_t *p0 = (const uint8_t *)t.plane[0];
+    row_bytes = t.w * (uint32_t)t.pixel_stride * item;
+    return (t.pixel_stride == 3 || t.pixel_stride == 4) && (const uint8_t *)t.plane[1] == p0 + item &&
+           (const uint8_t *)t.plane[2] == p0 + 2 * item && t.row_stride > 0 && row_bytes <= (uint32_t)kStageRowMax &&
+           (row_bytes & 15u) == 0 && (((uintptr_t)p0 | (uintptr_t)(t.row_stride * (int64_t)item)) & 15u) == 0;
+}
+
+__device__ __forceinline__ void stage_issue(const TileDesc &t, uint32_t item, uint32_t row_bytes, uint32_t y0, uint32_t rows,
+                                            uint8_t *s_in, uint64_t *mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * row_bytes) : "memory");
+    const uint8_t *src = (const uint8_t *)t.plane[0] + (int64_t)y0 * t.row_stride * (int64_t)item;
+    for (uint32_t r = 0; r < rows; r++) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in + r * kStagePitch);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src + (int64_t)r * t.row_stride * (int64_t)item), "r"(row_bytes), "r"(bar) : "memory");
+    }
+}
+
+template <typename Sample>
+__device__ __forceinline__ void load_xyb_staged(const TileDesc &t, const uint16_t *in_lut, const uint8_t *s_in, uint32_t px0,
+                                                uint32_t r, uint32_t y, float (&X)[8], float (&Y)[8], float (&B)[8]) {
+    const Sample *row = (const Sample *)(s_in + r * kStagePitch);
+    const uint32_t ps = (uint32_t)t.pixel_stride;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t px = px0 + i;
+        float x = 0.0f, yy = 0.0f, b = 0.0f;   // zero padding of partial blocks (format.c:182-191)
+        if (px < t.w && y < t.h) {
+            const uint32_t rr = in_lut[row[px * ps]], g = in_lut[row[px * ps + 1]], bl = in_lut[row[px * ps + 2]];
+            const float l = bias_entry(((19661u * rr + 40761u * g + 5112u * bl) >> 16) & 0xFFFFu);   // format.c:48-56
+            const float m = bias_entry(((15073u * rr + 45350u * g + 5112u * bl) >> 16) & 0xFFFFu);
+            const float s = bias_entry(((15953u * rr + 13419u * g + 36163u * bl) >> 16) & 0xFFFFu);
+            yy = __fmul_rn(__fadd_rn(l, m), 0.5f);
+            x = __fsub_rn(yy, m);
+            b = __fsub_rn(s, yy);
+        }
+        X[i] = x;
+        Y[i] = yy;
+        B[i] = b;
+    }
+}
+
 // HYD_FLOAT32 samples: no tables, the transfer curve and the opsin mix are evaluated per pixel in the
 // reference's operation order (format.c:38-46, 111-140).  Returns false for a NaN / Inf sample.
 __device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uint32_t px0, uint32_t y, float (&X)[8],
@@ -196,9 +251,11 @@ __device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uin
 __global__ void __launch_bounds__(256)
 k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__restrict__ coef,
                 uint16_t *__restrict__ nzinfo, int32_t *__restrict__ lfq, uint32_t *__restrict__ tile_err,
-                float *__restrict__ dbg_xyb, float *__restrict__ dbg_dct) {
-    __shared__ float s_rows[3 * 32 * kBlkPad];            // 27,648 B
+                float *__restrict__ dbg_xyb, float *__restrict__ dbg_dct, bool use_tma) {
+    __shared__ __align__(16) float s_rows[3 * 32 * kBlkPad];   // 27,648 B; first the staged input rows (8 x 2,064 B)
     __shared__ __align__(16) int16_t s_q[32 * 3 * 64];    // 12,288 B
+    __shared__ __align__(8) uint64_t s_mbar;
+    static_assert(8 * kStagePitch <= (int)sizeof(float) * 3 * 32 * kBlkPad, "staged rows alias the row-exchange tile");
     __shared__ uint16_t s_lut8[256];
     __shared__ float s_w[3 * 64];
     __shared__ uint8_t s_scan[64];
@@ -212,6 +269,17 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     const bool fmt16 = (t.flags & kTileFmt16) != 0, fmt32 = (t.flags & kTileFmtF32) != 0;
     const bool linear = (t.flags & kTileLinear) != 0;
 
+    // bulk-asynchronous staging of this CTA's pixel rows (see stage_applicable); HYDRIUM_B200_TMA=0 turns it off
+    uint8_t *s_in = reinterpret_cast<uint8_t *>(s_rows);
+    uint32_t row_bytes = 0;
+    const uint32_t item = fmt16 ? 2u : 1u;
+    const bool staged = use_tma && !fmt32 && stage_applicable(t, item, row_bytes);
+    if (staged && tid == 0) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_mbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t rows = t.h - by * 8 < 8 ? t.h - by * 8 : 8;
+        stage_issue(t, item, row_bytes, by * 8, rows, s_in, &s_mbar);
+    }
     if (!fmt16 && !fmt32)
         s_lut8[tid] = (linear ? luts.lut8_lin : luts.lut8_srgb)[tid];
     if (tid < 192)
@@ -221,11 +289,17 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     __syncthreads();
 
     // ---- colour transform + row pass --------------------------------------------------------
+    float v[3][8];
     if (b < vbw) {
-        float v[3][8];
         if (fmt32) {
             if (!load_xyb_f32(t, linear, b * 8, by * 8 + r, v[0], v[1], v[2]))
                 atomicOr(&tile_err[tile], (uint32_t)kErrNonFinite);
+        } else if (staged) {
+            mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0);
+            if (fmt16)
+                load_xyb_staged<uint16_t>(t, linear ? luts.lut16_lin : luts.lut16_srgb, s_in, b * 8, r, by * 8 + r, v[0], v[1], v[2]);
+            else
+                load_xyb_staged<uint8_t>(t, s_lut8, s_in, b * 8, r, by * 8 + r, v[0], v[1], v[2]);
         } else if (fmt16)
             load_xyb<uint16_t>(t, linear ? luts.lut16_lin : luts.lut16_srgb, luts.bias, b * 8, by * 8 + r, v[0], v[1], v[2]);
         else
@@ -239,6 +313,10 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
                 d[i * 3 + 2] = v[2][i];
             }
         }
+    }
+    if (staged)
+        __syncthreads();   // the staged rows live where the row-exchange tile goes: everyone has read its pixels
+    if (b < vbw) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             float o[8];
@@ -336,8 +414,9 @@ void launch_build_luts(uint16_t *lut8_srgb, uint16_t *lut8_lin, uint16_t *lut16_
 
 void launch_xyb_dct_quant(const Workspace &ws, const LutSet &luts, uint32_t ntiles, cudaStream_t st) {
     prefer_max_shared(k_xyb_dct_quant);
+    static const bool use_tma = [] { const char *e = getenv("HYDRIUM_B200_TMA"); return !(e && e[0] == '0'); }();
     k_xyb_dct_quant<<<dim3(kBlocksPerRow, ntiles), 256, 0, st>>>(ws.tiles, luts, ws.coef, ws.nzinfo, ws.lfq, ws.tile_err,
-                                                                 ws.dbg_xyb, ws.dbg_dct);
+                                                                 ws.dbg_xyb, ws.dbg_dct, use_tma);
 }
 
 }  // namespace hydb

@@ -65,7 +65,8 @@ void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 // allow_compact: no HYD_FLOAT32 tile in the launch (tokens stay below 32); large launches then take
 // k_ans_chain_compact (sixteen chains per SM), small ones the table kernel (two per SM, shorter steps)
-void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact = true);
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact = true,
+                      uint32_t concurrent_tiles = 0);
 void launch_ans_chain_compact(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 int ans_compact_smem_bytes();
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
