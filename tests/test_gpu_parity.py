@@ -370,6 +370,25 @@ def test_float_samples_beyond_the_16_bit_coefficient_range(product_lib, reflib):
         assert want is not None and got == want, scale
 
 
+def test_compute_sanitizer(product_lib):
+    """compute-sanitizer memcheck over one small pass through every kernel family (tools/sanitize_case.py:
+    both rANS chain kernels, TMA staging, multi-group frames, one-frame mode over two LF groups, the
+    asynchronous API with re-gather, float samples).  Invalid accesses or leaks of device errors fail it."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([exe, "--tool", "memcheck", "--error-exitcode", "86", "--launch-timeout", "120", sys.executable,
+                        os.path.join(root, "tools", "sanitize_case.py")], capture_output=True, text=True, timeout=1500)
+    tail = (p.stdout + p.stderr)[-3000:]
+    assert p.returncode == 0, tail
+    assert "ERROR SUMMARY: 0 errors" in p.stdout + p.stderr, tail
+
+
 def test_sample_layouts(product_lib, oracle):
     """Planar, RGBA-interleaved, BGR-ordered, negative row stride and odd strides (libhydrium.h:202-220)."""
     rgb = synth_image(300, 270, 8, seed=12)
