@@ -562,14 +562,24 @@ static void gpu_plan(const HYDEncoder *enc, size_t item, Gpu *g) {
     g->device = enc->device;
     const uint32_t depth = enc->depth;
     if (enc->groups_per_tile > 1 || enc->of_n) {
-        /* one frame of several groups per chunk */
+        /* frames of several groups: as many per chunk as fit ~32 workspace slots (a 512x512 tile is a prefix
+         * + 4 groups: six of them per job), one when the frame is an LF group of a one-frame image (its
+         * sections are collected job by job) */
         const uint64_t W = enc->metadata.width, H = enc->metadata.height;
         const uint64_t fw = W < enc->tile_w ? W : enc->tile_w, fh = H < enc->tile_h ? H : enc->tile_h;
-        g->units = 1;
-        g->slots_per_chunk = 1 + enc->groups_per_tile;
-        g->chunk_cap = (size_t)(fw * fh) * 4u * item + 4096;
+        const uint32_t spf = 1 + enc->groups_per_tile;
+        uint32_t units = enc->of_n || enc->batch == 1 ? 1u : 32u / spf;
+        if (enc->batch > 1 && !enc->of_n)
+            units = enc->batch;
+        if (units < 1)
+            units = 1;
+        if (units > 64)
+            units = 64;
+        g->units = units;
+        g->slots_per_chunk = units * spf;
+        g->chunk_cap = (size_t)units * (size_t)(fw * fh) * 4u * item + 4096;
         g->out_cap = (size_t)g->slots_per_chunk * (128u << 10) + (256u << 10);
-        g->nchunks = enc->batch == 1 ? 1 : (depth ? depth : (g->chunk_cap > ((size_t)40 << 20) ? 2 : 4));
+        g->nchunks = enc->batch == 1 ? 1 : (depth ? depth : (g->chunk_cap > ((size_t)40 << 20) ? 2 : (g->chunk_cap > ((size_t)12 << 20) ? 4 : 8)));
     } else {
         const uint32_t units = enc->batch ? enc->batch : 32u;
         g->units = units;

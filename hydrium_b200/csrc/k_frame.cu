@@ -25,6 +25,8 @@
 // k_frame_lf and k_icc_header spread the per-value work (residuals, tokens, histograms, symbol bits)
 // over 1024 threads with block scans; what is inherently small and sequential (code construction,
 // stream headers) runs on one thread through prefix_coder.cuh.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "sections.cuh"
 #include "lf_values.cuh"
@@ -326,17 +328,271 @@ struct ResidValues {
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return (uint32_t)v[i]; }
 };
 
-__global__ void __launch_bounds__(kLfThreads)
+// ---- the LF stream of a frame by a thread-block CLUSTER -------------------------------------------------
+// Up to 3 x 65 536 values go through one prefix-coded stream (one histogram, one header).  One CTA of 1024
+// threads walked 192 positions per thread, every access a trip to L2 (the kernel runs with the L1 carve-out
+// at maximum shared memory): 3.15 ms, longer than the 64 rANS chains it runs beside.  Here the stream
+// belongs to a cluster of kLfCluster CTAs that are scheduled together: 8192 threads take 24 positions each,
+// and what the single-CTA version kept in its shared memory -- scan carries, the histogram, the code
+// table, error flags -- travels between the CTAs through distributed shared memory
+// (cluster.map_shared_rank) around cluster-wide barriers.  CTA 0 is the master: it owns the bit sink,
+// builds the code and writes the stream header.
+namespace cg = cooperative_groups;
+constexpr int kLfCluster = 8;
+
+// exclusive scan over all threads of the cluster, in (rank, thread) order; `s_x`: one shared word per CTA
+template <typename Op>
+__device__ __forceinline__ uint32_t cluster_exclusive_scan(cg::cluster_group &cl, uint32_t v, uint32_t identity, Op op,
+                                                           uint32_t *s_warp, uint32_t *s_x, uint32_t &total) {
+    uint32_t btotal;
+    const uint32_t excl = block_exclusive_scan(v, identity, op, s_warp, btotal);
+    if (threadIdx.x == 0)
+        *s_x = btotal;
+    cl.sync();
+    uint32_t prefix = identity, all = identity;
+    const uint32_t r = cl.block_rank();
+    for (uint32_t k = 0; k < (uint32_t)kLfCluster; k++) {
+        const uint32_t t = *cl.map_shared_rank(s_x, k);
+        if (k < r)
+            prefix = op(prefix, t);
+        all = op(all, t);
+    }
+    cl.sync();   // everyone has read the slots: they may be written again
+    total = all;
+    return op(prefix, excl);
+}
+
+// block_prefix_stream (above) for a cluster.  Every CTA passes its own PrefixWork / scratch; on return
+// thread 0 of CTA 0 holds the bit sink behind the stream.  Returns error flags (uniform over the cluster).
+template <typename ValueAt>
+__device__ uint32_t cluster_prefix_stream(cg::cluster_group &cl, PrefixWork &w, BitSink &bw, uint32_t *outw, uint32_t out_words,
+                                          uint32_t *syms, uint32_t sym_cap, const PrefixParams &prm, uint32_t total,
+                                          ValueAt value_at, uint32_t *s_warp, uint32_t *s_first, uint32_t err_in) {
+    __shared__ uint32_t s_bitpos, s_err, s_x;
+    const uint32_t tid = threadIdx.x, rank = cl.block_rank();
+    const uint32_t gid = rank * kLfThreads + tid, gthreads = kLfCluster * kLfThreads;
+    const uint32_t lz = prm.lz_min_symbol;
+    __syncthreads();
+    for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads)
+        w.freq[i] = 0;
+    if (tid == 0) {
+        w.alpha0 = w.alpha1 = 0;
+        s_err = err_in;
+    }
+    cl.sync();   // nobody adds into CTA 0's histogram before it has been cleared
+    uint32_t my_err = 0;
+    // ---- symbols: thread = contiguous range of positions -------------------------------------------
+    const uint32_t per = (total + gthreads - 1) / gthreads;
+    const uint32_t a = gid * per < total ? gid * per : total, b = a + per < total ? a + per : total;
+    auto starts_run = [&](uint32_t i) -> bool { return !lz || i == 0 || value_at(i) != value_at(i - 1); };
+    uint32_t last_start = 0, first_start = total;
+    for (uint32_t i = a; i < b; i++) {
+        if (starts_run(i)) {
+            last_start = i + 1;
+            if (first_start == total)
+                first_start = i;
+        }
+    }
+    uint32_t dummy;
+    const uint32_t carry_start = cluster_exclusive_scan(cl, last_start, 0u, [](uint32_t x, uint32_t y) { return x > y ? x : y; },
+                                                        s_warp, &s_x, dummy);   // start (+1) of the run reaching into a
+    // next run start at or after b: exclusive min-scan from the right (mirrored thread order inside the
+    // CTA, then the minima of the CTAs to the right)
+    uint32_t carry_end;
+    {
+        s_first[kLfThreads - 1 - tid] = first_start;
+        __syncthreads();
+        const uint32_t mirrored = s_first[tid];
+        uint32_t bmin;
+        const uint32_t ex = block_exclusive_scan(mirrored, total, [](uint32_t x, uint32_t y) { return x < y ? x : y; }, s_warp, bmin);
+        s_first[tid] = ex;
+        if (tid == 0)
+            s_x = bmin;
+        __syncthreads();
+        carry_end = s_first[kLfThreads - 1 - tid];
+        cl.sync();
+        for (uint32_t k = rank + 1; k < (uint32_t)kLfCluster; k++) {
+            const uint32_t t = *cl.map_shared_rank(&s_x, k);
+            carry_end = t < carry_end ? t : carry_end;
+        }
+        cl.sync();
+    }
+    auto run_end = [&](uint32_t i) -> uint32_t {   // end of the run containing position i (i in [a, b))
+        uint32_t e = i + 1;
+        while (e < b && !starts_run(e))
+            e++;
+        return e < b ? e : carry_end;
+    };
+    const uint32_t sr0 = (a < b && !starts_run(a)) ? carry_start - 1 : a;
+    // pass 1: count
+    uint32_t count = 0;
+    {
+        uint32_t i = a, sr = sr0;
+        while (i < b) {
+            const uint32_t e = run_end(i);
+            const uint32_t v = value_at(i);
+            const uint32_t stop = e < b ? e : b;
+            for (; i < stop; i++)
+                count += lf_position_symbols(v, i, sr, e, prm).n;
+            sr = i;
+        }
+    }
+    uint32_t nsyms_total;
+    uint32_t off = cluster_exclusive_scan(cl, count, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, &s_x, nsyms_total);
+    if (nsyms_total > sym_cap)
+        my_err |= kErrLfCapacity;
+    // pass 2: emit + histogram (into this CTA's own bins)
+    if (nsyms_total <= sym_cap) {
+        uint32_t i = a, sr = sr0;
+        while (i < b) {
+            const uint32_t e = run_end(i);
+            const uint32_t v = value_at(i);
+            const uint32_t stop = e < b ? e : b;
+            for (; i < stop; i++) {
+                const LfEmit em = lf_position_symbols(v, i, sr, e, prm);
+                for (uint32_t k = 0; k < em.n; k++) {
+                    const uint32_t sym = em.sym[k];
+                    const uint32_t token = sym & 0x7FFFu, cluster = (sym >> 15) & 1u, nbits = (sym >> 16) & 0xFu;
+                    bool fits;
+                    if (cluster)
+                        fits = token < (uint32_t)kDistBins;
+                    else if (lz && token >= lz)
+                        fits = token - lz < (uint32_t)kLzBins;
+                    else
+                        fits = token < (uint32_t)kLitBins;
+                    if (!fits || nbits > 12) {
+                        my_err |= kErrLfAlphabet;
+                        syms[off++] = ps_pack(0, 0, 0, 0);
+                        continue;
+                    }
+                    syms[off++] = sym;
+                    atomicAdd(&w.freq[ps_bin(token, cluster, lz)], 1u);
+                    if (cluster)
+                        atomicMax(&w.alpha1, token + 1);
+                    else
+                        atomicMax(&w.alpha0, token + 1);
+                }
+            }
+            sr = i;
+        }
+    }
+    if (my_err)
+        atomicOr(&s_err, my_err);
+    __syncthreads();
+    // ---- the CTAs' histograms, alphabet bounds and error flags meet in CTA 0 ---------------------------
+    if (rank != 0) {
+        PrefixWork *w0 = cl.map_shared_rank(&w, 0);
+        for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads)
+            if (w.freq[i])
+                atomicAdd(&w0->freq[i], w.freq[i]);
+        if (tid == 0) {
+            atomicMax(&w0->alpha0, w.alpha0);
+            atomicMax(&w0->alpha1, w.alpha1);
+            if (s_err)
+                atomicOr(cl.map_shared_rank(&s_err, 0), s_err);
+        }
+    }
+    cl.sync();
+    // ---- CTA 0: code lengths of the literal / length cluster by its first warp, then the stream header ---
+    if (rank == 0) {
+        const bool warp_lengths = w.alpha0 > 1;
+        if (tid < 32 && warp_lengths)
+            warp_code_lengths(w, w.alpha0, 15, lz, tid);
+        __syncthreads();
+        if (tid == 0) {
+            w.nsyms = nsyms_total;
+            ps_put_header(w, bw, prm, warp_lengths);
+            bw.flush_partial();
+            s_bitpos = bw.bitlen();
+            if (bw.overflow)
+                s_err |= kErrSlab;
+            if (w.error)
+                s_err |= w.error;
+        }
+    }
+    cl.sync();
+    // ---- everyone takes the code table, the header's end and the verdict from CTA 0 ------------------------
+    if (rank != 0) {
+        const PrefixWork *w0 = cl.map_shared_rank(&w, 0);
+        for (uint32_t i = tid; i < (uint32_t)kAllBins; i += kLfThreads) {
+            w.len[i] = w0->len[i];
+            w.code[i] = w0->code[i];
+        }
+        if (tid == 0) {
+            s_bitpos = *cl.map_shared_rank(&s_bitpos, 0);
+            s_err = *cl.map_shared_rank(&s_err, 0);
+        }
+    }
+    cl.sync();   // (also: CTA 0's table is not touched again before everyone has copied it)
+    const uint32_t p0 = s_bitpos;
+    const uint32_t err_now = s_err;
+    // ---- symbol bits, in parallel: thread = contiguous range of symbols -----------------------------
+    uint32_t total_bits = 0;
+    uint32_t late_err = 0;
+    if (!err_now) {
+        const uint32_t sper = (nsyms_total + gthreads - 1) / gthreads;
+        const uint32_t sa = gid * sper < nsyms_total ? gid * sper : nsyms_total;
+        const uint32_t sb = sa + sper < nsyms_total ? sa + sper : nsyms_total;
+        uint32_t bits = 0;
+        for (uint32_t i = sa; i < sb; i++) {
+            const uint32_t sym = syms[i];
+            bits += w.len[ps_bin(sym & 0x7FFFu, (sym >> 15) & 1u, lz)] + ((sym >> 16) & 0xFu);
+        }
+        const uint32_t boff = cluster_exclusive_scan(cl, bits, 0u, [](uint32_t x, uint32_t y) { return x + y; }, s_warp, &s_x, total_bits);
+        const uint64_t endbit = (uint64_t)p0 + total_bits;
+        if (endbit + 64 > (uint64_t)out_words * 32) {
+            late_err = kErrSlab;   // uniform: every thread sees the same totals
+        } else {
+            // flush_partial() wrote word p0 >> 5 only when the header left a partial word there
+            for (uint32_t wd = ((p0 + 31) >> 5) + gid; wd <= (uint32_t)(endbit >> 5) + 1; wd += gthreads)
+                outw[wd] = 0;
+            cl.sync();   // the words are clear before any CTA ORs bits into them
+            uint64_t pos = (uint64_t)p0 + boff;
+            uint32_t wpos = (uint32_t)(pos >> 5), nacc = (uint32_t)(pos & 31u);
+            uint64_t acc = 0;
+            auto put = [&](uint32_t v, uint32_t n) {
+                acc |= (uint64_t)v << nacc;
+                nacc += n;
+                if (nacc >= 32) {
+                    atomicOr(&outw[wpos], (uint32_t)acc);
+                    wpos++;
+                    acc >>= 32;
+                    nacc -= 32;
+                }
+            };
+            for (uint32_t i = sa; i < sb; i++) {
+                const uint32_t sym = syms[i];
+                const uint32_t bin = ps_bin(sym & 0x7FFFu, (sym >> 15) & 1u, lz);
+                const uint32_t nbits = (sym >> 16) & 0xFu;
+                if (w.len[bin])
+                    put(w.code[bin], w.len[bin]);
+                if (nbits)
+                    put(sym >> 20, nbits);
+            }
+            if (nacc && (uint32_t)acc)
+                atomicOr(&outw[wpos], (uint32_t)acc);
+        }
+    }
+    cl.sync();   // all bits are in place before CTA 0's thread 0 continues behind them
+    const uint32_t err = err_now | late_err;
+    if (rank == 0 && tid == 0 && !err)
+        bw.resume(outw, out_words, p0 + total_bits);
+    return err;
+}
+
+__global__ void __cluster_dims__(kLfCluster, 1, 1) __launch_bounds__(kLfThreads)
 k_frame_lf(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
     __shared__ uint32_t s_warp[64];
     __shared__ uint32_t s_first[kLfThreads];
     __shared__ uint32_t s_resid_err;
-    const uint32_t slot = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cl = cg::this_cluster();
+    const uint32_t slot = blockIdx.x / kLfCluster, tid = threadIdx.x, rank = cl.block_rank();
+    const uint32_t gid = rank * kLfThreads + tid, gthreads = kLfCluster * kLfThreads;
     const TileDesc t = ws.tiles[slot];
     if (!(t.flags & kTilePrefix))
-        return;
+        return;   // (the whole cluster leaves: its CTAs share the slot)
     PrefixWork &w = s.work;
     const uint32_t vbw = (t.frame_w + 7) >> 3, vbh = (t.frame_h + 7) >> 3, nb = vbw * vbh, total = 3 * nb;
     uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
@@ -348,7 +604,7 @@ k_frame_lf(Workspace ws) {
     __syncthreads();
     // ---- residuals of the whole LF image, channel order Y, X, B (encoder.c:574-592) ---------------
     uint16_t *resid = reinterpret_cast<uint16_t *>(ws.coef + (size_t)slot * kMaxBlocks * 3 * 64);   // 196 608 x u16
-    for (uint32_t i = tid; i < total; i += kLfThreads) {
+    for (uint32_t i = gid; i < total; i += gthreads) {
         const uint32_t ci = i / nb, r = i - ci * nb;
         const uint32_t c = ci < 2 ? 1 - ci : ci;
         const uint32_t by = r / vbw, bx = r - by * vbw;
@@ -365,18 +621,20 @@ k_frame_lf(Workspace ws) {
             s_resid_err = kErrLfAlphabet;   // would need more than 12 residue bits: outside what the LF coder holds
         resid[i] = (uint16_t)(packed > 0xFFFFu ? 0xFFFFu : packed);
     }
-    // ---- section head (one thread; uses the prefix work area for the small MA-tree stream) ---------
+    // ---- section head (one thread of the master CTA; uses the prefix work area for the small MA-tree stream)
     BitSink bw;
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         w.error = 0;
         bw.init(outw, kOutWords);
         put_lf_group_head(w, syms, bw);
     }
+    __syncthreads();
+    const uint32_t resid_err = s_resid_err;
+    cl.sync();   // every CTA's residuals are in HBM before any CTA reads its range of them
     // ---- the LF stream ---------------------------------------------------------------------------------
-    uint32_t err = block_prefix_stream(w, bw, outw, kOutWords, syms, (uint32_t)kMaxHfSyms, lf_stream_params(), total,
-                                       ResidValues{resid}, s_warp, s_first);
-    err |= s_resid_err;
-    if (tid != 0)
+    uint32_t err = cluster_prefix_stream(cl, w, bw, outw, kOutWords, syms, (uint32_t)kMaxHfSyms, lf_stream_params(), total,
+                                         ResidValues{resid}, s_warp, s_first, resid_err);
+    if (rank != 0 || tid != 0)
         return;
     // ---- the constant HF-metadata image behind it, then the section is closed ------------------------
     err |= w.error;
@@ -908,7 +1166,7 @@ void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st
 void launch_frame_lf(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
     prefer_max_shared(k_frame_lf);
     cudaFuncSetAttribute(k_frame_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
-    k_frame_lf<<<nslots, kLfThreads, sizeof(FrameShared), st>>>(ws);
+    k_frame_lf<<<nslots * kLfCluster, kLfThreads, sizeof(FrameShared), st>>>(ws);   // one cluster per slot
 }
 
 void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st) {
