@@ -885,7 +885,7 @@ def run_ours(args) -> int:
     configs = {}
     if not args.quick:
         from hydrium_b200.engine import Engine
-        big = Engine(device=ctx.local_rank, max_batch_tiles=4096)
+        big = Engine(device=ctx.local_rank, max_batch_tiles=8192)   # 20 GB of workspace: fewer, longer launches (less tail per launch)
         for k in (3, 4, 5):
             try:
                 configs[f"config{k}"] = run_big_config(ctx, k, big)

@@ -1074,26 +1074,41 @@ HYDStatusCode hydb_encode_image_device(HydbEngine *eng, const void *d_pixels, ui
     uint64_t pos = 0;
     const uint64_t ntiles = (uint64_t)tiles_x * (tile_row_end - tile_row_begin);
     std::vector<HydbTile> tiles;
-    if (ntiles <= eng->max_batch && tile_row_end - tile_row_begin >= 2 && !eng->timing) {
-        // one batch: band-pipelined (see launch_bands); with per-kernel timing on, the plain
-        // single-stream sequence below is used so that the events bracket whole kernels
-        image_tiles(tiles, d_pixels, width, height, channels, row_stride, sample_fmt, linear_light, tile_row_begin,
-                    tile_row_end, with_header);
-        HYDStatusCode rc = prepare_tiles(eng, tiles.data(), (uint32_t)ntiles, eng->st);
-        if (rc == HYD_OK)
-            rc = launch_bands(eng, tiles_x, tile_row_end - tile_row_begin, nullptr, nullptr, 0, 0, sample_fmt == HYD_FLOAT32);
-        if (rc != HYD_OK)
-            return rc;
-        launch_gather(eng->ws, (uint32_t)ntiles, d_out, d_out_cap, 0, eng->d_overflow, eng->st);
-        eng->launches += 2;
-        rc = queue_readback(eng, (uint32_t)ntiles, 0);
-        if (rc != HYD_OK)
-            return rc;
-        uint64_t total = 0;
-        rc = hydb_engine_finish(eng, &total);
-        if (rc != HYD_OK)
-            return rc;
-        *out_len = total;
+    // Band pipelining pays while the chains are few and long (the table kernel's regime: a band's chains start
+    // while later bands are still in their front-end kernels); a launch of thousands of tiles is bound by
+    // chain throughput and every band adds a tail, so it runs as one plain sequence instead (8192 tiles of
+    // config 5: 4096-tile batches 49.6 ms plain, 55.5 ms banded).  HYDRIUM_B200_BAND_TILES moves the limit.
+    static const uint32_t band_tiles = [] { const char *e = getenv("HYDRIUM_B200_BAND_TILES"); int v = e ? atoi(e) : 0;
+                                            return (uint32_t)(v > 0 ? v : 1024); }();
+    uint32_t rows_per_batch = (eng->max_batch < band_tiles ? eng->max_batch : band_tiles) / tiles_x;
+    if (ntiles <= eng->max_batch && ntiles <= band_tiles)
+        rows_per_batch = tile_row_end - tile_row_begin;
+    if (rows_per_batch >= 2 && tile_row_end - tile_row_begin >= 2 && !eng->timing && ntiles <= band_tiles) {
+        // whole tile rows per batch, each batch band-pipelined (see launch_bands).  With per-kernel timing
+        // on, the plain single-stream sequence below is used so that the events bracket whole kernels.
+        const size_t item = sample_item_bytes(sample_fmt);
+        for (uint32_t r0 = tile_row_begin, r1; r0 < tile_row_end; r0 = r1) {
+            r1 = tile_row_end - r0 > rows_per_batch ? r0 + rows_per_batch : tile_row_end;
+            const uint32_t n = (r1 - r0) * tiles_x;
+            image_tiles(tiles, (const uint8_t *)d_pixels + (int64_t)(r0 - tile_row_begin) * 256 * row_stride * (int64_t)item, width,
+                        height, channels, row_stride, sample_fmt, linear_light, r0, r1, with_header && r0 == tile_row_begin);
+            HYDStatusCode rc = prepare_tiles(eng, tiles.data(), n, eng->st);
+            if (rc == HYD_OK)
+                rc = launch_bands(eng, tiles_x, r1 - r0, nullptr, nullptr, 0, 0, sample_fmt == HYD_FLOAT32);
+            if (rc != HYD_OK)
+                return rc;
+            launch_gather(eng->ws, n, d_out, d_out_cap, pos, eng->d_overflow, eng->st);
+            eng->launches += 2;
+            rc = queue_readback(eng, n, pos);
+            if (rc != HYD_OK)
+                return rc;
+            uint64_t total = 0;
+            rc = hydb_engine_finish(eng, &total);
+            if (rc != HYD_OK)
+                return rc;
+            pos += total;
+        }
+        *out_len = pos;
         return HYD_OK;
     }
     for (uint64_t first = 0; first < ntiles; first += eng->max_batch) {

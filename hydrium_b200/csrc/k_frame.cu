@@ -367,7 +367,8 @@ __device__ __forceinline__ uint32_t cluster_exclusive_scan(cg::cluster_group &cl
 template <typename ValueAt>
 __device__ uint32_t cluster_prefix_stream(cg::cluster_group &cl, PrefixWork &w, BitSink &bw, uint32_t *outw, uint32_t out_words,
                                           uint32_t *syms, uint32_t sym_cap, const PrefixParams &prm, uint32_t total,
-                                          ValueAt value_at, uint32_t *s_warp, uint32_t *s_first, uint32_t err_in) {
+                                          ValueAt value_at, uint32_t *s_warp, uint32_t *s_first, uint32_t err_in,
+                                          long long *stamps = nullptr) {
     __shared__ uint32_t s_bitpos, s_err, s_x;
     const uint32_t tid = threadIdx.x, rank = cl.block_rank();
     const uint32_t gid = rank * kLfThreads + tid, gthreads = kLfCluster * kLfThreads;
@@ -493,6 +494,8 @@ __device__ uint32_t cluster_prefix_stream(cg::cluster_group &cl, PrefixWork &w, 
         }
     }
     cl.sync();
+    if (stamps)
+        stamps[0] = clock64();   // symbols emitted, histograms merged
     // ---- CTA 0: code lengths of the literal / length cluster by its first warp, then the stream header ---
     if (rank == 0) {
         const bool warp_lengths = w.alpha0 > 1;
@@ -511,6 +514,8 @@ __device__ uint32_t cluster_prefix_stream(cg::cluster_group &cl, PrefixWork &w, 
         }
     }
     cl.sync();
+    if (stamps)
+        stamps[1] = clock64();   // code built, stream header written
     // ---- everyone takes the code table, the header's end and the verdict from CTA 0 ------------------------
     if (rank != 0) {
         const PrefixWork *w0 = cl.map_shared_rank(&w, 0);
@@ -593,6 +598,8 @@ k_frame_lf(Workspace ws) {
     const TileDesc t = ws.tiles[slot];
     if (!(t.flags & kTilePrefix))
         return;   // (the whole cluster leaves: its CTAs share the slot)
+    const long long clk0 = clock64();
+    long long stamps[2] = {0, 0};
     PrefixWork &w = s.work;
     const uint32_t vbw = (t.frame_w + 7) >> 3, vbh = (t.frame_h + 7) >> 3, nb = vbw * vbh, total = 3 * nb;
     uint32_t *syms = ws.syms + (size_t)slot * kMaxHfSyms;
@@ -631,11 +638,13 @@ k_frame_lf(Workspace ws) {
     __syncthreads();
     const uint32_t resid_err = s_resid_err;
     cl.sync();   // every CTA's residuals are in HBM before any CTA reads its range of them
+    const long long clk1 = clock64();
     // ---- the LF stream ---------------------------------------------------------------------------------
     uint32_t err = cluster_prefix_stream(cl, w, bw, outw, kOutWords, syms, (uint32_t)kMaxHfSyms, lf_stream_params(), total,
-                                         ResidValues{resid}, s_warp, s_first, resid_err);
+                                         ResidValues{resid}, s_warp, s_first, resid_err, ws.dbg_clk ? stamps : nullptr);
     if (rank != 0 || tid != 0)
         return;
+    const long long clk2 = clock64();
     // ---- the constant HF-metadata image behind it, then the section is closed ------------------------
     err |= w.error;
     if (!err) {
@@ -651,6 +660,12 @@ k_frame_lf(Workspace ws) {
     }
     if (err)
         atomicOr(&ws.tile_err[slot], err);
+    if (ws.dbg_clk) {   // stage-tap builds: cycles of residuals + section head, symbols, code + header, (bits, HF metadata)
+        ws.dbg_clk[slot * 4 + 0] = (uint32_t)(clk1 - clk0);
+        ws.dbg_clk[slot * 4 + 1] = (uint32_t)(stamps[0] - clk1);
+        ws.dbg_clk[slot * 4 + 2] = (uint32_t)(stamps[1] - stamps[0]);
+        ws.dbg_clk[slot * 4 + 3] = (uint32_t)(clk2 - stamps[1]) | ((uint32_t)((clock64() - clk2) >> 8) << 20);
+    }
 }
 
 struct ClusterMapMtf {
