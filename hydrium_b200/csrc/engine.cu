@@ -10,6 +10,7 @@
 //   st : [descs H2D] -> k_xyb_dct_quant -+-> k_hf_tokens ------+-> k_ans_encode -> k_frame_offsets -> k_gather_frames
 //   st2:                                  +-> k_lf_group -------+
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,6 +24,12 @@
 #include "kernels.h"
 
 using namespace hydb;
+
+// NVTX range over the host-side enqueue of one stage (nsys / ncu --nvtx show the pipeline by name)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct HydbEngine {
     int device = 0;
@@ -456,23 +463,24 @@ static HYDStatusCode queue_readback(HydbEngine *eng, uint32_t n, uint64_t d_out_
 static HYDStatusCode enqueue_tile_kernels(HydbEngine *eng, const Workspace &v, uint32_t n, cudaStream_t st, cudaStream_t st2,
                                           cudaEvent_t ev_front, cudaEvent_t ev_lf, bool allow_compact, uint8_t *out,
                                           uint64_t out_cap, uint64_t out_pos, uint32_t *d_ovf, bool tm) {
+    NvtxRange range("hydb:tile_batch");
     if (tm) CK(cudaEventRecord(eng->tev[0], st));
-    launch_xyb_dct_quant(v, eng->luts, n, st);
+    { NvtxRange r("hydb:xyb_dct_quant"); launch_xyb_dct_quant(v, eng->luts, n, st); }
     if (tm) CK(cudaEventRecord(eng->tev[1], st));
     CK(cudaEventRecord(ev_front, st));
     CK(cudaStreamWaitEvent(st2, ev_front, 0));
     if (tm) CK(cudaEventRecord(eng->lev[0], st2));
-    launch_lf_group(v, n, st2);
+    { NvtxRange r("hydb:lf_group"); launch_lf_group(v, n, st2); }
     if (tm) CK(cudaEventRecord(eng->lev[1], st2));
     CK(cudaEventRecord(ev_lf, st2));
-    launch_hf_tokens(v, n, st);
+    { NvtxRange r("hydb:hf_tokens"); launch_hf_tokens(v, n, st); }
     if (tm) CK(cudaEventRecord(eng->tev[2], st));
-    launch_ans_chain(v, n, st, allow_compact);
+    { NvtxRange r("hydb:ans_chain"); launch_ans_chain(v, n, st, allow_compact); }
     if (tm) CK(cudaEventRecord(eng->tev[3], st));
     CK(cudaStreamWaitEvent(st, ev_lf, 0));   // the LF stream is first needed by the packer
-    launch_ans_pack(v, eng->templ, n, st);
+    { NvtxRange r("hydb:ans_pack"); launch_ans_pack(v, eng->templ, n, st); }
     if (tm) CK(cudaEventRecord(eng->tev[4], st));
-    launch_gather(v, n, out, out_cap, out_pos, d_ovf, st);
+    { NvtxRange r("hydb:gather"); launch_gather(v, n, out, out_cap, out_pos, d_ovf, st); }
     if (tm) CK(cudaEventRecord(eng->tev[5], st));
     eng->launches += 7;
     return HYD_OK;
@@ -589,6 +597,7 @@ static HYDStatusCode expand_frames(HydbEngine *eng, const HydbFrame *frames, uin
 static HYDStatusCode enqueue_frame_kernels(HydbEngine *eng, const Workspace &v, uint32_t slots, cudaStream_t st,
                                            cudaStream_t st2, cudaEvent_t ev_front, cudaEvent_t ev_lf, bool allow_compact,
                                            uint8_t *out, uint64_t out_cap, uint64_t out_pos, uint32_t *d_ovf) {
+    NvtxRange range("hydb:frame_batch");
     launch_xyb_dct_quant(v, eng->luts, slots, st);
     CK(cudaEventRecord(ev_front, st));
     CK(cudaStreamWaitEvent(st2, ev_front, 0));
@@ -666,6 +675,7 @@ HYDStatusCode hydb_engine_submit_frames(HydbEngine *eng, const HydbFrame *frames
         eng->error = "no free job: poll and release a finished one first";
         return HYD_API_ERROR;
     }
+    NvtxRange range("hydb:submit_job");
     std::vector<HydbTile> tiles;
     std::vector<SlotExtra> extra;
     bool any_multi = false;
@@ -991,6 +1001,7 @@ static void image_tiles(std::vector<HydbTile> &tiles, const void *base, uint32_t
 // order-dependent; the caller gathers all tiles afterwards on eng->st, which waits for every band.
 static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t rows, const void *h_src, void *d_dst,
                                   size_t row_bytes, uint32_t pixel_rows, bool any_float) {
+    NvtxRange range("hydb:band_pipeline");
     // HYDRIUM_B200_BANDTRACE=1: print when each band's stages started / ended (development aid; synchronises)
     static const bool trace = [] { const char *e = getenv("HYDRIUM_B200_BANDTRACE"); return e && e[0] == '1'; }();
     static cudaEvent_t tr[1 + HydbEngine::kBands * 5];

@@ -110,3 +110,33 @@ def test_image_headers(oracle):
         assert oracle.image_header(w, h).hex() == hx
     big = oracle.image_header(65536, 65536)
     assert len(big) == 59 and big[49:].hex() == "ff0afcff07feff033201" and big[4:8] == b"JXL "
+
+
+def test_bench_sampled_tile_reference_driver(reflib):
+    """bench.py's parity leg drives the unmodified reference with the full image's metadata and only a
+    few tiles (gaps are legal, libhydrium.h:235-240) and cuts our stream at the engine's frame lengths.
+    Here, on the CPU: the frames that driver returns, in any order and from a window of the image, are
+    exactly the pieces of the reference's own whole-image stream."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from hydrium_b200.encoder import encode_cli_loop
+    from hydrium_b200.synth import synth_image
+    img = synth_image(1100, 800, 8, seed=3)            # 5 x 4 tiles, partial right / bottom tiles
+    whole = encode_cli_loop(reflib, img)
+    tiles = [(x, y) for y in range(4) for x in range(5)]
+    frames = bench.ref_encode_tiles(reflib, img, 1100, 800, tiles)
+    assert b"".join(frames) == whole
+    # a subset in another order: same frames (position-, not order-dependent), image header stripped
+    sub = [(4, 3), (0, 0), (2, 1)]
+    got = bench.ref_encode_tiles(reflib, img, 1100, 800, sub)
+    hdr = len(frames[0]) - len(bench.ref_encode_tiles(reflib, img, 1100, 800, [(1, 0), (0, 0)])[1])
+    assert got[0] == frames[19] and got[2] == frames[7]
+    assert got[1] == frames[0][hdr:]                   # (0, 0) sent second carries no image header
+    # a window of the image whose upper-left tile is (1, 2), 16-bit linear
+    img16 = synth_image(700, 900, 16, seed=5)
+    all16 = bench.ref_encode_tiles(reflib, img16, 700, 900, [(x, y) for y in range(4) for x in range(3)], linear=1)
+    win = np.ascontiguousarray(img16[512:, 256:])
+    part = bench.ref_encode_tiles(reflib, win, 700, 900, [(1, 2), (2, 3)], linear=1, origin=(1, 2))
+    assert part[0] == all16[2 * 3 + 1] and part[1] == all16[3 * 3 + 2]
