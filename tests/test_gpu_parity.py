@@ -154,6 +154,24 @@ def test_compact_chain_kernel(product_lib, oracle):
             eng.device_free(d_out)
     assert outs[0] == outs[1] == outs[2]
     assert outs[1] == oracle.encode_image(img)
+    # 512 tiles: more chains than the table kernel keeps resident (296) but below the compact kernel's
+    # threshold -- two rounds of the table kernel (band-pipelined whole image, and one plain batch through
+    # hydb_engine_encode_tiles)
+    w, h = 4096, 32 * 256
+    with E.Engine(device=0, max_batch_tiles=512) as eng:
+        d_in, cap = eng.device_alloc(w * h * 3), E.output_bound(w, h)
+        d_out = eng.device_alloc(cap)
+        eng.synth_fill(d_in, w, h, bits=8, seed=9)
+        got = eng.download(d_out, eng.encode_image_device(d_in, w, h, 3, d_out=d_out, d_out_cap=cap))
+        img = np.frombuffer(eng.download(d_in, w * h * 3), np.uint8).reshape(h, w, 3)
+        want = oracle.encode_image(img)
+        assert got == want, "512 tiles, band pipeline"
+        tiles = [_tile_desc(d_in, img, tx, ty, 0) for ty in range(32) for tx in range(16)]
+        tiles[0].with_image_header = 1
+        n = eng.encode_tiles(tiles, d_out, cap)
+        assert eng.download(d_out, n) == want, "512 tiles, one batch"
+        eng.device_free(d_in)
+        eng.device_free(d_out)
 
 
 def test_batches_larger_than_the_workspace(product_lib, oracle):
