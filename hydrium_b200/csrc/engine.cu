@@ -185,6 +185,7 @@ HYDStatusCode hydb_engine_create(HydbEngine **out, int device, uint32_t max_batc
     A(dalloc(&w.tile_err, T));
     A(dalloc(&w.sm_ticket, 256));
     A(cudaMemsetAsync(w.sm_ticket, 0, 256 * sizeof(uint32_t), eng->st));
+    A(dalloc(&w.chain_order, T));
     A(dalloc(&w.sm_load, 1024));
     A(cudaMemsetAsync(w.sm_load, 0, 1024 * sizeof(uint32_t), eng->st));
     A(dalloc(&eng->lut8_srgb, 256));
@@ -244,7 +245,7 @@ void hydb_engine_destroy(HydbEngine *eng) {
     if (eng->st2) cudaStreamSynchronize(eng->st2);
     Workspace &w = eng->ws;
     void *dev[] = {w.tiles, w.coef, w.nzinfo, w.lfq, w.syms, w.nsyms, w.resbits, w.hist, w.lfbits, w.lfbitlen, w.flags, w.dbits, w.chain_out,
-                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.sm_ticket, w.sm_load, w.dbg_xyb, w.dbg_dct,
+                   w.fwords, w.slab, w.frame_off, w.frame_len, w.out_off, w.tile_err, w.sm_ticket, w.sm_load, w.chain_order, w.dbg_xyb, w.dbg_dct,
                    w.dbg_freqs, w.dbg_sect, w.dbg_clk, eng->lut8_srgb, eng->lut8_lin, eng->lut16_srgb, eng->lut16_lin, eng->bias,
                    eng->templ.words, eng->templ.bits, eng->d_shape_dims, eng->d_overflow};
     for (void *p : dev)
@@ -357,6 +358,7 @@ static Workspace ws_view(const Workspace &w, uint32_t first) {
     v.frame_len += f;
     v.out_off += 2 * f;
     v.tile_err += f;
+    v.chain_order += f;
     if (v.dbg_xyb) v.dbg_xyb += f * 65536 * 3;
     if (v.dbg_dct) v.dbg_dct += f * 65536 * 3;
     if (v.dbg_freqs) v.dbg_freqs += f * kHfClusters * kHfTokens;
@@ -475,7 +477,7 @@ static HYDStatusCode enqueue_tile_kernels(HydbEngine *eng, const Workspace &v, u
     CK(cudaEventRecord(ev_lf, st2));
     { NvtxRange r("hydb:hf_tokens"); launch_hf_tokens(v, n, st); }
     if (tm) CK(cudaEventRecord(eng->tev[2], st));
-    { NvtxRange r("hydb:ans_chain"); launch_ans_chain(v, n, st, allow_compact); }
+    { NvtxRange r("hydb:ans_chain"); launch_ans_chain(v, n, st, allow_compact, 0, true); }
     if (tm) CK(cudaEventRecord(eng->tev[3], st));
     CK(cudaStreamWaitEvent(st, ev_lf, 0));   // the LF stream is first needed by the packer
     { NvtxRange r("hydb:ans_pack"); launch_ans_pack(v, eng->templ, n, st); }
@@ -1044,7 +1046,7 @@ static HYDStatusCode launch_bands(HydbEngine *eng, uint32_t tiles_x, uint32_t ro
         CK(cudaEventRecord(eng->band_lf[b], sb2));
         launch_hf_tokens(v, n, sb);
         if (trace) cudaEventRecord(tr[1 + b * 5 + 2], sb);
-        launch_ans_chain(v, n, sb, !any_float, rows * tiles_x);
+        launch_ans_chain(v, n, sb, !any_float, rows * tiles_x, true);
         if (trace) cudaEventRecord(tr[1 + b * 5 + 3], sb);
         CK(cudaStreamWaitEvent(sb, eng->band_lf[b], 0));
         launch_ans_pack(v, eng->templ, n, sb);

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kAnsThreads)
 k_ans_chain(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AnsShared &s = *reinterpret_cast<AnsShared *>(smem_raw);
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = ws.chain_lpt ? ws.chain_order[blockIdx.x] : blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (ws.tiles[tile].flags & kTilePrefix)   // pseudo-tile of a multi-group frame (k_frame.cu)
         return;
     const uint32_t N = ws.nsyms[tile];
@@ -690,18 +691,43 @@ static uint32_t chain_table_limit() {
     return lim;
 }
 
-void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact, uint32_t concurrent_tiles) {
+// rank of every tile by symbol count (descending, ties by index): chain_order[rank] = tile
+__global__ void __launch_bounds__(256)
+k_chain_order(Workspace ws, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t mine = ws.nsyms[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t o = ws.nsyms[j];
+        rank += (o > mine || (o == mine && j < i)) ? 1u : 0u;
+    }
+    ws.chain_order[rank] = i;
+}
+
+void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact, uint32_t concurrent_tiles,
+                      bool longest_first) {
     const int mode = ws.chain_mode ? (int)ws.chain_mode : chain_mode_override();
     // what counts is how many chains compete for the GPU at once: a band of a larger batch is launched next
     // to its sibling bands on other streams
     const uint32_t competing = concurrent_tiles > ntiles ? concurrent_tiles : ntiles;
-    if (allow_compact && (mode == 2 || (mode == 0 && competing > chain_table_limit()))) {
-        launch_ans_chain_compact(ws, ntiles, st);
+    const bool compact = allow_compact && (mode == 2 || (mode == 0 && competing > chain_table_limit()));
+    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    static const bool lpt_on = [] { const char *e = getenv("HYDRIUM_B200_CHAIN_LPT"); return !(e && e[0] == '0'); }();
+    Workspace w = ws;
+    w.chain_lpt = 0;
+    if (longest_first && lpt_on && competing > (uint32_t)(compact ? 16 * sms : 2 * sms)) {
+        k_chain_order<<<(ntiles + 255) / 256, 256, 0, st>>>(ws, ntiles);
+        w.chain_lpt = 1;
+    }
+    if (compact) {
+        launch_ans_chain_compact(w, ntiles, st);
         return;
     }
     cudaFuncSetAttribute(k_ans_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsShared));
     prefer_max_shared(k_ans_chain);
-    k_ans_chain<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(ws);
+    k_ans_chain<<<ntiles, kAnsThreads, sizeof(AnsShared), st>>>(w);
 }
 
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st) {

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kCThreads, 16)
 k_ans_chain_compact(Workspace ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CompactShared &s = *reinterpret_cast<CompactShared *>(smem_raw);
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = ws.chain_lpt ? ws.chain_order[blockIdx.x] : blockIdx.x;   // longest chains first
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileDesc &td = ws.tiles[tile];
     if (td.flags & kTilePrefix)
         return;

@@ -21,6 +21,7 @@ struct LutSet {
 struct Workspace {
     uint32_t capacity;        // tiles
     uint32_t chain_mode;      // 0 choose by launch size, 1 table kernel, 2 compact kernel (hydb_engine_set_chain_kernel)
+    uint32_t chain_lpt;       // set by the launcher: chain CTA b codes tile chain_order[b] (longest chains first)
     TileDesc *tiles;          // [T]
     int16_t *coef;            // [T][1024 blocks (row stride 32)][3 channels X,Y,B][64 scan order]
     uint16_t *nzinfo;         // [T][1024][3]  nz count | last scan index << 8
@@ -42,6 +43,7 @@ struct Workspace {
     uint32_t *tile_err;       // [T] TileError bits
     uint32_t *sm_ticket;      // [256] per-SM ticket counter (spreads chain warps over sub-partitions)
     uint32_t *sm_load;        // [256][4] chain warps currently running per SM sub-partition (k_ans_chain_compact)
+    uint32_t *chain_order;    // [T] tiles of the launch by descending symbol count (launches with more chains than fit at once)
     // optional stage taps for the parity tests (NULL in production)
     float *dbg_xyb, *dbg_dct; // [T][256][256][3]
     uint32_t *dbg_freqs;      // [T][9][64] normalised frequencies
@@ -65,8 +67,11 @@ void launch_hf_tokens(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 void launch_lf_group(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 // allow_compact: no HYD_FLOAT32 tile in the launch (tokens stay below 32); large launches then take
 // k_ans_chain_compact (sixteen chains per SM), small ones the table kernel (two per SM, shorter steps)
+// longest_first: the launch holds plain tiles (every slot has a symbol count): when it has more chains than
+// the GPU keeps resident, the CTAs take the tiles by descending symbol count, so that the chains that start
+// last are the short ones (the launch ends when its last chain does)
 void launch_ans_chain(const Workspace &ws, uint32_t ntiles, cudaStream_t st, bool allow_compact = true,
-                      uint32_t concurrent_tiles = 0);
+                      uint32_t concurrent_tiles = 0, bool longest_first = false);
 void launch_ans_chain_compact(const Workspace &ws, uint32_t ntiles, cudaStream_t st);
 int ans_compact_smem_bytes();
 void launch_ans_pack(const Workspace &ws, const Templates &t, uint32_t ntiles, cudaStream_t st);
