@@ -22,6 +22,7 @@
 #include "../../include/hydrium_b200.h"
 #include "headers.cuh"
 #include "kernels.h"
+#include "sections.cuh"
 
 using namespace hydb;
 
@@ -431,15 +432,30 @@ static HYDStatusCode prepare_tiles(HydbEngine *eng, const HydbTile *tiles, uint3
         }
     }
     if (!fresh.empty()) {
-        std::vector<uint32_t> dims;
-        for (uint32_t k : fresh) {
-            dims.push_back(k >> 16);
-            dims.push_back(k & 0xFFFF);
+        // Section B of a new tile shape (nb_blocks, the zero-predictor MA tree, the constant HF-metadata image:
+        // encoder.c:598-626) depends on nothing but the shape.  It is a strictly sequential bit string of a
+        // few hundred bits: one GPU thread needed 0.8-1.4 ms for it (k_build_templates, round 1), the host
+        // runs the same source (sections.cuh, compiled for both sides) in microseconds and uploads the words.
+        std::vector<uint32_t> words((size_t)fresh.size() * kTemplWords, 0u), bits(fresh.size(), 0u);
+        std::vector<uint32_t> syms(kSectionSymCap);
+        PrefixWork *work = new (std::nothrow) PrefixWork();
+        if (!work) {
+            eng->error = "out of memory";
+            return HYD_NOMEM;
         }
-        CK(cudaMemcpyAsync(eng->d_shape_dims, dims.data(), dims.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        launch_build_templates(eng->templ, eng->d_shape_dims, first_fresh, (uint32_t)fresh.size(), false, st);
-        eng->launches++;
-        CK(cudaStreamSynchronize(st));   // dims is a stack-lifetime buffer
+        for (size_t k = 0; k < fresh.size(); k++) {
+            memset(work, 0, sizeof(*work));
+            BitSink bw;
+            bw.init(words.data() + k * kTemplWords, kTemplWords);
+            build_section_b(*work, syms.data(), bw, fresh[k] >> 16, fresh[k] & 0xFFFF);
+            bw.flush_partial();
+            bits[k] = (bw.overflow || work->error) ? 0xFFFFFFFFu : bw.bitlen();
+        }
+        delete work;
+        CK(cudaMemcpyAsync(eng->templ.words + (size_t)(1 + first_fresh) * kTemplWords, words.data(), words.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(eng->templ.bits + 1 + first_fresh, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // other streams (jobs, bands) may use the shape from now on
     }
     // pageable source: the runtime stages it before returning, so h_tiles may be reused immediately
     CK(cudaMemcpyAsync(eng->ws.tiles + slot0, h_tiles, n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));

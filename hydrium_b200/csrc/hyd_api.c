@@ -481,14 +481,17 @@ static HYDStatusCode gpu_error(HYDEncoder *enc, HYDStatusCode rc) {
  * device twin, a page-locked output area and a range of workspace slots.  hyd_send_tile fills the current
  * chunk and submits it when it is full (or holds the last tile); up to `nchunks` are in flight, so the
  * staging copy of later tiles runs while the GPU encodes earlier ones, and hyd_flush only ever copies
- * finished bytes.  One set is kept alive across encoders (creating the CUDA workspace and the page-locked
- * memory costs far more than encoding an image): hyd_encoder_destroy parks it, the next encoder with the
- * same geometry takes it back.  Distinct encoders may live on different threads, hence the mutex. */
+ * finished bytes.  Up to three sets are kept alive across encoders (creating the CUDA workspace and the
+ * page-locked memory costs far more than encoding an image): hyd_encoder_destroy parks its set, the next
+ * encoder with the same geometry takes it back, the least recently parked one makes room.  Distinct encoders
+ * may live on different threads, hence the mutex. */
+#define PARKED_MAX 3   /* e.g. tile mode, one-frame mode and a second device alternate without rebuilding */
 static struct {
     pthread_mutex_t lock;
-    int valid;
-    Gpu gpu;
-} g_parked = {PTHREAD_MUTEX_INITIALIZER, 0, {0}};
+    int valid[PARKED_MAX];
+    uint64_t stamp[PARKED_MAX], clock;
+    Gpu gpu[PARKED_MAX];
+} g_parked = {PTHREAD_MUTEX_INITIALIZER, {0}, {0}, 0, {{0}}};
 
 static void gpu_free(Gpu *g) {
     if (g->stage_host) hydb_host_free(g->stage_host);
@@ -545,10 +548,22 @@ static void release_gpu(HYDEncoder *enc) {
     pthread_mutex_lock(&g_parked.lock);
     Gpu stale;
     memset(&stale, 0, sizeof(stale));
-    if (g_parked.valid)
-        stale = g_parked.gpu;   /* the most recent geometry is the one most likely to come back */
-    g_parked.gpu = enc->gpu;
-    g_parked.valid = 1;
+    int slot = -1;
+    for (int i = 0; i < PARKED_MAX; i++)
+        if (!g_parked.valid[i]) {
+            slot = i;
+            break;
+        }
+    if (slot < 0) {   /* all taken: the least recently parked set goes */
+        slot = 0;
+        for (int i = 1; i < PARKED_MAX; i++)
+            if (g_parked.stamp[i] < g_parked.stamp[slot])
+                slot = i;
+        stale = g_parked.gpu[slot];
+    }
+    g_parked.gpu[slot] = enc->gpu;
+    g_parked.valid[slot] = 1;
+    g_parked.stamp[slot] = ++g_parked.clock;
     pthread_mutex_unlock(&g_parked.lock);
     memset(&enc->gpu, 0, sizeof(enc->gpu));
     gpu_free(&stale);
@@ -619,17 +634,13 @@ static HYDStatusCode ensure_gpu(HYDEncoder *enc, size_t item) {
         release_gpu(enc);
     }
     pthread_mutex_lock(&g_parked.lock);
-    Gpu stale;
-    memset(&stale, 0, sizeof(stale));
-    if (g_parked.valid) {
-        g_parked.valid = 0;
-        if (gpu_same_shape(&g_parked.gpu, &want))
-            enc->gpu = g_parked.gpu;
-        else
-            stale = g_parked.gpu;
-    }
+    for (int i = 0; i < PARKED_MAX; i++)
+        if (g_parked.valid[i] && gpu_same_shape(&g_parked.gpu[i], &want)) {
+            g_parked.valid[i] = 0;
+            enc->gpu = g_parked.gpu[i];
+            break;
+        }
     pthread_mutex_unlock(&g_parked.lock);
-    gpu_free(&stale);
     if (!enc->gpu.engine) {
         enc->gpu = want;
         Gpu *g = &enc->gpu;
