@@ -48,6 +48,7 @@ enum TileError : uint32_t {
     kErrLfAlphabet = 1u << 6,     // more distinct LF tokens than the sparse coder holds
     kErrNonFinite = 1u << 7,      // NaN / Inf float sample (reference: format.c:123-126 "Invalid NaN Float")
     kErrRange = 1u << 8,          // quantised HF coefficient outside int16 (float samples far outside [0, 1])
+    kErrNegative = 1u << 9,       // float samples whose opsin mix is negative (the reference's result is undefined there)
 };
 
 // Device-visible tile descriptor (mirrors what hyd_send_tile is given,

@@ -105,6 +105,7 @@ static size_t sample_item_bytes(int sample_fmt) {
 
 static const char *tile_error_text(uint32_t bits) {
     if (bits & kErrNonFinite) return "Invalid NaN Float";                 // reference: format.c:124
+    if (bits & kErrNegative) return "float samples with a negative opsin mix cannot be encoded (the reference's cube root is undefined there)";
     if (bits & kErrRange) return "HF coefficient exceeds the 16-bit range of the B200 encoder (float samples far outside [0, 1])";
     if (bits & kErrAlphabet) return "HF token alphabet exceeds 64 symbols";
     if (bits & kErrHuffman) return "couldn't find target";               // reference: entropy.c:635
@@ -758,7 +759,7 @@ HYDStatusCode hydb_engine_job_poll(HydbEngine *eng, uint32_t job, int wait, uint
     const uint32_t err = (uint32_t)res & 0x7FFFFFFFu;
     if (err) {
         eng->error = tile_error_text(err);
-        return (err & kErrNonFinite) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
+        return (err & (kErrNonFinite | kErrNegative)) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
     }
     return (res >> 31) & 1u ? HYD_NEED_MORE_OUTPUT : HYD_OK;
 }
@@ -929,7 +930,7 @@ HYDStatusCode hydb_engine_finish(HydbEngine *eng, uint64_t *batch_bytes) {
     for (uint32_t i = 0; i < eng->last_n; i++) {
         if (eng->h_err[i]) {
             eng->error = tile_error_text(eng->h_err[i]);
-            return (eng->h_err[i] & kErrNonFinite) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
+            return (eng->h_err[i] & (kErrNonFinite | kErrNegative)) ? HYD_API_ERROR : HYD_INTERNAL_ERROR;
         }
     }
     if (eng->last_n && eng->h_err[eng->max_batch]) {

@@ -210,13 +210,15 @@ __device__ __forceinline__ void load_xyb_staged(const TileDesc &t, const uint16_
 }
 
 // HYD_FLOAT32 samples: no tables, the transfer curve and the opsin mix are evaluated per pixel in the
-// reference's operation order (format.c:38-46, 111-140).  Returns false for a NaN / Inf sample.
-__device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uint32_t px0, uint32_t y, float (&X)[8],
-                                             float (&Y)[8], float (&B)[8]) {
+// reference's operation order (format.c:38-46, 111-140).  Returns 0, or kErrNonFinite for a NaN / Inf sample,
+// or kErrNegative when an opsin mix (plus bias) is negative: the reference's bit-hack cube root then yields
+// NaN and its conversion to int is undefined in C (INT_MIN on x86) -- there is nothing to be bit-exact with.
+__device__ __forceinline__ uint32_t load_xyb_f32(const TileDesc &t, bool linear, uint32_t px0, uint32_t y, float (&X)[8],
+                                                 float (&Y)[8], float (&B)[8]) {
     const float *p0 = (const float *)t.plane[0];
     const float *p1 = (const float *)t.plane[1];
     const float *p2 = (const float *)t.plane[2];
-    bool finite = true;
+    bool finite = true, nonneg = true;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t px = px0 + i;
@@ -234,9 +236,12 @@ __device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uin
             auto mix = [&](float c0, float c1, float c2) {
                 return __fadd_rn(__fadd_rn(__fmul_rn(c0, r), __fmul_rn(c1, g)), __fmul_rn(c2, bl));
             };
-            const float l = opsin_bias(mix(0.3f, 0.622f, 0.078f));
-            const float m = opsin_bias(mix(0.23f, 0.692f, 0.078f));
-            const float s = opsin_bias(mix(0.243423f, 0.204767f, 0.55181f));
+            const float ml = mix(0.3f, 0.622f, 0.078f), mm = mix(0.23f, 0.692f, 0.078f), ms = mix(0.243423f, 0.204767f, 0.55181f);
+            const float kBias = 0.0037930732552754493f;   // what opsin_bias adds before the cube root
+            nonneg = nonneg && !(__fadd_rn(ml, kBias) < 0.0f) && !(__fadd_rn(mm, kBias) < 0.0f) && !(__fadd_rn(ms, kBias) < 0.0f);
+            const float l = opsin_bias(ml);
+            const float m = opsin_bias(mm);
+            const float s = opsin_bias(ms);
             yy = __fmul_rn(__fadd_rn(l, m), 0.5f);
             x = __fsub_rn(yy, m);
             b = __fsub_rn(s, yy);
@@ -245,7 +250,7 @@ __device__ __forceinline__ bool load_xyb_f32(const TileDesc &t, bool linear, uin
         Y[i] = yy;
         B[i] = b;
     }
-    return finite;
+    return (finite ? 0u : (uint32_t)kErrNonFinite) | ((nonneg || !finite) ? 0u : (uint32_t)kErrNegative);
 }
 
 __global__ void __launch_bounds__(256)
@@ -292,8 +297,9 @@ k_xyb_dct_quant(const TileDesc *__restrict__ tiles, LutSet luts, int16_t *__rest
     float v[3][8];
     if (b < vbw) {
         if (fmt32) {
-            if (!load_xyb_f32(t, linear, b * 8, by * 8 + r, v[0], v[1], v[2]))
-                atomicOr(&tile_err[tile], (uint32_t)kErrNonFinite);
+            const uint32_t bad = load_xyb_f32(t, linear, b * 8, by * 8 + r, v[0], v[1], v[2]);
+            if (bad)
+                atomicOr(&tile_err[tile], bad);
         } else if (staged) {
             mbar_wait((uint32_t)__cvta_generic_to_shared(&s_mbar), 0);
             if (fmt16)

@@ -388,6 +388,89 @@ def test_float_samples_beyond_the_16_bit_coefficient_range(product_lib, reflib):
         assert want is not None and got == want, scale
 
 
+def test_engine_jobs_api(product_lib, oracle):
+    """hydb_engine_submit_frames / job_poll / job_regather / job_release (include/hydrium_b200.h): two jobs in
+    flight on disjoint workspace slots, one gathering into device memory and one straight into page-locked
+    host memory, pixels copied from page-locked staging by the job itself; an output area that is too small
+    answers HYD_NEED_MORE_OUTPUT and the frames are gathered again."""
+    from hydrium_b200.lib import load_library
+
+    class HydbFrame(C.Structure):
+        _fields_ = [("plane", C.c_void_p * 3), ("row_stride", C.c_int64), ("pixel_stride", C.c_int64),
+                    ("width", C.c_uint32), ("height", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32),
+                    ("image_width", C.c_uint32), ("image_height", C.c_uint32), ("is_last", C.c_int32),
+                    ("sample_fmt", C.c_int32), ("linear_light", C.c_int32), ("with_image_header", C.c_int32),
+                    ("one_frame", C.c_int32), ("lf_part", C.c_int32), ("preset", C.c_uint32), ("preset_bits", C.c_uint32),
+                    ("alpha_floor", C.c_uint32), ("clusters_per_preset", C.c_uint32)]
+
+    lib = load_library()
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.hydb_engine_submit_frames.restype = C.c_int
+    lib.hydb_engine_submit_frames.argtypes = [vp, vp, u32, u32, vp, vp, C.c_size_t, vp, u64, C.POINTER(u32), C.POINTER(u32)]
+    lib.hydb_engine_job_poll.restype = C.c_int
+    lib.hydb_engine_job_poll.argtypes = [vp, u32, C.c_int, C.POINTER(u64)]
+    lib.hydb_engine_job_regather.restype = C.c_int
+    lib.hydb_engine_job_regather.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+    lib.hydb_engine_job_release.restype = C.c_int
+    lib.hydb_engine_job_release.argtypes = [vp, u32]
+    imgs = [synth_image(512, 256, 8, seed=21), synth_image(700, 200, 8, seed=22)]   # 2 and 3 tiles in a row
+    with E.Engine(device=0, max_batch_tiles=8) as eng:
+        jobs = []
+        for k, img in enumerate(imgs):
+            h, w, _ = img.shape
+            n_in = img.nbytes
+            h_stage = lib.hydb_host_alloc(n_in)
+            C.memmove(h_stage, img.ctypes.data, n_in)
+            d_stage = eng.device_alloc(n_in)
+            ntx = (w + 255) // 256
+            frames = (HydbFrame * ntx)()
+            for tx in range(ntx):
+                f = frames[tx]
+                p = d_stage + tx * 256 * 3
+                f.plane = (C.c_void_p * 3)(p, p + 1, p + 2)
+                f.row_stride, f.pixel_stride = w * 3, 3
+                f.width, f.height, f.x0, f.y0 = min(256, w - tx * 256), h, tx * 256, 0
+                f.image_width, f.image_height = w, h
+                f.is_last, f.sample_fmt, f.with_image_header = int(tx == ntx - 1), HYD_UINT8, int(tx == 0)
+            cap = 1 << 20
+            out_host = lib.hydb_host_alloc(cap) if k == 1 else None
+            out = out_host if k == 1 else eng.device_alloc(cap)
+            job, slots = u32(0), u32(0)
+            eng._check(lib.hydb_engine_submit_frames(eng._h, frames, ntx, 4 * k, h_stage, d_stage, n_in, out, cap, C.byref(job), C.byref(slots)))
+            assert slots.value == ntx
+            jobs.append((job.value, out, out_host, h_stage, d_stage, img))
+        for job, out, out_host, h_stage, d_stage, img in jobs:
+            nbytes = u64(0)
+            eng._check(lib.hydb_engine_job_poll(eng._h, job, 1, C.byref(nbytes)))
+            got = C.string_at(out_host, nbytes.value) if out_host else eng.download(out, nbytes.value)
+            assert got == oracle.encode_image(img)
+            eng._check(lib.hydb_engine_job_release(eng._h, job))
+        # too small an output area: HYD_NEED_MORE_OUTPUT, then gathered again into a big enough one
+        job, out, out_host, h_stage, d_stage, img = jobs[0]
+        frames = (HydbFrame * 2)()
+        for tx in range(2):
+            f = frames[tx]
+            p = d_stage + tx * 256 * 3
+            f.plane = (C.c_void_p * 3)(p, p + 1, p + 2)
+            f.row_stride, f.pixel_stride = 512 * 3, 3
+            f.width, f.height, f.x0, f.y0, f.image_width, f.image_height = 256, 256, tx * 256, 0, 512, 256
+            f.is_last, f.sample_fmt, f.with_image_header = int(tx == 1), HYD_UINT8, int(tx == 0)
+        j2 = u32(0)
+        eng._check(lib.hydb_engine_submit_frames(eng._h, frames, 2, 0, None, None, 0, out, 4096, C.byref(j2), None))
+        nbytes = u64(0)
+        assert lib.hydb_engine_job_poll(eng._h, j2.value, 1, C.byref(nbytes)) == HYD_NEED_MORE_OUTPUT
+        eng._check(lib.hydb_engine_job_regather(eng._h, j2.value, out, 1 << 20, C.byref(nbytes)))
+        assert eng.download(out, nbytes.value) == oracle.encode_image(img)
+        eng._check(lib.hydb_engine_job_release(eng._h, j2.value))
+        for job, out, out_host, h_stage, d_stage, img in jobs:
+            lib.hydb_host_free(h_stage)
+            eng.device_free(d_stage)
+            if out_host:
+                lib.hydb_host_free(out_host)
+            else:
+                eng.device_free(out)
+
+
 def test_compute_sanitizer(product_lib):
     """compute-sanitizer memcheck over one small pass through every kernel family (tools/sanitize_case.py:
     both rANS chain kernels, TMA staging, multi-group frames, one-frame mode over two LF groups, the
@@ -496,6 +579,16 @@ def test_float32_samples(product_lib, engine, oracle):
             engine.encode_image(bad)
         assert ei.value.message == "Invalid NaN Float"
     assert engine.encode_image(img) == want   # the engine is still usable afterwards
+    # a negative opsin mix (here: a strongly negative red sample) makes the reference's bit-hack cube root
+    # return NaN, whose conversion to int is undefined in C: refused loudly instead of guessing
+    bad = img.copy()
+    bad[10, 10, 0] = -3.0
+    with pytest.raises(HydriumError) as ei:
+        encode_cli_loop(product_lib, bad)
+    assert ei.value.code == HYD_API_ERROR and "negative opsin mix" in ei.value.message
+    slightly = img.copy()
+    slightly[10, 10, 0] = -0.001   # the mix stays above -bias: still encodable, still the reference's bytes
+    assert encode_cli_loop(product_lib, slightly) == oracle.encode_image(slightly)
 
 
 def _split_frames(stream: bytes, header_len: int):
