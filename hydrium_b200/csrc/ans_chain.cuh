@@ -13,22 +13,25 @@
 //     a = q_prev << 12 (no renormalisation) or q_prev >> 4 (renormalised)    known BEFORE the previous
 //                                                                            step's table load returns
 //     v = slot_prev (no renormalisation) or 0                                the load result.
-// With mc = ceil(2^32 / f) and e = f * mc - 2^32 (0 <= e < f), x * mc / 2^32 over-estimates x / f by
-// x * e / (f * 2^32), which can reach 1.  Subtracting qa * e for ANY qa with 0 <= x - qa * f < 2^14
-// shrinks that error to (x - qa * f) * e / (f * 2^32) < 2^26 / (f * 2^32) < 1 / f, so
-//     q = hi32( x * mc - qa * e )        is exact.
+// Division by multiplication, exact (round 2, second form).  M = ceil(2^32 / f) - 1 (for every f >= 1: the
+// floor for a non-power of two, one less than the quotient for a power of two, 2^32 - 1 for f = 1) and
+// e = 2^32 - f * M, so 1 <= e <= f and f * M + e = 2^32.  For 0 <= y < 2^14
+//     hi32((y + 1) * M) = y / f :   (y + 1) * M / 2^32 = (y + 1) / f - d  with  0 < d = (y + 1) e / (f 2^32) <= 2^-18,
+//     which lies in [k, k + 1) for y = k f + r because (r + 1) / f >= 2^-12 > d, and strictly below k + 1 when
+//     r = f - 1 because d > 0.
 // While the previous load is in flight the "shadow" computes, for the coming symbol,
-//     w  = a * mc (64 bit),  qa = hi32(w) - 1        qa in {a/f - 1, a/f}, so x - qa * f < 2f + 4096
-//     R  = w - qa * e,       C0 = base2 + 2 * a
+//     w  = (a + 1) * M (64 bit),  qa = hi32(w)       qa in {a/f - 1, a/f}: (a + 1) M / 2^32 = (a + 1)/f - (a + 1) e / (f 2^32)
+//                                                    and the last term is at most 1; so y = x - qa f < 2f + 4096 <= 2^14 - 1
+//     R  = w + qa * e = (a + 1 - qa f) * M + qa * 2^32,       C0 = base2 + 2 * a
 // and once v arrives the dependent path is
-//     q    = hi32(v * mc + R)                                               multiply-high, 64-bit addend
-//     addr = C0 + 2 * v - 2 * f * q  = base2 + 2 * (x - q * f)              multiply-add -> next load
-// When the previous step renormalised, v must not count: the shadow replaces mc by 0 and the factor
+//     q    = hi32(v * M + R) = qa + hi32((y + 1) * M) = qa + y / f = x / f       multiply-high, 64-bit addend
+//     addr = C0 + 2 * v - 2 * f * q  = base2 + 2 * (x - q * f)                   multiply-add -> next load
+// When the previous step renormalised, v must not count: the shadow replaces M by 0 and the factor
 // 2 by 0, so the two path instructions are the same in both cases.
-// f = 1 has no 32-bit reciprocal: mc = 2^32 - 1 with e = -2 gives R = a * 2^32 + (a - 4) and
-// t = x * 2^32 + (a - 4 - v) with 0 <= a - 4 - v < 2^32, i.e. q = x exactly.  Power-of-two f >= 2
-// use mc = 2^32 / f, e = 0.  tests/test_host_logic.py checks the identity exhaustively at the range
-// boundaries and the whole formulation against the oracle.
+// (The first form used mc = ceil(2^32 / f) with a signed correction R = a mc - (hi32(a mc) - 1) e: the "- 1"
+// was one more dependent instruction between the two wide multiplies of the state recurrence.)
+// tests/test_host_logic.py checks the identity exhaustively at the range boundaries and the whole
+// formulation against the oracle.
 //
 // Why this shape: measured on B200 (tools/ubench), a single warp pays ~8 issue cycles per IMAD.WIDE,
 // ~6 per IMAD.HI, ~8 per LDS.128 and ~2.6 per IMAD, so the step is bound by instruction issue as
@@ -43,8 +46,8 @@ namespace hydb {
 constexpr uint32_t kAnsInitState = 0x130000u;   // reference: entropy.c:1083
 // per (cluster, token) constants for the chain: also the 16-byte record staged per symbol
 struct AnsSymInfo {
-    uint32_t mc;    // ceil(2^32 / f)   (2^32 - 1 for f = 1); 0 for an unused symbol
-    uint32_t ne;    // -e = 2^32 - f * mc (mod 2^32), a small non-positive signed value (+2 for f = 1)
+    uint32_t mc;    // M = ceil(2^32 / f) - 1; 0 for an unused symbol
+    uint32_t ne;    // e = 2^32 - f * M, 1 <= e <= f
     uint32_t nf2;   // -2f (mod 2^32)
     uint32_t b2;    // byte offset of the symbol's first slot in the flat uint16 inverse table
 };
@@ -54,13 +57,8 @@ HD AnsSymInfo ans_sym_info(uint32_t f, uint32_t base) {
     s.mc = s.ne = s.nf2 = s.b2 = 0;
     if (!f)
         return s;
-    if (f == 1) {
-        s.mc = 0xFFFFFFFFu;
-        s.ne = 2u;
-    } else {
-        s.mc = (uint32_t)((1ull << 32) / f) + ((f & (f - 1)) ? 1u : 0u);
-        s.ne = (0u - f) * s.mc;
-    }
+    s.mc = (uint32_t)(((1ull << 32) + f - 1u) / f - 1u);
+    s.ne = (0u - f) * s.mc;
     s.nf2 = 0u - 2u * f;
     s.b2 = 2u * base;
     return s;
@@ -93,10 +91,10 @@ HD uint32_t ans_hi32(uint64_t w) {
 HD void ans_prepare(AnsCarry &c, uint32_t a, bool v_counts, uint32_t mc, uint32_t ne, uint32_t b2) {
     c.meff = v_counts ? mc : 0u;
     c.k = v_counts ? 2u : 0u;
-    const uint64_t w = (uint64_t)a * mc;
-    const uint32_t qa = ans_hi32(w) - 1u;
+    const uint64_t w = (uint64_t)a * mc + mc;
+    const uint32_t qa = ans_hi32(w);
     c.c0 = 2u * a + b2;
-    c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)ne);
+    c.R = w + (uint64_t)qa * ne;
 }
 
 // set-up before the first step: the initial state renormalised for the first coded symbol
@@ -133,8 +131,8 @@ HD void ans_step(AnsCarry &c, const AnsSymInfo &own, const AnsSymInfo *next, uin
 // g into the slot (a warp-wide search over the cluster's sorted pieces).  Same quotient, same exactness
 // argument; k is 1 / 0 instead of 2 / 0 and c0 = a + cum.
 struct AnsRecC {
-    uint32_t mc;    // ceil(2^32 / f), as AnsSymInfo
-    uint32_t ne;    // -e
+    uint32_t mc;    // M, as AnsSymInfo
+    uint32_t ne;    // e
     uint32_t nf;    // -f (mod 2^32)
     uint32_t cum;   // cumulative frequency of the symbol inside its cluster
 };
@@ -150,10 +148,10 @@ HD AnsRecC ans_rec_c(uint32_t f, uint32_t cum) {
 HD void ans_prepare_c(AnsCarry &c, uint32_t a, bool v_counts, uint32_t mc, uint32_t ne, uint32_t cum) {
     c.meff = v_counts ? mc : 0u;
     c.k = v_counts ? 1u : 0u;
-    const uint64_t w = (uint64_t)a * mc;
-    const uint32_t qa = ans_hi32(w) - 1u;
+    const uint64_t w = (uint64_t)a * mc + mc;
+    const uint32_t qa = ans_hi32(w);
     c.c0 = a + cum;
-    c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)ne);
+    c.R = w + (uint64_t)qa * ne;
 }
 HD void ans_chain_begin_c(AnsCarry &c, const AnsRecC &first) {
     const uint32_t f = 0u - first.nf;

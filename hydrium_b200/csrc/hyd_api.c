@@ -30,6 +30,7 @@
 #include <time.h>
 
 #include "../../include/hydrium_b200.h"
+#include "stage_pool.h"
 
 /* Staging copy.  The destination is page-locked memory that only the GPU's copy engine reads afterwards, so
  * on x86 the rows are written with non-temporal stores: no read-for-ownership of the destination lines and
@@ -133,12 +134,14 @@ struct HYDEncoder {
     int device;
     uint32_t batch;                 /* 0 = automatic chunks, 1 = synchronous per tile, n = chunks of n tiles */
     uint32_t depth;                 /* chunks in flight (0 = default) */
+    uint32_t stage_workers;         /* helper threads of the staging copy (stage_pool.h; HYDRIUM_B200_THREADS) */
     uint32_t outcap_kb;             /* HYDRIUM_B200_OUTCAP_KB: output area per chunk (tests: forces the re-gather path) */
     Gpu gpu;
     Chunk chunks[MAX_CHUNKS];
     int cur;                        /* chunk being filled, -1 = none */
     uint64_t ring_head, ring_next;  /* oldest chunk not yet retired / next chunk to open (counters, index = % nchunks) */
     char errbuf[256];
+    double tr_stage, tr_submit, tr_flush, tr_first, tr_last_send;   /* HYDRIUM_B200_APITRACE: where the caller's thread spent its time */
 
     /* one-frame mode over several LF groups (encoder.c:752-1011): every hyd_send_tile encodes one
      * 2048x2048 LF group as a frame part; nothing surfaces until the last one (libhydrium.c:147-166) */
@@ -157,6 +160,8 @@ struct HYDEncoder {
 };
 
 static HYDStatusCode chunk_submit(HYDEncoder *enc);
+static int api_trace(void);
+static double now_ms(void);
 static void release_gpu(HYDEncoder *enc);
 static void segs_clear(HYDEncoder *enc);
 
@@ -180,6 +185,7 @@ HYDRIUM_EXPORT HYDEncoder *hyd_encoder_new(void) { /* libhydrium.c:16-19 */
     enc->batch = env_u32("HYDRIUM_B200_BATCH", 0);
     enc->depth = env_u32("HYDRIUM_B200_DEPTH", 0);
     enc->outcap_kb = env_u32("HYDRIUM_B200_OUTCAP_KB", 0);
+    enc->stage_workers = hyd_stage_default_workers();
     enc->cur = -1;
     return enc;
 }
@@ -205,6 +211,9 @@ static void of_reset(HYDEncoder *enc) {
 HYDRIUM_EXPORT HYDStatusCode hyd_encoder_destroy(HYDEncoder *enc) { /* libhydrium.c:21-44 */
     if (!enc)
         return HYD_OK;
+    if (api_trace() && enc->tr_first > 0)
+        fprintf(stderr, "[hydrium_b200] encoder: first tile to destroy %.2f ms (last send at %.2f); caller's thread: staging %.2f ms, submitting %.2f ms, flushing %.2f ms\n",
+                now_ms() - enc->tr_first, enc->tr_last_send - enc->tr_first, enc->tr_stage, enc->tr_submit, enc->tr_flush);
     release_gpu(enc);
     segs_clear(enc);
     free(enc->segs);
@@ -819,6 +828,7 @@ static HYDStatusCode chunk_submit(HYDEncoder *enc) {
     stage_fence();
     HYDStatusCode rc = hydb_engine_submit_frames(enc->gpu.engine, c->frames, c->nframes, c->slot0, c->stage_host, c->stage_dev,
                                                  c->used, c->out_host, enc->gpu.out_cap, &job, &slots);
+    enc->tr_submit += now_ms() - c->t_submit;
     if (rc != HYD_OK)
         return gpu_error(enc, rc);
     c->job = job;
@@ -992,8 +1002,8 @@ static int stage_pixels(HYDEncoder *enc, Chunk *c, uint32_t w, uint32_t h, const
         const size_t need = (size_t)(w - 1) * (size_t)pixel_stride * item + (size_t)(hi - lo) + item;
         if (span * h > room)
             return 0;
-        for (uint32_t y = 0; y < h; y++)
-            stage_copy(dst + (size_t)y * span, lo + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, need);
+        HydStageJob job = {1, h, need, {lo, NULL, NULL}, {dst, NULL, NULL}, row_stride * (ptrdiff_t)item, span, stage_copy, stage_fence};
+        hyd_stage_run(&job, enc->stage_workers);
         for (int k = 0; k < 3; k++)
             plane[k] = ddst + (p[k] - lo);
         *out_row_stride = (int64_t)w * pixel_stride;
@@ -1004,12 +1014,11 @@ static int stage_pixels(HYDEncoder *enc, Chunk *c, uint32_t w, uint32_t h, const
         const size_t span = (size_t)w * item;
         if (3 * span * h > room)
             return 0;
-        for (int k = 0; k < 3; k++) {
-            uint8_t *pd = dst + (size_t)k * span * h;
-            for (uint32_t y = 0; y < h; y++)
-                stage_copy(pd + (size_t)y * span, p[k] + (ptrdiff_t)y * row_stride * (ptrdiff_t)item, span);
+        HydStageJob job = {3, h, span, {p[0], p[1], p[2]}, {dst, dst + span * h, dst + 2 * span * h},
+                           row_stride * (ptrdiff_t)item, span, stage_copy, stage_fence};
+        hyd_stage_run(&job, enc->stage_workers);
+        for (int k = 0; k < 3; k++)
             plane[k] = ddst + (size_t)k * span * h;
-        }
         *out_row_stride = w;
         *out_pixel_stride = 1;
         used = 3 * span * h;
@@ -1061,6 +1070,7 @@ HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-16
     }
     if (enc->async_rc < HYD_ERROR_START)
         return enc->async_rc;
+    const double t_flush0 = api_trace() ? now_ms() : 0;
     if (enc->gpu.engine) {
         /* Everything is due once the last tile is in (libhydrium.c:147-166: the caller's flush loop after
          * the last tile must surface the whole image), or when the caller asks again right after a flush
@@ -1091,6 +1101,8 @@ HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-16
             enc->chunks[sg->chunk].state = CH_FREE;
         enc->seg_head++;
     }
+    if (t_flush0 > 0)
+        enc->tr_flush += now_ms() - t_flush0;
     if (enc->seg_head < enc->seg_tail)
         return HYD_NEED_MORE_OUTPUT;
     enc->flush_idle = 1;
@@ -1143,6 +1155,9 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
         return rc;
     HydbFrame *fr = &c->frames[c->nframes];
     memset(fr, 0, sizeof(*fr));
+    const double t_stage0 = api_trace() ? now_ms() : 0;
+    if (t_stage0 > 0 && enc->tr_first == 0)
+        enc->tr_first = t_stage0;
     if (!stage_pixels(enc, c, tw, th, fr->plane, &fr->row_stride, &fr->pixel_stride, buffer, row_stride, pixel_stride, item)) {
         /* the chunk is full in bytes before it is full in tiles (wider samples than it was sized for are
          * handled by ensure_gpu; this is a mix of layouts): send it off and start the next one */
@@ -1162,6 +1177,10 @@ HYDRIUM_EXPORT HYDStatusCode hyd_send_tile(HYDEncoder *enc, const void *const bu
             enc->error = "internal: tile does not fit an empty staging chunk";
             return HYD_INTERNAL_ERROR;
         }
+    }
+    if (t_stage0 > 0) {
+        enc->tr_last_send = now_ms();
+        enc->tr_stage += enc->tr_last_send - t_stage0;
     }
     fr->width = tw;
     fr->height = th;

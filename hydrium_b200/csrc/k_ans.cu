@@ -368,7 +368,11 @@ k_ans_chain(Workspace ws) {
         // One step, spelled out in the order the instructions should issue (ans_chain.cuh has the
         // maths).  `own` / `nxt` = {mc, -e, -2f, table address}.  The state a step leaves is stored by
         // the following step, once the table load has returned.
-#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr)                                                   \
+#ifndef HYDB_CHAIN_V
+#define HYDB_CHAIN_V 1
+#endif
+#if HYDB_CHAIN_V == 0
+#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
         {                                                                                                      \
             const uint32_t vprev = c.v;                                                                        \
             const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
@@ -383,12 +387,37 @@ k_ans_chain(Workspace ws) {
             const uint32_t a = p ? q4 : q12_prev;                                                              \
             c.meff = p ? 0u : (nxt).x;                                                                         \
             c.k = p ? 0u : 2u;                                                                                 \
-            const uint64_t w = (uint64_t)a * (nxt).x;                                                          \
-            const uint32_t qa = ans_hi32(w) - 1u;                                                              \
+            const uint64_t w = (uint64_t)a * (nxt).x + (nxt).x;                                                \
+            const uint32_t qa = ans_hi32(w);                                                                   \
             c.c0 = 2u * a + (nxt).w;                                                                           \
-            c.R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)(nxt).y);                            \
+            c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
             c.v = slotv;                                                                                       \
         }
+#else
+        // the table load first, then (in the load's shadow) the state store and the record prefetch
+#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
+        {                                                                                                      \
+            const uint32_t vprev = c.v;                                                                        \
+            const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
+            const uint32_t cv = vprev * c.k + c.c0;                                                            \
+            const uint32_t sp = q12_prev | vprev;                                                              \
+            const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
+            if (store_prev)                                                                                    \
+                sts32((cap_addr), sp);                                                                         \
+            PREFETCH;                                                                                          \
+            const bool p = q >= (thr_n);                                                                       \
+            const uint32_t q4 = q >> 4;                                                                        \
+            q12_prev = q << 12;                                                                                \
+            const uint32_t a = p ? q4 : q12_prev;                                                              \
+            c.meff = p ? 0u : (nxt).x;                                                                         \
+            c.k = p ? 0u : 2u;                                                                                 \
+            const uint64_t w = (uint64_t)a * (nxt).x + (nxt).x;                                                \
+            const uint32_t qa = ans_hi32(w);                                                                   \
+            c.c0 = 2u * a + (nxt).w;                                                                           \
+            c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
+            c.v = slotv;                                                                                       \
+        }
+#endif
         bar_sync(kBarFull + 0, 64);
         {
             const uint4 fr = lds128(rec_at(nbatch - 1, (int)((N - 1) & 31u)));
@@ -406,6 +435,7 @@ k_ans_chain(Workspace ws) {
             const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
             const uint32_t stg = stage_base + (uint32_t)slot * 32u * 16u, capb = cap_base + (uint32_t)slot * 32u * 4u;
             const uint32_t nstg = stage_base + (uint32_t)((seq + 1) % kRing) * 32u * 16u;
+#if HYDB_CHAIN_V == 0
             if (jtop == 31) {
                 if (seq == 0 || (seq == 1 && ((N - 1) & 31u) != 31u)) {   // first straight-line batch: fill the pipeline
                     r0 = lds128(stg + 31 * 16);
@@ -424,13 +454,37 @@ k_ans_chain(Workspace ws) {
                     r3 = j >= 4 ? lds128(stg + (uint32_t)(j - 4) * 16u) : lds128(nstg + (uint32_t)(28 + j) * 16u);
                     const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
                     if (j == 31) {   // the previous batch's last state is complete now: store it and release the batch
-                        HYDB_ANS_STEP(own, nxt, thr_n, prev_slot >= 0, prev_cap0);
+                        HYDB_ANS_STEP(own, nxt, thr_n, prev_slot >= 0, prev_cap0, (void)0);
                         if (prev_slot >= 0)
                             bar_arrive(kBarEmpty + prev_slot, 64);
                     } else {
-                        HYDB_ANS_STEP(own, nxt, thr_n, true, capb + (uint32_t)(j + 1) * 4u);
+                        HYDB_ANS_STEP(own, nxt, thr_n, true, capb + (uint32_t)(j + 1) * 4u, (void)0);
                     }
                 }
+#else
+            if (jtop == 31) {
+                if (seq == 0 || (seq == 1 && ((N - 1) & 31u) != 31u)) {   // first straight-line batch: fill the pipeline
+                    r0 = lds128(stg + 31 * 16);
+                    r1 = lds128(stg + 30 * 16);
+                }
+#pragma unroll
+                for (int j = 31; j >= 0; --j) {
+                    const uint4 own = r0, nxt = r1;
+                    if (j == 6 && seq + 1 < nbatch)   // the next batch's records are read from step 1 on
+                        bar_sync(kBarFull + (seq + 1) % kRing, 64);
+                    const uint32_t pf = j >= 2 ? stg + (uint32_t)(j - 2) * 16u : nstg + (uint32_t)(30 + j) * 16u;
+                    const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
+                    if (j == 31) {   // the previous batch's last state is complete now: store it and release the batch
+                        HYDB_ANS_STEP(own, nxt, thr_n, prev_slot >= 0, prev_cap0, r2 = lds128(pf));
+                        if (prev_slot >= 0)
+                            bar_arrive(kBarEmpty + prev_slot, 64);
+                    } else {
+                        HYDB_ANS_STEP(own, nxt, thr_n, true, capb + (uint32_t)(j + 1) * 4u, r2 = lds128(pf));
+                    }
+                    r0 = r1;
+                    r1 = r2;
+                }
+#endif
             } else {
                 if (seq + 1 < nbatch)
                     bar_sync(kBarFull + (seq + 1) % kRing, 64);
@@ -438,7 +492,7 @@ k_ans_chain(Workspace ws) {
                     const uint4 own = lds128(stg + (uint32_t)j * 16u);
                     const uint4 nxt = j ? lds128(stg + (uint32_t)(j - 1) * 16u) : lds128(nstg + 31u * 16u);
                     const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
-                    HYDB_ANS_STEP(own, nxt, thr_n, j < jtop, capb + (uint32_t)(j + 1) * 4u);
+                    HYDB_ANS_STEP(own, nxt, thr_n, j < jtop, capb + (uint32_t)(j + 1) * 4u, (void)0);
                 }
             }
             prev_cap0 = capb;

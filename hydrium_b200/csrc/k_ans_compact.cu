@@ -264,7 +264,7 @@ k_ans_chain_compact(Workspace ws) {
                 drain(seq - kCRing);
             }
             const uint32_t f = inf_cur.y & 0x1FFFu, cum = (inf_cur.y >> 13) & 0xFFFu, cl = inf_cur.y >> 25;
-            const uint32_t ne = f == 1u ? 2u : (0u - f) * inf_cur.x;   // AnsSymInfo::ne
+            const uint32_t ne = (0u - f) * inf_cur.x;   // AnsSymInfo::ne = 2^32 - f * M
             s.r.rec_a[slot][lane] = make_uint4(inf_cur.x, ne, cum, f << 8);
             s.r.rec_b[slot][lane] = make_uint2(0u - f, cl * (uint32_t)(32 * sizeof(AnsPieceLane)));
             s.r.fring[slot][lane] = f;
@@ -332,9 +332,9 @@ k_ans_chain_compact(Workspace ws) {
         vmask = p ? 0u : 0xFFFu;                                                                               \
         mc = (nxt_a).x;                                                                                        \
         cum = (nxt_a).z;                                                                                       \
-        const uint64_t w = (uint64_t)a_prev * mc;                                                              \
-        const uint32_t qa = ans_hi32(w) - 1u;                                                                  \
-        R = w + (uint64_t)((int64_t)(int32_t)qa * (int64_t)(int32_t)(nxt_a).y);                                \
+        const uint64_t w = (uint64_t)a_prev * mc + mc;                                                         \
+        const uint32_t qa = ans_hi32(w);                                                                       \
+        R = w + (uint64_t)qa * (nxt_a).y;                                                                      \
     }
 #define HYDB_LDS64(dst, addr) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"((dst).x), "=r"((dst).y) : "r"(addr))
     for (int seq = 0; seq < nbatch; seq++) {

@@ -130,3 +130,19 @@ def test_image_header_matches_oracle(host_harness, oracle):
         got = out.view(np.uint8)[:n // 8].tobytes()
         want = oracle.image_header(w, h)
         assert got == want[-len(got):]
+
+
+def test_staging_copy_pool(tmp_path):
+    """hydrium_b200/csrc/stage_pool.c (the staging copy of hyd_send_tile spread over helper threads): 400 random
+    jobs (interleaved and planar, negative pitches, 0..8 helpers), helpers that went to sleep in between, and
+    four threads calling at once -- every byte in place, nothing written past the destination."""
+    import os
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(ROOT, "tests", "host_harness", "stage_pool_test.c")
+    inc = os.path.join(ROOT, "hydrium_b200", "csrc")
+    exe = str(tmp_path / "stage_pool_test")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-I", inc, "-o", exe, src, os.path.join(inc, "stage_pool.c"), "-lpthread"],
+                   check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and res.stdout.strip() == "0", res.stdout + res.stderr
