@@ -35,6 +35,11 @@ namespace hydb {
 
 constexpr int kAnsThreads = 256;    // k_ans_chain
 constexpr int kPackThreads = 1024;  // k_ans_pack: one thread per ~3 chunks of 32 symbols, so its global loads overlap
+#ifndef HYDB_CHAIN_V
+#define HYDB_CHAIN_V 2
+#endif
+constexpr uint32_t kRecAddrBias = HYDB_CHAIN_V == 2 ? 2u : 0u;   // see HYDB_ANS_STEP
+constexpr uint32_t kSlotBias = HYDB_CHAIN_V == 2 ? 1u : 0u;      // added to every entry of the inverse alias table
 constexpr int kRing = 4;                 // batches in flight between the helper and the chain warp
 constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;   // named barrier ids (0 is __syncthreads)
 
@@ -214,7 +219,7 @@ k_ans_chain(Workspace ws) {
         if (s.alpha[c]) {
             uint32_t sym, off;
             ans_slot_symbol(s.cl[c], slot, log_alpha, sym, off);
-            s.inv[c * kAnsTotal + s.cl[c].cum[sym] + off] = (uint16_t)slot;
+            s.inv[c * kAnsTotal + s.cl[c].cum[sym] + off] = (uint16_t)(slot + kSlotBias);
         }
     }
     // (section D is written further down by a third warp, while the chain is already running)
@@ -338,7 +343,7 @@ k_ans_chain(Workspace ws) {
             }
             // record of lane L = the chain constants of symbol base + L, table address folded in;
             // unused lanes of the last batch carry frequency 0 and are never read by the chain
-            s.stage[slot][lane] = make_uint4(inf_cur.x, inf_cur.y, inf_cur.z, inf_cur.w + inv_base);
+            s.stage[slot][lane] = make_uint4(inf_cur.x, inf_cur.y, inf_cur.z, inf_cur.w + inv_base - kRecAddrBias);
             s.fring[slot][lane] = (0u - inf_cur.z) >> 1;
             bar_arrive(kBarFull + slot, 64);
             inf_cur = inf_nxt;
@@ -368,9 +373,6 @@ k_ans_chain(Workspace ws) {
         // One step, spelled out in the order the instructions should issue (ans_chain.cuh has the
         // maths).  `own` / `nxt` = {mc, -e, -2f, table address}.  The state a step leaves is stored by
         // the following step, once the table load has returned.
-#ifndef HYDB_CHAIN_V
-#define HYDB_CHAIN_V 1
-#endif
 #if HYDB_CHAIN_V == 0
 #define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
         {                                                                                                      \
@@ -418,12 +420,43 @@ k_ans_chain(Workspace ws) {
             c.v = slotv;                                                                                       \
         }
 #endif
+#if HYDB_CHAIN_V == 2
+#undef HYDB_ANS_STEP
+        // Third form.  The table holds slot + 1 (kSlotBias), so the dependent multiply is (slot + 1) * M and the
+        // shadow's first wide multiply is a * M without the "+ M" addend: R = a M + qa e with qa = hi32(a M),
+        // which is a/f - 2 .. a/f, so y = x - qa f < 3f + 4095 < 2^14 still holds and
+        // hi32((v + 1) M + R) = qa + hi32((y + 1) M) = x / f.  After a renormalisation v does not count and
+        // the + 1 moves into the known part: a' = (q >> 4) + 1, R = a' M + qa e.  Both cases address the
+        // table 2 bytes high; the helper folds - 2 into the records' table address (kRecAddrBias).
+#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
+        {                                                                                                      \
+            const uint32_t vprev = c.v;                                                                        \
+            const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
+            const uint32_t cv = vprev * c.k + c.c0;                                                            \
+            const uint32_t sp = q12_prev + vprev - 1u;                                                         \
+            const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
+            if (store_prev)                                                                                    \
+                sts32((cap_addr), sp);                                                                         \
+            PREFETCH;                                                                                          \
+            const bool p = q >= (thr_n);                                                                       \
+            const uint32_t q4 = (q >> 4) + 1u;                                                                 \
+            q12_prev = q << 12;                                                                                \
+            const uint32_t a = p ? q4 : q12_prev;                                                              \
+            c.meff = p ? 0u : (nxt).x;                                                                         \
+            c.k = p ? 0u : 2u;                                                                                 \
+            const uint64_t w = (uint64_t)a * (nxt).x;                                                          \
+            const uint32_t qa = ans_hi32(w);                                                                   \
+            c.c0 = 2u * a + (nxt).w;                                                                           \
+            c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
+            c.v = slotv;                                                                                       \
+        }
+#endif
         bar_sync(kBarFull + 0, 64);
         {
             const uint4 fr = lds128(rec_at(nbatch - 1, (int)((N - 1) & 31u)));
             AnsSymInfo first;
             first.mc = fr.x; first.ne = fr.y; first.nf2 = fr.z; first.b2 = fr.w;
-            ans_chain_begin(c, first, 0u);
+            ans_chain_begin(c, first, kRecAddrBias);
         }
         uint4 r0, r1, r2, r3;
         r0 = r1 = r2 = r3 = make_uint4(0u, 0u, 0u, 0u);
@@ -498,7 +531,7 @@ k_ans_chain(Workspace ws) {
             prev_cap0 = capb;
             prev_slot = slot;
         }
-        x = q12_prev | c.v;   // final state: what the last step leaves (no renormalisation follows)
+        x = q12_prev + c.v - kSlotBias;   // final state: what the last step leaves (no renormalisation follows)
         sts32(prev_cap0, x);
         bar_arrive(kBarEmpty + prev_slot, 64);
 #undef HYDB_ANS_STEP
