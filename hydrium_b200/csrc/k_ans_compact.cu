@@ -147,7 +147,7 @@ k_ans_chain_compact(Workspace ws) {
             const uint32_t rank = ans_piece_rank(s.b.lo, tid), L = rank >> 1;
             uint32_t *pl = reinterpret_cast<uint32_t *>(&s.pieces[c][L]);
             pl[rank & 1u] = s.b.lo[tid];
-            pl[2u + (rank & 1u)] = (uint32_t)s.b.delta[tid] + (L << 13);
+            pl[2u + (rank & 1u)] = (uint32_t)s.b.delta[tid] + 1u + (L << 13);   // + 1: the chain works on slot + 1
             __syncthreads();
         }
     }
@@ -233,7 +233,7 @@ k_ans_chain_compact(Workspace ws) {
             auto state_at = [&](uint32_t addr) {
                 uint32_t hi, lo;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(lo) : "r"(addr));
-                return hi | (lo & 0xFFFu);
+                return hi + (lo & 0x1FFFu) - 1u;   // the reduction yields slot + 1 (third form, ans_chain.cuh)
             };
             const uint32_t sprev = (int)lane >= jtop ? carry_s : state_at(capb + (lane + 1u) * 8u);
             const bool flagged = (int)lane <= jtop && (sprev >> 20) >= s.r.fring[slot][lane];
@@ -265,7 +265,7 @@ k_ans_chain_compact(Workspace ws) {
             }
             const uint32_t f = inf_cur.y & 0x1FFFu, cum = (inf_cur.y >> 13) & 0xFFFu, cl = inf_cur.y >> 25;
             const uint32_t ne = (0u - f) * inf_cur.x;   // AnsSymInfo::ne = 2^32 - f * M
-            s.r.rec_a[slot][lane] = make_uint4(inf_cur.x, ne, cum, f << 8);
+            s.r.rec_a[slot][lane] = make_uint4(inf_cur.x, ne, cum - 1u, f << 8);   // - 1: see HYDB_ANS_STEP_C
             s.r.rec_b[slot][lane] = make_uint2(0u - f, cl * (uint32_t)(32 * sizeof(AnsPieceLane)));
             s.r.fring[slot][lane] = f;
             arrive_full(seq);
@@ -288,7 +288,7 @@ k_ans_chain_compact(Workspace ws) {
     // ---- chain warp: every lane carries the same state; lane L also holds pieces 2L, 2L+1 of the
     //      cluster of the symbol being coded ----------------------------------------------------------
     // Carried from step to step: R, a + cum (as two addends), mc of the symbol being coded, vraw (the
-    // last reduction result, lane tag included), vmask (0xFFF, or 0 when the previous step
+    // last reduction result = slot + 1, lane tag included), vmask (0x1FFF, or 0 when the previous step
     // renormalised: then v must not count), q12_prev.  The state a step leaves ({q << 12, vraw}) is
     // stored by the FOLLOWING step, once its reduction has returned.  Full batches are 32 straight-line
     // steps: every ring address is an immediate and nothing but the step itself is issued.
@@ -307,7 +307,7 @@ k_ans_chain_compact(Workspace ws) {
         AnsCarry c;
         ans_chain_begin_c(c, first);
         R = c.R;
-        a_prev = c.c0 - fa.z;
+        a_prev = c.c0 - fa.z + 1u;   // the first step's + 1 sits in the known part (fa.z = cum - 1)
         cum = fa.z;
         mc = fa.x;
         pc = lds128(piece_lane + own_b.y);
@@ -328,11 +328,11 @@ k_ans_chain_compact(Workspace ws) {
         vraw = __reduce_max_sync(FULLM, cand);                                                                 \
         const bool p = q >= (thr_n);                                                                           \
         q12_prev = q << 12;                                                                                    \
-        a_prev = p ? (q >> 4) : q12_prev;                                                                      \
-        vmask = p ? 0u : 0xFFFu;                                                                               \
+        a_prev = p ? (q >> 4) + 1u : q12_prev;                                                                 \
+        vmask = p ? 0u : 0x1FFFu;                                                                              \
         mc = (nxt_a).x;                                                                                        \
         cum = (nxt_a).z;                                                                                       \
-        const uint64_t w = (uint64_t)a_prev * mc + mc;                                                         \
+        const uint64_t w = (uint64_t)a_prev * mc;                                                              \
         const uint32_t qa = ans_hi32(w);                                                                       \
         R = w + (uint64_t)qa * (nxt_a).y;                                                                      \
     }
@@ -394,7 +394,7 @@ k_ans_chain_compact(Workspace ws) {
     }
 #undef HYDB_ANS_STEP_C
 #undef HYDB_LDS64
-    const uint32_t x = q12_prev | (vraw & 0xFFFu);   // final state: what the last step leaves
+    const uint32_t x = q12_prev + (vraw & 0x1FFFu) - 1u;   // final state: what the last step leaves
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(prev_cap), "r"(q12_prev), "r"(vraw));
     arrive_empty(prev_seq);
     if (lane == 0) {
