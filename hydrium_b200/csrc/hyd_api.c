@@ -1061,6 +1061,32 @@ static HYDStatusCode emit_icc_header(HYDEncoder *enc) {
     return seg_push(enc, blk, NULL, (size_t)len, -1);
 }
 
+/* move queued bytes into the lent buffer, oldest first */
+static void flush_copy(HYDEncoder *enc) {
+    while (enc->seg_head < enc->seg_tail && enc->out_pos < enc->out_len) {
+        Seg *sg = &enc->segs[enc->seg_head];
+        size_t n = enc->out_len - enc->out_pos;
+        if (n > sg->len - sg->pos)
+            n = sg->len - sg->pos;
+        memcpy(enc->out + enc->out_pos, sg->p + sg->pos, n);
+        enc->out_pos += n;
+        sg->pos += n;
+        if (sg->pos < sg->len)
+            break;
+        free(sg->heap);
+        if (sg->chunk >= 0)
+            enc->chunks[sg->chunk].state = CH_FREE;
+        enc->seg_head++;
+    }
+}
+
+static int chunks_in_flight(const HYDEncoder *enc) {
+    for (uint64_t k = enc->ring_head; k != enc->ring_next; k++)
+        if (enc->chunks[k % enc->gpu.nchunks].state == CH_INFLIGHT)
+            return 1;
+    return 0;
+}
+
 HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-166 */
     if (enc->one_frame && !enc->last_tile)
         return HYD_OK;
@@ -1082,24 +1108,23 @@ HYDRIUM_EXPORT HYDStatusCode hyd_flush(HYDEncoder *enc) { /* libhydrium.c:147-16
             if (rc < HYD_ERROR_START)
                 return rc;
         }
-        HYDStatusCode rc = retire(enc, drain, drain);
-        if (rc < HYD_ERROR_START)
-            return rc;
-    }
-    while (enc->seg_head < enc->seg_tail && enc->out_pos < enc->out_len) {
-        Seg *sg = &enc->segs[enc->seg_head];
-        size_t n = enc->out_len - enc->out_pos;
-        if (n > sg->len - sg->pos)
-            n = sg->len - sg->pos;
-        memcpy(enc->out + enc->out_pos, sg->p + sg->pos, n);
-        enc->out_pos += n;
-        sg->pos += n;
-        if (sg->pos < sg->len)
-            break;
-        free(sg->heap);
-        if (sg->chunk >= 0)
-            enc->chunks[sg->chunk].state = CH_FREE;
-        enc->seg_head++;
+        /* Hand out what has finished without waiting; when draining, block for the OLDEST job only while
+         * there is room in the caller's buffer and nothing to put there, so that the caller copies chunk k
+         * away while the GPU is still coding chunk k + 1 (waiting for all of them first left the whole
+         * image to be copied after the last job: 0.7 ms of a 5.3 ms 4096x4096 encode). */
+        for (;;) {
+            HYDStatusCode rc = retire(enc, 0, 0);
+            if (rc < HYD_ERROR_START)
+                return rc;
+            flush_copy(enc);
+            if (enc->seg_head < enc->seg_tail || !drain || !chunks_in_flight(enc))
+                break;
+            rc = retire(enc, 1, 0);
+            if (rc < HYD_ERROR_START)
+                return rc;
+        }
+    } else {
+        flush_copy(enc);
     }
     if (t_flush0 > 0)
         enc->tr_flush += now_ms() - t_flush0;

@@ -28,6 +28,8 @@
 #define BLOCK_ROWS 16u
 #define SPIN_BEFORE_SLEEP 6000u   /* pause iterations (a few hundred microseconds) a helper stays hot after a job */
 #define SMALL_JOB_BYTES (96u * 1024u)
+#define SLOW_WAIT 3000u           /* pause iterations the owner may wait for the helpers' last blocks (about 100 us; a whole tile copies in 20) */
+#define CALM_JOBS 512u            /* jobs without a slow wait before another helper is invited again */
 
 /* The descriptor is published and read word by word with relaxed atomics: a helper that lost the race for
  * the last rows of job k may still be reading while the caller writes job k + 1; its claim then fails (see
@@ -50,7 +52,12 @@ static struct {
     uint32_t done_rows;
     uint32_t sleepers;
     int stop;
-} P = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, {{0}}, 0, 0, 0, 0};
+    /* Oversubscribed hosts (several encoder processes, fewer free cores than threads): a helper that holds a
+     * block and loses its core makes the caller wait for a scheduler quantum.  The owner of a job measures how
+     * long it waited after finishing its own share; long waits lower the number of helpers invited, calm
+     * stretches raise it again. */
+    uint32_t cap, calm;
+} P = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, {{0}}, 0, 0, 0, 0, HYD_STAGE_MAX_WORKERS, 0};
 
 static void copy_rows(const HydStageJob *j, uint32_t first, uint32_t n) {
     for (uint32_t r = first; r < first + n; r++) {
@@ -157,6 +164,8 @@ void hyd_stage_run(const HydStageJob *job, uint32_t workers) {
         copy_rows(job, 0, total);
         return;
     }
+    if (workers > P.cap)
+        workers = P.cap;
     workers = ensure_threads(workers);
     JobWords jw;
     memset(&jw, 0, sizeof(jw));
@@ -173,8 +182,19 @@ void hyd_stage_run(const HydStageJob *job, uint32_t workers) {
         pthread_mutex_unlock(&P.mu);
     }
     work_on(seq);
-    while (__atomic_load_n(&P.done_rows, __ATOMIC_ACQUIRE) != total)
+    uint32_t waited = 0;
+    while (__atomic_load_n(&P.done_rows, __ATOMIC_ACQUIRE) != total) {
         cpu_relax();
+        waited++;
+    }
+    if (waited > SLOW_WAIT) {          /* a helper was not running: invite one fewer from now on */
+        P.cap = workers ? workers - 1 : 0;
+        P.calm = 0;
+    } else if (++P.calm >= CALM_JOBS) {   /* try one more again */
+        if (P.cap < HYD_STAGE_MAX_WORKERS)
+            P.cap++;
+        P.calm = 0;
+    }
     pthread_mutex_unlock(&P.owner);
 }
 
@@ -192,9 +212,11 @@ uint32_t hyd_stage_default_workers(void) {
     if (sched_getaffinity(0, sizeof(set), &set) == 0)
         cpus = CPU_COUNT(&set);
 #endif
-    if (cpus > 4)
-        cpus = 4;
-    return cpus > 1 ? (uint32_t)cpus - 1 : 0;
+    /* up to six copying threads, at most half of the CPUs this process may run on */
+    int n = cpus / 2;
+    if (n > 6)
+        n = 6;
+    return n > 1 ? (uint32_t)n - 1 : 0;
 }
 
 /* the library may be unloaded (dlclose): its code must not disappear under running helpers */

@@ -37,7 +37,7 @@ typedef struct HydStageJob {
 void hyd_stage_run(const HydStageJob *job, uint32_t workers);
 
 /* helpers the pool would use by default: HYDRIUM_B200_THREADS (total copying threads, 1 = caller only),
- * else min(4, CPUs this process may run on) - 1 */
+ * else min(6, half the CPUs this process may run on) - 1 */
 uint32_t hyd_stage_default_workers(void);
 
 #endif

@@ -191,6 +191,12 @@ int main(int argc, char **argv) {
         }
         fclose(f);
     }
+    if (getenv("API_BENCH_VERBOSE")) {
+        fprintf(stderr, "api_bench: ms per rep:");
+        for (int i = 0; i < reps; i++)
+            fprintf(stderr, " %.2f", ms[i]);
+        fprintf(stderr, "\n");
+    }
     qsort(ms, (size_t)reps, sizeof(double), cmp_double);
     const double mean = sum / reps, mpx = (double)w * h / 1e6;
     printf("{\"width\": %u, \"height\": %u, \"bits\": %d, \"channels\": %d, \"linear\": %d, \"shift\": %d, \"reps\": %d, "
