@@ -17,6 +17,7 @@
 #include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #if defined(__x86_64__) || defined(__i386__)
 #include <immintrin.h>
@@ -26,9 +27,14 @@
 #endif
 
 #define BLOCK_ROWS 16u
-#define SPIN_BEFORE_SLEEP 6000u   /* pause iterations (a few hundred microseconds) a helper stays hot after a job */
+#define SPIN_PAUSES 2000u         /* a helper spins on pause for this many iterations (the next tile is microseconds away), ... */
+#define HOT_MS 5.0                /* ... then on sched_yield until this long after its last job (the GPU tail of an image; the next
+                                   * image of a busy caller), and only then sleeps.  A helper that sleeps is woken next to the
+                                   * caller's core and the two then share it for a scheduler tick or more -- measured as images
+                                   * that stage in 25 ms instead of 3 -- so helpers of a busy encoder should not sleep at all;
+                                   * yielding keeps them out of the way of other runnable threads on a crowded host. */
 #define SMALL_JOB_BYTES (96u * 1024u)
-#define SLOW_WAIT 3000u           /* pause iterations the owner may wait for the helpers' last blocks (about 100 us; a whole tile copies in 20) */
+#define SLOW_WAIT 2000u           /* iterations (256 pauses, then yields) the owner may wait for the helpers' last blocks; a whole tile copies in 20 us */
 #define CALM_JOBS 512u            /* jobs without a slow wait before another helper is invited again */
 
 /* The descriptor is published and read word by word with relaxed atomics: a helper that lost the race for
@@ -92,16 +98,29 @@ static void work_on(uint32_t seq) {
     }
 }
 
+static double mono_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+
 static void *helper_main(void *arg) {
     const uint32_t me = (uint32_t)(uintptr_t)arg;
     uint32_t seen = 0, spin = 0;
+    double idle_since = 0;
     for (;;) {
         const uint64_t t = __atomic_load_n(&P.ticket, __ATOMIC_SEQ_CST);
         if ((uint32_t)(t >> 32) == seen) {
             if (__atomic_load_n(&P.stop, __ATOMIC_RELAXED))
                 return NULL;
-            if (++spin < SPIN_BEFORE_SLEEP) {
+            if (++spin < SPIN_PAUSES) {
                 cpu_relax();
+                continue;
+            }
+            if (spin == SPIN_PAUSES)
+                idle_since = mono_ms();
+            if (mono_ms() - idle_since < HOT_MS) {
+                sched_yield();
                 continue;
             }
             pthread_mutex_lock(&P.mu);
@@ -184,8 +203,10 @@ void hyd_stage_run(const HydStageJob *job, uint32_t workers) {
     work_on(seq);
     uint32_t waited = 0;
     while (__atomic_load_n(&P.done_rows, __ATOMIC_ACQUIRE) != total) {
-        cpu_relax();
-        waited++;
+        if (++waited < 256u)
+            cpu_relax();
+        else
+            sched_yield();   /* whoever holds the last block may be waiting for this very core */
     }
     if (waited > SLOW_WAIT) {          /* a helper was not running: invite one fewer from now on */
         P.cap = workers ? workers - 1 : 0;

@@ -65,7 +65,37 @@ static void *caller(void *arg) {
     return (void *)(uintptr_t)bad;
 }
 
-int main(void) {
+/* stage_pool_test bench HELPERS IMAGES: time IMAGES passes of 256 tile copies (a 4096x4096 RGB8 image) with a
+ * pause between passes, print mean / median / worst -- run several at once to see oversubscription */
+static int cmp_d(const void *a, const void *b) { return *(const double *)a < *(const double *)b ? -1 : 1; }
+static int bench(uint32_t workers, int images) {
+    const size_t w = 4096 * 3, n = w * 4096;
+    uint8_t *img = malloc(n), *stage = malloc(n);
+    double *ms = malloc(sizeof(double) * (size_t)images);
+    memset(img, 1, n);
+    memset(stage, 0, n);
+    for (int k = 0; k < images; k++) {
+        const double t0 = now_ms();
+        for (uint32_t t = 0; t < 256; t++) {
+            HydStageJob job = {1, 256, 768, {img + (size_t)(t / 16) * 256 * w + (size_t)(t % 16) * 768, NULL, NULL},
+                               {stage + (size_t)t * 256 * 768, NULL, NULL}, (ptrdiff_t)w, 768, plain_copy, NULL};
+            hyd_stage_run(&job, workers);
+        }
+        ms[k] = now_ms() - t0;
+        struct timespec ts = {0, 3 * 1000 * 1000};   /* the GPU tail: helpers go to sleep */
+        nanosleep(&ts, NULL);
+    }
+    double sum = 0;
+    for (int k = 0; k < images; k++)
+        sum += ms[k];
+    qsort(ms, (size_t)images, sizeof(double), cmp_d);
+    printf("helpers %u: mean %.2f ms, median %.2f, p90 %.2f, worst %.2f\n", workers, sum / images, ms[images / 2], ms[images * 9 / 10], ms[images - 1]);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 4 && !strcmp(argv[1], "bench"))
+        return bench((uint32_t)atoi(argv[2]), atoi(argv[3]));
     size_t bad = 0;
     uint32_t seed = 7;
     for (int i = 0; i < 400; i++)
