@@ -35,11 +35,8 @@ namespace hydb {
 
 constexpr int kAnsThreads = 256;    // k_ans_chain
 constexpr int kPackThreads = 1024;  // k_ans_pack: one thread per ~3 chunks of 32 symbols, so its global loads overlap
-#ifndef HYDB_CHAIN_V
-#define HYDB_CHAIN_V 2
-#endif
-constexpr uint32_t kRecAddrBias = HYDB_CHAIN_V == 2 ? 2u : 0u;   // see HYDB_ANS_STEP
-constexpr uint32_t kSlotBias = HYDB_CHAIN_V == 2 ? 1u : 0u;      // added to every entry of the inverse alias table
+constexpr uint32_t kRecAddrBias = 2u;   // see HYDB_ANS_STEP
+constexpr uint32_t kSlotBias = 1u;      // added to every entry of the inverse alias table
 constexpr int kRing = 4;                 // batches in flight between the helper and the chain warp
 constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;   // named barrier ids (0 is __syncthreads)
 
@@ -363,80 +360,34 @@ k_ans_chain(Workspace ws) {
         // Steps run in chain order n = 0 .. N-1 (symbol N-1-n); a step needs the record of its own
         // symbol and, in the table load's shadow, that of the next one.  Only the first batch can be
         // partial; it runs through a plain loop.  Full batches are 32 straight-line steps whose records
-        // roll through four registers sets loaded four steps ahead -- across the batch boundary too,
-        // which is why the FULL barrier of batch seq + 1 is taken before batch seq starts.
+        // roll through three register sets loaded two steps ahead -- across the batch boundary too,
+        // which is why the FULL barrier of batch seq + 1 is taken inside batch seq.
         AnsCarry c;
         uint32_t x = 0, q12_prev = 0;
         auto rec_at = [&](int bi, int j) -> uint32_t {   // shared address of the record of symbol bi * 32 + j
             return stage_base + (uint32_t)((((nbatch - 1 - bi) % kRing) * 32 + j) * 16);
         };
-        // One step, spelled out in the order the instructions should issue (ans_chain.cuh has the
-        // maths).  `own` / `nxt` = {mc, -e, -2f, table address}.  The state a step leaves is stored by
-        // the following step, once the table load has returned.
-#if HYDB_CHAIN_V == 0
-#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
+        // One step, spelled out in the order the instructions should issue.  `own` / `nxt` = {M, e, -2f, table
+        // address - 2}.  This is the third form of ans_chain.cuh's division: the table holds slot + 1
+        // (kSlotBias), so the dependent multiply is (slot + 1) * M and the shadow's first wide multiply is a * M
+        // without a "+ M" addend: R = a M + qa e with qa = hi32(a M), which is a/f - 2 .. a/f, so
+        // y = x - qa f < 3f + 4095 < 2^14 still holds and hi32((v + 1) M + R) = qa + hi32((y + 1) M) = x / f.
+        // After a renormalisation v does not count and the + 1 moves into the known part: a' = (q >> 4) + 1,
+        // R = a' M + qa e.  Both cases address the table 2 bytes high; the helper folds - 2 into the records'
+        // table address (kRecAddrBias).  Order: the table load first, then, in its shadow, the state export and
+        // the record prefetch (two steps ahead), then the state recurrence q -> p -> a -> a M -> R.
+        // The state a step leaves, (q << 12) | slot, is complete in the FOLLOWING step (once the table load has
+        // returned), which stores it for the helper.  Wider stores were measured and are slower: {q << 12,
+        // slot + 1} as 8 bytes per step (no combining add) 50.3 cycles per symbol, two steps' pairs as one
+        // 16-byte store every other step 53.9, against 49.1 for this 4-byte store.
+#define HYDB_ANS_STEP(own, nxt, thr_n, EXPORT, cap_addr, PREFETCH)                                             \
         {                                                                                                      \
             const uint32_t vprev = c.v;                                                                        \
             const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
             const uint32_t cv = vprev * c.k + c.c0;                                                            \
-            const uint32_t sp = q12_prev | vprev;                                                              \
-            if (store_prev)                                                                                    \
-                sts32((cap_addr), sp);                                                                         \
             const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
-            const bool p = q >= (thr_n);                                                                       \
-            const uint32_t q4 = q >> 4;                                                                        \
-            q12_prev = q << 12;                                                                                \
-            const uint32_t a = p ? q4 : q12_prev;                                                              \
-            c.meff = p ? 0u : (nxt).x;                                                                         \
-            c.k = p ? 0u : 2u;                                                                                 \
-            const uint64_t w = (uint64_t)a * (nxt).x + (nxt).x;                                                \
-            const uint32_t qa = ans_hi32(w);                                                                   \
-            c.c0 = 2u * a + (nxt).w;                                                                           \
-            c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
-            c.v = slotv;                                                                                       \
-        }
-#else
-        // the table load first, then (in the load's shadow) the state store and the record prefetch
-#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
-        {                                                                                                      \
-            const uint32_t vprev = c.v;                                                                        \
-            const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
-            const uint32_t cv = vprev * c.k + c.c0;                                                            \
-            const uint32_t sp = q12_prev | vprev;                                                              \
-            const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
-            if (store_prev)                                                                                    \
-                sts32((cap_addr), sp);                                                                         \
-            PREFETCH;                                                                                          \
-            const bool p = q >= (thr_n);                                                                       \
-            const uint32_t q4 = q >> 4;                                                                        \
-            q12_prev = q << 12;                                                                                \
-            const uint32_t a = p ? q4 : q12_prev;                                                              \
-            c.meff = p ? 0u : (nxt).x;                                                                         \
-            c.k = p ? 0u : 2u;                                                                                 \
-            const uint64_t w = (uint64_t)a * (nxt).x + (nxt).x;                                                \
-            const uint32_t qa = ans_hi32(w);                                                                   \
-            c.c0 = 2u * a + (nxt).w;                                                                           \
-            c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
-            c.v = slotv;                                                                                       \
-        }
-#endif
-#if HYDB_CHAIN_V == 2
-#undef HYDB_ANS_STEP
-        // Third form.  The table holds slot + 1 (kSlotBias), so the dependent multiply is (slot + 1) * M and the
-        // shadow's first wide multiply is a * M without the "+ M" addend: R = a M + qa e with qa = hi32(a M),
-        // which is a/f - 2 .. a/f, so y = x - qa f < 3f + 4095 < 2^14 still holds and
-        // hi32((v + 1) M + R) = qa + hi32((y + 1) M) = x / f.  After a renormalisation v does not count and
-        // the + 1 moves into the known part: a' = (q >> 4) + 1, R = a' M + qa e.  Both cases address the
-        // table 2 bytes high; the helper folds - 2 into the records' table address (kRecAddrBias).
-#define HYDB_ANS_STEP(own, nxt, thr_n, store_prev, cap_addr, PREFETCH)                                         \
-        {                                                                                                      \
-            const uint32_t vprev = c.v;                                                                        \
-            const uint32_t q = ans_hi32((uint64_t)vprev * c.meff + c.R);                                       \
-            const uint32_t cv = vprev * c.k + c.c0;                                                            \
-            const uint32_t sp = q12_prev + vprev - 1u;                                                         \
-            const uint32_t slotv = lds16(q * (own).z + cv);                                                    \
-            if (store_prev)                                                                                    \
-                sts32((cap_addr), sp);                                                                         \
+            if (EXPORT)                                                                                        \
+                sts32((cap_addr), q12_prev + vprev - kSlotBias);                                               \
             PREFETCH;                                                                                          \
             const bool p = q >= (thr_n);                                                                       \
             const uint32_t q4 = (q >> 4) + 1u;                                                                 \
@@ -450,7 +401,6 @@ k_ans_chain(Workspace ws) {
             c.R = w + (uint64_t)qa * (nxt).y;                                                                  \
             c.v = slotv;                                                                                       \
         }
-#endif
         bar_sync(kBarFull + 0, 64);
         {
             const uint4 fr = lds128(rec_at(nbatch - 1, (int)((N - 1) & 31u)));
@@ -458,8 +408,8 @@ k_ans_chain(Workspace ws) {
             first.mc = fr.x; first.ne = fr.y; first.nf2 = fr.z; first.b2 = fr.w;
             ans_chain_begin(c, first, kRecAddrBias);
         }
-        uint4 r0, r1, r2, r3;
-        r0 = r1 = r2 = r3 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 r0, r1, r2;
+        r0 = r1 = r2 = make_uint4(0u, 0u, 0u, 0u);
         uint32_t prev_cap0 = 0;   // where the state left by the previous batch's last step goes
         int prev_slot = -1;
         for (int seq = 0; seq < nbatch; seq++) {
@@ -468,33 +418,6 @@ k_ans_chain(Workspace ws) {
             const int jtop = (int)((N - 1 - base) < 31u ? (N - 1 - base) : 31u);
             const uint32_t stg = stage_base + (uint32_t)slot * 32u * 16u, capb = cap_base + (uint32_t)slot * 32u * 4u;
             const uint32_t nstg = stage_base + (uint32_t)((seq + 1) % kRing) * 32u * 16u;
-#if HYDB_CHAIN_V == 0
-            if (jtop == 31) {
-                if (seq == 0 || (seq == 1 && ((N - 1) & 31u) != 31u)) {   // first straight-line batch: fill the pipeline
-                    r0 = lds128(stg + 31 * 16);
-                    r1 = lds128(stg + 30 * 16);
-                    r2 = lds128(stg + 29 * 16);
-                    r3 = lds128(stg + 28 * 16);
-                }
-#pragma unroll
-                for (int j = 31; j >= 0; --j) {
-                    const uint4 own = r0, nxt = r1;
-                    r0 = r1;
-                    r1 = r2;
-                    r2 = r3;
-                    if (j == 8 && seq + 1 < nbatch)   // the next batch's records are read from step 3 on
-                        bar_sync(kBarFull + (seq + 1) % kRing, 64);
-                    r3 = j >= 4 ? lds128(stg + (uint32_t)(j - 4) * 16u) : lds128(nstg + (uint32_t)(28 + j) * 16u);
-                    const uint32_t thr_n = (j == 0 && bi == 0) ? kAnsNoNext : (0u - nxt.z) << 7;
-                    if (j == 31) {   // the previous batch's last state is complete now: store it and release the batch
-                        HYDB_ANS_STEP(own, nxt, thr_n, prev_slot >= 0, prev_cap0, (void)0);
-                        if (prev_slot >= 0)
-                            bar_arrive(kBarEmpty + prev_slot, 64);
-                    } else {
-                        HYDB_ANS_STEP(own, nxt, thr_n, true, capb + (uint32_t)(j + 1) * 4u, (void)0);
-                    }
-                }
-#else
             if (jtop == 31) {
                 if (seq == 0 || (seq == 1 && ((N - 1) & 31u) != 31u)) {   // first straight-line batch: fill the pipeline
                     r0 = lds128(stg + 31 * 16);
@@ -517,7 +440,6 @@ k_ans_chain(Workspace ws) {
                     r0 = r1;
                     r1 = r2;
                 }
-#endif
             } else {
                 if (seq + 1 < nbatch)
                     bar_sync(kBarFull + (seq + 1) % kRing, 64);
