@@ -796,28 +796,33 @@ static HYDStatusCode of_assemble(HYDEncoder *enc) {
         free(head); free(hf);
         return gpu_error(enc, rc);
     }
-    size_t total = (size_t)head_len + hf_len + enc->of_e_len;
-    for (uint32_t i = 0; i < n; i++)
-        total += enc->of_len1[i];
-    uint8_t *blk = malloc(total ? total : 1);
-    if (!blk) {
-        free(head); free(hf);
-        return HYD_NOMEM;
-    }
-    uint8_t *d = blk;
-    memcpy(d, head, head_len);
-    d += head_len;
-    for (uint32_t i = 0; i < n; i++) {
-        memcpy(d, enc->of_lf[i], enc->of_len1[i]);
-        d += enc->of_len1[i];
-    }
-    memcpy(d, hf, hf_len);
-    d += hf_len;
-    memcpy(d, enc->of_e, enc->of_e_len);
+    /* head | LFGroups | HFGlobal | PassGroups go to the output queue as they are: the blocks change owner,
+     * nothing is concatenated (a 4096x4096 image saved a 5.7 MB copy on its critical path) */
     enc->wrote_header = 1;
-    free(head);
-    free(hf);
-    return seg_push(enc, blk, NULL, total, -1);
+    rc = seg_push(enc, head, NULL, head_len, -1);   /* seg_push frees the block itself when it fails */
+    if (rc < HYD_ERROR_START) {
+        free(hf);
+        return rc;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t *lf = enc->of_lf[i];
+        enc->of_lf[i] = NULL;
+        rc = seg_push(enc, lf, NULL, enc->of_len1[i], -1);
+        if (rc < HYD_ERROR_START) {
+            free(hf);
+            return rc;
+        }
+    }
+    rc = seg_push(enc, hf, NULL, hf_len, -1);
+    if (rc < HYD_ERROR_START)
+        return rc;
+    uint8_t *e = enc->of_e ? enc->of_e : malloc(1);
+    const size_t e_len = enc->of_e_len;
+    enc->of_e = NULL;
+    enc->of_e_len = enc->of_e_cap = 0;
+    if (!e)
+        return HYD_NOMEM;
+    return seg_push(enc, e, NULL, e_len, -1);
 }
 
 /* ---- chunk life cycle ------------------------------------------------------------------------------------ */
