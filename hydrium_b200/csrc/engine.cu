@@ -322,6 +322,7 @@ const char *hydb_engine_error(const HydbEngine *eng) { return eng ? eng->error.c
 uint32_t hydb_engine_max_batch(const HydbEngine *eng) { return eng ? eng->max_batch : 0; }
 uint64_t hydb_engine_stream(const HydbEngine *eng) { return eng ? (uint64_t)(uintptr_t)eng->st : 0; }
 uint64_t hydb_engine_launch_count(const HydbEngine *eng) { return eng ? eng->launches : 0; }
+uint64_t hydb_engine_graph_launch_count(const HydbEngine *eng) { return eng ? eng->graph_launches : 0; }
 
 HYDStatusCode hydb_engine_set_chain_kernel(HydbEngine *eng, int mode) {
     if (!eng || mode < 0 || mode > 2)

@@ -233,6 +233,13 @@ HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *enc, uint32_t ti
     return HYD_OK;
 }
 
+HYDRIUM_EXPORT void hydb_encoder_stats(const HYDEncoder *enc, uint64_t *kernel_launches, uint64_t *graph_launches) {
+    if (kernel_launches)
+        *kernel_launches = enc && enc->gpu.engine ? hydb_engine_launch_count(enc->gpu.engine) : 0;
+    if (graph_launches)
+        *graph_launches = enc && enc->gpu.engine ? hydb_engine_graph_launch_count(enc->gpu.engine) : 0;
+}
+
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_device(HYDEncoder *enc, int device) {
     if (!enc || enc->tiles_sent) {
         if (enc)

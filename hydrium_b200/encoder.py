@@ -116,7 +116,7 @@ def tile_grid(width: int, height: int, shift_x: int, shift_y: int) -> tuple[int,
 def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, shift_x: int = 0,
                     shift_y: int = 0, out_buf_size: int = 1 << 20, pixel_stride: int | None = None,
                     tiles=None, is_last=-1, per_tile: list | None = None, icc: bytes | None = None,
-                    batch: int | None = None) -> bytes:
+                    batch: int | None = None, stats: dict | None = None) -> bytes:
     """Encode `image` (H, W, C>=3 interleaved; uint8/uint16/float32) exactly the way the reference
     CLI drives the library: one output buffer, and after every tile the
     flush / release / consume / provide loop (hydrium.c:402-480).
@@ -130,6 +130,7 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
     After the last tile the flush loop is run once more: a no-op for the reference, and for
     libhydrium_b200 the documented way to collect everything when no tile was marked last
     (tile subsets without is_last are legal).
+    `stats` (libhydrium_b200 only): receives the engine's kernel-launch and graph-replay counters.
     """
     if image.ndim != 3 or image.shape[2] < 3:
         raise ValueError("image must be (H, W, C>=3)")
@@ -184,6 +185,12 @@ def encode_cli_loop(lib: C.CDLL, image: np.ndarray, *, linear_light: int = 0, sh
             if ret != HYD_NEED_MORE_OUTPUT:
                 enc.check(ret)
                 break
+        if stats is not None and hasattr(lib, "hydb_encoder_stats"):   # libhydrium_b200 only
+            k, g = C.c_uint64(0), C.c_uint64(0)
+            lib.hydb_encoder_stats.restype = None
+            lib.hydb_encoder_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+            lib.hydb_encoder_stats(enc._enc, C.byref(k), C.byref(g))
+            stats["kernel_launches"], stats["graph_launches"] = k.value, g.value
     finally:
         enc.destroy()
     return bytes(out)

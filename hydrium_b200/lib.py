@@ -18,6 +18,7 @@ _lib = None
 HYDB_SYMBOLS = (
     "hydb_encoder_set_batch", "hydb_encoder_set_device", "hydb_engine_create", "hydb_engine_destroy",
     "hydb_engine_error", "hydb_engine_max_batch", "hydb_engine_stream", "hydb_engine_launch_count",
+    "hydb_engine_graph_launch_count", "hydb_encoder_stats",
     "hydb_engine_encode_tiles", "hydb_engine_finish", "hydb_encode_image_device", "hydb_encode_image_host",
     "hydb_image_header", "hydb_host_alloc", "hydb_host_free", "hydb_device_alloc", "hydb_device_free",
     "hydb_memcpy_h2d", "hydb_memcpy_d2h", "hydb_device_count", "hydb_synth_fill", "hydb_engine_enable_taps",
@@ -71,6 +72,10 @@ def load_library() -> C.CDLL:
     lib.hydb_engine_stream.argtypes = [vp]
     lib.hydb_engine_launch_count.restype = u64
     lib.hydb_engine_launch_count.argtypes = [vp]
+    lib.hydb_engine_graph_launch_count.restype = u64
+    lib.hydb_engine_graph_launch_count.argtypes = [vp]
+    lib.hydb_encoder_stats.restype = None
+    lib.hydb_encoder_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.hydb_engine_encode_tiles.restype = C.c_int
     lib.hydb_engine_encode_tiles.argtypes = [vp, C.POINTER(HydbTile), u32, vp, u64, u64]
     lib.hydb_engine_finish.restype = C.c_int

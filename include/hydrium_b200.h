@@ -110,6 +110,9 @@ HYDRIUM_EXPORT HYDStatusCode hyd_set_suggested_icc_profile(HYDEncoder *encoder, 
  * exactly like the reference.  N > 1 = asynchronous with chunks of N tiles.
  * Must be called before the first hyd_send_tile. */
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_batch(HYDEncoder *encoder, uint32_t tiles);
+/* counters of the engine behind this encoder (0 before the first tile): kernels launched, jobs replayed as
+ * CUDA graphs -- what bench.py's gpu_launches and the graph-replay test read */
+HYDRIUM_EXPORT void hydb_encoder_stats(const HYDEncoder *encoder, uint64_t *kernel_launches, uint64_t *graph_launches);
 /* CUDA device ordinal for this encoder.  Default: env HYDRIUM_B200_DEVICE, else the current device. */
 HYDRIUM_EXPORT HYDStatusCode hydb_encoder_set_device(HYDEncoder *encoder, int device);
 
@@ -137,8 +140,10 @@ HYDRIUM_EXPORT const char *hydb_engine_error(const HydbEngine *engine);
 HYDRIUM_EXPORT uint32_t hydb_engine_max_batch(const HydbEngine *engine);
 /* the cudaStream_t the engine launches on (as an integer handle), for CUDA-event timing */
 HYDRIUM_EXPORT uint64_t hydb_engine_stream(const HydbEngine *engine);
-/* number of kernel launches issued by the engine so far */
+/* number of kernel launches issued by the engine so far (kernels replayed from a CUDA graph count) */
 HYDRIUM_EXPORT uint64_t hydb_engine_launch_count(const HydbEngine *engine);
+/* how many asynchronous jobs were submitted as one cudaGraphLaunch (recurring chunk geometries) */
+HYDRIUM_EXPORT uint64_t hydb_engine_graph_launch_count(const HydbEngine *engine);
 
 /* Which rANS chain kernel the engine launches: 0 (default) = by launch size -- the table kernel (72 KB
  * inverse alias table per tile, two chains per SM, shortest step) up to 2 x SM-count tiles per launch,

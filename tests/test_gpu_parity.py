@@ -968,3 +968,24 @@ def test_icc_profile_cleared_and_refused_in_tile_mode(product_lib):
     _, written = enc.release_output_buffer()
     enc.destroy()
     assert obuf[:written].tobytes() == plain
+
+
+@pytest.mark.gpu
+def test_recurring_chunks_replayed_as_cuda_graphs(product_lib, oracle):
+    """A chunk geometry seen for the second time is captured as a CUDA graph and replayed from then on
+    (engine.cu, hydb_engine_submit_frames): same bytes as the oracle every time, the replay counter moves
+    from the third encode on, and the kernel counter keeps counting replayed kernels.  HYDRIUM_B200_GRAPHS=0
+    is read once per process, so the switch is not exercised here."""
+    img = synth_image(2304, 512, 8, seed=21)   # 18 tiles: one chunk
+    want = oracle.encode_image(img)
+    seen = []
+    for _ in range(4):
+        st = {}
+        assert encode_cli_loop(product_lib, img, stats=st) == want
+        seen.append(st)
+    assert seen[3]["graph_launches"] > seen[1]["graph_launches"], seen
+    per_encode = seen[3]["kernel_launches"] - seen[2]["kernel_launches"]
+    assert per_encode == seen[1]["kernel_launches"] - seen[0]["kernel_launches"] > 0, seen
+    # a different image of the same geometry through the replayed graph
+    img2 = synth_image(2304, 512, 8, seed=22)
+    assert encode_cli_loop(product_lib, img2) == oracle.encode_image(img2)

@@ -1,7 +1,7 @@
 """One small pass over every kernel family, meant to run under compute-sanitizer
 (tests/test_gpu_parity.py::test_compute_sanitizer): whole-image device path with both rANS chain kernels,
 a multi-group frame, one-frame mode over two LF groups, the asynchronous nine-symbol API with a tiny
-output area (re-gather), and float samples.  Exits non-zero when a result differs from the oracle /
+output area (re-gather), a recurring chunk (CUDA-graph capture and replay), and float samples.  Exits non-zero when a result differs from the oracle /
 reference."""
 import os
 import sys
@@ -32,6 +32,12 @@ os.environ["HYDRIUM_B200_OUTCAP_KB"] = "64"
 os.environ["HYDRIUM_B200_BATCH"] = "3"
 bad += encode_cli_loop(lib, img) != want
 del os.environ["HYDRIUM_B200_OUTCAP_KB"], os.environ["HYDRIUM_B200_BATCH"]
+# the same chunk geometry three times: the second submission captures the job as a CUDA graph, the third replays it
+# (engine.cu, hydb_engine_submit_frames); the staging copy runs on the helper-thread pool
+wide = synth_image(2304, 256, 8, seed=6)
+want_wide = orc.encode_image(wide)
+for _ in range(3):
+    bad += encode_cli_loop(lib, wide) != want_wide
 f32 = (synth_image(270, 130, 16, seed=5).astype(np.float32) / np.float32(65535))
 bad += encode_cli_loop(lib, f32) != orc.encode_image(f32)
 if have_ref():
