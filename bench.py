@@ -587,7 +587,7 @@ def run_api_bench(ctx: Ctx, extra: list[str], want: bytes | None) -> dict:
         env["HYDRIUM_B200_DEVICE"] = str(ctx.local_rank)
         for k in ("HYDRIUM_B200_BATCH", "HYDRIUM_B200_DEPTH", "HYDRIUM_B200_CHAIN"):
             env.pop(k, None)
-        if ctx.world > 1 and "HYDRIUM_B200_THREADS" not in env:
+        if ctx.world > 1 and not env.get("HYDRIUM_B200_THREADS"):
             # one encoder process per GPU on one host: each gets its share of the cores for the staging copy
             # (the library's own default, up to six threads, assumes it has the machine to itself)
             env["HYDRIUM_B200_THREADS"] = str(staging_threads(ctx.world))
@@ -614,7 +614,7 @@ def api_bench_all_ranks(ctx: Ctx, extra: list[str], want: bytes) -> dict:
             "ms_per_step": ms, "ms_best_rank0": res["ms_best"], "first_call_ms_rank0": res["first_call_ms"], "identical": ok,
             "api": "the nine libhydrium entry points, default settings: hyd_send_tile x 256 with the flush / release / provide loop "
                    "after every tile (tools/api_bench.c, the reference CLI's sequence), pageable host image, per rank on its own GPU",
-            "staging_threads": int(os.environ.get("HYDRIUM_B200_THREADS", 0)) or (staging_threads(ctx.world) if ctx.world > 1 else "library default (up to 6)"),
+            "staging_threads": int(os.environ.get("HYDRIUM_B200_THREADS") or 0) or (staging_threads(ctx.world) if ctx.world > 1 else "library default (up to 6)"),
             "l2": "every step copies its pixels from host memory again; nothing is reused on the device between steps"}
 
 
