@@ -608,10 +608,13 @@ def api_bench_all_ranks(ctx: Ctx, extra: list[str], want: bytes) -> dict:
     ctx.barrier()
     res = run_api_bench(ctx, ["--reps", str(args.steps), "--warmup", str(max(args.warmup, 3))] + extra, want)
     ms = ctx.max_over_ranks(res["ms_mean"])
+    ms_median = ctx.max_over_ranks(res["ms_median"])
+    ms_worst = ctx.max_over_ranks(res.get("ms_worst", res["ms_mean"]))
     ok = ctx.all_true(bool(res["identical"]))
     mpx_total = ctx.world * WIDTH * HEIGHT / 1e6
     return {"value": mpx_total / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": res["bytes_in"], "d2h_bytes_per_step": res["bytes_out"],
-            "ms_per_step": ms, "ms_best_rank0": res["ms_best"], "first_call_ms_rank0": res["first_call_ms"], "identical": ok,
+            "ms_per_step": ms, "ms_best_rank0": res["ms_best"], "ms_median_max_over_ranks": ms_median,
+            "ms_worst_step_any_rank": ms_worst, "first_call_ms_rank0": res["first_call_ms"], "identical": ok,
             "api": "the nine libhydrium entry points, default settings: hyd_send_tile x 256 with the flush / release / provide loop "
                    "after every tile (tools/api_bench.c, the reference CLI's sequence), pageable host image, per rank on its own GPU",
             "staging_threads": int(os.environ.get("HYDRIUM_B200_THREADS") or 0) or (staging_threads(ctx.world) if ctx.world > 1 else "library default (up to 6)"),

@@ -324,9 +324,18 @@ uint64_t hydb_engine_stream(const HydbEngine *eng) { return eng ? (uint64_t)(uin
 uint64_t hydb_engine_launch_count(const HydbEngine *eng) { return eng ? eng->launches : 0; }
 uint64_t hydb_engine_graph_launch_count(const HydbEngine *eng) { return eng ? eng->graph_launches : 0; }
 
+// captured job graphs hold the workspace's pointers and launch choices as they were: drop them when those change
+static void drop_job_graphs(HydbEngine *eng) {
+    for (HydbEngine::JobGraph &g : eng->job_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    eng->job_graphs.clear();
+}
+
 HYDStatusCode hydb_engine_set_chain_kernel(HydbEngine *eng, int mode) {
     if (!eng || mode < 0 || mode > 2)
         return HYD_API_ERROR;
+    if (eng->ws.chain_mode != (uint32_t)mode)
+        drop_job_graphs(eng);
     eng->ws.chain_mode = (uint32_t)mode;
     return HYD_OK;
 }
@@ -337,6 +346,11 @@ HYDStatusCode hydb_engine_enable_taps(HydbEngine *eng, int enable) {
     CK(cudaSetDevice(eng->device));
     Workspace &w = eng->ws;
     const size_t T = eng->max_batch;
+    if (!!enable != eng->taps) {
+        for (HydbEngine::Job &jb : eng->jobs)   // graphs in flight must finish before they are destroyed
+            if (jb.st) CK(cudaStreamSynchronize(jb.st));
+        drop_job_graphs(eng);
+    }
     if (enable && !eng->taps) {
         CK(dalloc(&w.dbg_xyb, T * 65536 * 3));
         CK(dalloc(&w.dbg_dct, T * 65536 * 3));

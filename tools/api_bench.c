@@ -200,9 +200,10 @@ int main(int argc, char **argv) {
     qsort(ms, (size_t)reps, sizeof(double), cmp_double);
     const double mean = sum / reps, mpx = (double)w * h / 1e6;
     printf("{\"width\": %u, \"height\": %u, \"bits\": %d, \"channels\": %d, \"linear\": %d, \"shift\": %d, \"reps\": %d, "
-           "\"first_call_ms\": %.3f, \"ms_mean\": %.3f, \"ms_best\": %.3f, \"ms_median\": %.3f, \"mpx_per_s\": %.1f, "
+           "\"first_call_ms\": %.3f, \"ms_mean\": %.3f, \"ms_best\": %.3f, \"ms_median\": %.3f, \"ms_p90\": %.3f, \"ms_worst\": %.3f, \"mpx_per_s\": %.1f, "
            "\"bytes_in\": %zu, \"bytes_out\": %zu}\n",
-           w, h, bits, channels, linear, shift, reps, first, mean, ms[0], ms[reps / 2], mpx / (mean / 1e3), n_in, sink.len);
+           w, h, bits, channels, linear, shift, reps, first, mean, ms[0], ms[reps / 2], ms[(reps * 9) / 10 < reps ? (reps * 9) / 10 : reps - 1],
+           ms[reps - 1], mpx / (mean / 1e3), n_in, sink.len);
     free(pixels);
     free(obuf);
     free(ms);
