@@ -326,6 +326,10 @@ uint64_t hydb_engine_graph_launch_count(const HydbEngine *eng) { return eng ? en
 
 // captured job graphs hold the workspace's pointers and launch choices as they were: drop them when those change
 static void drop_job_graphs(HydbEngine *eng) {
+    if (eng->job_graphs.empty())
+        return;
+    for (HydbEngine::Job &jb : eng->jobs)   // replays in flight finish first
+        if (jb.st) cudaStreamSynchronize(jb.st);
     for (HydbEngine::JobGraph &g : eng->job_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     eng->job_graphs.clear();
@@ -346,11 +350,8 @@ HYDStatusCode hydb_engine_enable_taps(HydbEngine *eng, int enable) {
     CK(cudaSetDevice(eng->device));
     Workspace &w = eng->ws;
     const size_t T = eng->max_batch;
-    if (!!enable != eng->taps) {
-        for (HydbEngine::Job &jb : eng->jobs)   // graphs in flight must finish before they are destroyed
-            if (jb.st) CK(cudaStreamSynchronize(jb.st));
+    if (!!enable != eng->taps)
         drop_job_graphs(eng);
-    }
     if (enable && !eng->taps) {
         CK(dalloc(&w.dbg_xyb, T * 65536 * 3));
         CK(dalloc(&w.dbg_dct, T * 65536 * 3));
