@@ -125,6 +125,17 @@ struct HydbEngine {
         }                                                                               \
     } while (0)
 
+// captured job graphs hold the workspace's pointers and launch choices as they were: drop them when those change
+static void drop_job_graphs(HydbEngine *eng) {
+    if (eng->job_graphs.empty())
+        return;
+    for (HydbEngine::Job &jb : eng->jobs)   // replays in flight finish first
+        if (jb.st) cudaStreamSynchronize(jb.st);
+    for (HydbEngine::JobGraph &g : eng->job_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    eng->job_graphs.clear();
+}
+
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
@@ -290,8 +301,7 @@ void hydb_engine_destroy(HydbEngine *eng) {
         if (eng->band_done[b]) cudaEventDestroy(eng->band_done[b]);
         if (eng->band_h2d[b]) cudaEventDestroy(eng->band_h2d[b]);
     }
-    for (HydbEngine::JobGraph &g : eng->job_graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
+    drop_job_graphs(eng);
     for (HydbEngine::Job &jb : eng->jobs) {
         if (jb.st) { cudaStreamSynchronize(jb.st); cudaStreamDestroy(jb.st); }
         if (jb.st2) { cudaStreamSynchronize(jb.st2); cudaStreamDestroy(jb.st2); }
@@ -323,17 +333,6 @@ uint32_t hydb_engine_max_batch(const HydbEngine *eng) { return eng ? eng->max_ba
 uint64_t hydb_engine_stream(const HydbEngine *eng) { return eng ? (uint64_t)(uintptr_t)eng->st : 0; }
 uint64_t hydb_engine_launch_count(const HydbEngine *eng) { return eng ? eng->launches : 0; }
 uint64_t hydb_engine_graph_launch_count(const HydbEngine *eng) { return eng ? eng->graph_launches : 0; }
-
-// captured job graphs hold the workspace's pointers and launch choices as they were: drop them when those change
-static void drop_job_graphs(HydbEngine *eng) {
-    if (eng->job_graphs.empty())
-        return;
-    for (HydbEngine::Job &jb : eng->jobs)   // replays in flight finish first
-        if (jb.st) cudaStreamSynchronize(jb.st);
-    for (HydbEngine::JobGraph &g : eng->job_graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-    eng->job_graphs.clear();
-}
 
 HYDStatusCode hydb_engine_set_chain_kernel(HydbEngine *eng, int mode) {
     if (!eng || mode < 0 || mode > 2)
