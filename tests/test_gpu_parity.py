@@ -989,3 +989,25 @@ def test_recurring_chunks_replayed_as_cuda_graphs(product_lib, oracle):
     # a different image of the same geometry through the replayed graph
     img2 = synth_image(2304, 512, 8, seed=22)
     assert encode_cli_loop(product_lib, img2) == oracle.encode_image(img2)
+
+
+@pytest.mark.gpu
+def test_host_side_under_address_sanitizer(product_lib, tmp_path):
+    """hyd_api.c + stage_pool.c + the C harness built with -fsanitize=address,undefined and linked with the same
+    CUDA objects (make asan): tile mode, larger tiles, one-frame mode over several LF groups and a ragged image
+    run clean and write the same bytes as the regular build."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "hydrium_b200", "csrc"), "asan"], check=True, capture_output=True)
+    plain = os.path.join(root, "hydrium_b200", "bin", "api_bench")
+    asan = os.path.join(root, "hydrium_b200", "bin", "api_bench_asan")
+    env = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0:abort_on_error=0", UBSAN_OPTIONS="halt_on_error=1")
+    cases = [["--width", "2304", "--height", "1100"], ["--width", "1300", "--height", "700", "--shift", "1"],
+             ["--width", "4096", "--height", "2100", "--one-frame"], ["--width", "300", "--height", "260", "--bits", "16", "--linear"]]
+    for i, case in enumerate(cases):
+        a, b = str(tmp_path / f"a{i}.jxl"), str(tmp_path / f"b{i}.jxl")
+        p = subprocess.run([asan, "--reps", "3", "--warmup", "1", "--out", a] + case, env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0 and "ERROR: AddressSanitizer" not in p.stderr and "runtime error" not in p.stderr, (case, p.stderr[-3000:])
+        subprocess.run([plain, "--reps", "1", "--warmup", "1", "--out", b] + case, check=True, capture_output=True, timeout=600)
+        assert open(a, "rb").read() == open(b, "rb").read(), case

@@ -68,6 +68,8 @@ typedef struct {
 } Sink;
 
 static int sink_put(Sink *s, const uint8_t *d, size_t n) {
+    if (!n)
+        return 0;
     if (s->len + n > s->cap) {
         size_t cap = s->cap ? s->cap : (size_t)1 << 20;
         while (cap < s->len + n)
