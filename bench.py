@@ -576,7 +576,11 @@ def run_config2(ctx: Ctx) -> dict:
 
 
 def staging_threads(world: int) -> int:
-    return max(1, min(6, (os.cpu_count() or 1) // max(1, world)))
+    """Staging threads per rank when several encoder processes share the host: half of the rank's share of the
+    cores (the library's own default is "up to six, at most half the CPUs" for a process that has the host to
+    itself).  With every core spinning in a staging pool the CUDA runtime's own threads wait for a core: at
+    N = 8 on 32 cores, 4 threads per rank gave steps of up to 54 ms."""
+    return max(1, min(6, (os.cpu_count() or 1) // (2 * max(1, world))))
 
 
 def run_api_bench(ctx: Ctx, extra: list[str], want: bytes | None) -> dict:
