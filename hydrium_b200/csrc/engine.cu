@@ -66,6 +66,18 @@ struct HydbEngine {
     void *host_in = nullptr;
     uint8_t *host_out = nullptr;
     size_t host_in_cap = 0, host_out_cap = 0;
+    // one-frame head assembly (hydb_oneframe_finish): device arena {info | scratch | out} and its page-locked mirror, grow-only
+    void *of_dev = nullptr;
+    size_t of_dev_cap = 0;
+    uint8_t *of_host = nullptr;
+    size_t of_host_cap = 0;
+    // bits of the HF context map's stream for of_ctx_n presets (k_oneframe_finish): it depends on nothing else
+    uint32_t *of_ctx = nullptr;
+    uint32_t of_ctx_cap_words = 0, of_ctx_n = 0, of_ctx_bits = 0;
+    // ... and of the TOC permutation's stream for the geometry and send order in of_perm_key
+    uint32_t *of_perm = nullptr;
+    uint32_t of_perm_cap_words = 0, of_perm_bits = 0;
+    std::vector<uint32_t> of_perm_key;
     // optional per-stage timing with CUDA events on the launching streams
     bool timing = false, timed_pending = false;
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, lev[2] = {nullptr, nullptr};
@@ -313,6 +325,10 @@ void hydb_engine_destroy(HydbEngine *eng) {
     if (eng->d_job_ovf) cudaFree(eng->d_job_ovf);
     if (eng->h_job_tiles) cudaFreeHost(eng->h_job_tiles);
     if (eng->ev_desc) cudaEventDestroy(eng->ev_desc);
+    if (eng->of_dev) cudaFree(eng->of_dev);
+    if (eng->of_host) cudaFreeHost(eng->of_host);
+    if (eng->of_ctx) cudaFree(eng->of_ctx);
+    if (eng->of_perm) cudaFree(eng->of_perm);
     if (eng->host_in) cudaFree(eng->host_in);
     if (eng->host_out) cudaFree(eng->host_out);
     for (cudaEvent_t ev : eng->tev) if (ev) cudaEventDestroy(ev);
@@ -949,43 +965,106 @@ HYDStatusCode hydb_oneframe_finish(HydbEngine *eng, const uint32_t *info, uint32
     if (!eng || !info || info_words < 8 || !head || !head_len || !hf_global || !hf_len)
         return HYD_API_ERROR;
     CK(cudaSetDevice(eng->device));
-    uint32_t *d_info = nullptr, *d_scratch = nullptr;
-    uint8_t *d_out = nullptr;
+    // One device arena {info | scratch | out} and one page-locked mirror {info | out}, kept by the engine: this
+    // call sits on the tail of every one-frame image (nothing surfaces before it), where three cudaMalloc /
+    // cudaFree pairs (each cudaFree synchronises the device) and two pageable copies cost more than the kernel.
     const uint32_t n = info[4];
     const size_t scratch_words = (size_t)2 * 1485 * n + 16384 + (size_t)4 * (8 + n + info[5]);
+    const size_t info_bytes = ((size_t)info_words * 4 + 255) & ~(size_t)255, scratch_bytes = (scratch_words * 4 + 255) & ~(size_t)255;
     const size_t out_bytes = (size_t)head_cap + hf_cap + 64;
-    if (cudaMalloc(&d_info, (size_t)info_words * 4) != cudaSuccess || cudaMalloc(&d_scratch, scratch_words * 4) != cudaSuccess ||
-        cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
-        cudaFree(d_info); cudaFree(d_scratch); cudaFree(d_out);
-        eng->error = "device allocation failed";
-        return HYD_NOMEM;
+    if (eng->of_dev_cap < info_bytes + scratch_bytes + out_bytes) {
+        if (eng->of_dev) cudaFree(eng->of_dev);
+        eng->of_dev = nullptr;
+        eng->of_dev_cap = 0;
+        const size_t want = (info_bytes + scratch_bytes + out_bytes) * 2;
+        if (cudaMalloc(&eng->of_dev, want) != cudaSuccess) {
+            eng->error = "device allocation failed";
+            return HYD_NOMEM;
+        }
+        eng->of_dev_cap = want;
     }
-    HYDStatusCode rc = HYD_OK;
-    uint32_t res[4] = {0, 0, 0, 0};
-    if (cudaMemcpyAsync(d_info, info, (size_t)info_words * 4, cudaMemcpyHostToDevice, eng->st) != cudaSuccess)
-        rc = HYD_INTERNAL_ERROR;
-    if (rc == HYD_OK) {
-        launch_oneframe_finish(d_info, info_words, d_scratch, (uint32_t)scratch_words, d_out, head_cap, hf_cap, eng->st);
-        eng->launches++;
-        if (cudaMemcpyAsync(res, d_out + head_cap + hf_cap, 16, cudaMemcpyDeviceToHost, eng->st) != cudaSuccess ||
-            cudaStreamSynchronize(eng->st) != cudaSuccess)
-            rc = HYD_INTERNAL_ERROR;
+    if (eng->of_host_cap < info_bytes + out_bytes) {
+        if (eng->of_host) cudaFreeHost(eng->of_host);
+        eng->of_host = nullptr;
+        eng->of_host_cap = 0;
+        const size_t want = (info_bytes + out_bytes) * 2;
+        if (cudaMallocHost((void **)&eng->of_host, want) != cudaSuccess) {
+            eng->error = "page-locked allocation failed";
+            return HYD_NOMEM;
+        }
+        eng->of_host_cap = want;
     }
-    if (rc == HYD_OK && (res[2] || res[0] > head_cap || res[1] > hf_cap)) {
+    uint8_t *dev = static_cast<uint8_t *>(eng->of_dev);
+    uint32_t *d_info = reinterpret_cast<uint32_t *>(dev), *d_scratch = reinterpret_cast<uint32_t *>(dev + info_bytes);
+    uint8_t *d_out = dev + info_bytes + scratch_bytes, *h_out = eng->of_host + info_bytes;
+    memcpy(eng->of_host, info, (size_t)info_words * 4);
+    CK(cudaMemcpyAsync(d_info, eng->of_host, (size_t)info_words * 4, cudaMemcpyHostToDevice, eng->st));
+    if (eng->of_ctx_n != n || !eng->of_ctx) {   // another geometry: the cached stream is of no use
+        eng->of_ctx_bits = 0;
+        eng->of_ctx_n = n;
+        const uint32_t want_words = 1485u * n + 1024u;
+        if (eng->of_ctx_cap_words < want_words) {
+            if (eng->of_ctx) cudaFree(eng->of_ctx);
+            eng->of_ctx = nullptr;
+            eng->of_ctx_cap_words = 0;
+            if (cudaMalloc(&eng->of_ctx, (size_t)want_words * 4) != cudaSuccess) {
+                eng->error = "device allocation failed";
+                return HYD_NOMEM;
+            }
+            eng->of_ctx_cap_words = want_words;
+        }
+    }
+    const bool ctx_hit = eng->of_ctx_bits != 0;
+    {   // key of the permutation stream: image size, whether the image header precedes, LF groups and their send order
+        std::vector<uint32_t> key;
+        if (info_words >= 8 + n) {
+            key.assign({info[0], info[1], info[4], info[5]});
+            key.insert(key.end(), info + 8, info + 8 + n);
+        }
+        const uint32_t want_words = 2u + info[5] + n + 1024u;
+        if (key.empty() || key != eng->of_perm_key || !eng->of_perm) {
+            eng->of_perm_bits = 0;
+            eng->of_perm_key = key;
+            if (eng->of_perm_cap_words < want_words) {
+                if (eng->of_perm) cudaFree(eng->of_perm);
+                eng->of_perm = nullptr;
+                eng->of_perm_cap_words = 0;
+                if (cudaMalloc(&eng->of_perm, (size_t)want_words * 4) != cudaSuccess) {
+                    eng->error = "device allocation failed";
+                    return HYD_NOMEM;
+                }
+                eng->of_perm_cap_words = want_words;
+            }
+        }
+    }
+    const bool perm_hit = eng->of_perm_bits != 0;
+    launch_oneframe_finish(d_info, info_words, d_scratch, (uint32_t)scratch_words, d_out, head_cap, hf_cap, eng->of_ctx,
+                           eng->of_ctx_cap_words, eng->of_ctx_bits, eng->of_perm, eng->of_perm_cap_words, eng->of_perm_bits, eng->st);
+    eng->launches++;
+    CK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, eng->st));
+    CK(cudaStreamSynchronize(eng->st));
+    uint32_t res[10];
+    memcpy(res, h_out + head_cap + hf_cap, 40);
+    if (!ctx_hit && !res[2])
+        eng->of_ctx_bits = res[8];   // 0 when the stream did not fit the cache: coded again next time
+    if (!perm_hit && !res[2] && !eng->of_perm_key.empty())
+        eng->of_perm_bits = res[9];
+    {
+        static const bool trace = [] { const char *e = getenv("HYDRIUM_B200_APITRACE"); return e && *e && *e != '0'; }();
+        if (trace)
+            fprintf(stderr, "[hydrium_b200] k_oneframe_finish phases (cycles): TOC permutation %u, context map stream %u, permutation stream %u, "
+                    "single-thread tail %u\n", res[4], res[5], res[6], res[7]);
+    }
+    if (res[2] || res[0] > head_cap || res[1] > hf_cap || res[3] > 52 || res[3] > res[0] || 52 + (res[0] - res[3]) > head_cap) {
         eng->error = "one-frame head does not fit its buffer";
-        rc = HYD_INTERNAL_ERROR;
+        return HYD_INTERNAL_ERROR;
     }
-    if (rc == HYD_OK) {
-        *head_len = res[0];
-        *hf_len = res[1];
-        if (cudaMemcpy(head, d_out, res[0], cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(hf_global, d_out + head_cap, res[1], cudaMemcpyDeviceToHost) != cudaSuccess)
-            rc = HYD_INTERNAL_ERROR;
-    }
-    cudaFree(d_info); cudaFree(d_scratch); cudaFree(d_out);
-    if (rc != HYD_OK && eng->error.empty())
-        eng->error = "CUDA failure while assembling the one-frame head";
-    return rc;
+    *head_len = res[0];
+    *hf_len = res[1];
+    memcpy(head, h_out, res[3]);                              // container prefix, if any
+    memcpy(head + res[3], h_out + 52, res[0] - res[3]);      // image / frame header, TOC, LFGlobal
+    memcpy(hf_global, h_out + head_cap, res[1]);
+    return HYD_OK;
 }
 
 // Image header of an ICC-tagged codestream (k_icc_header): `icc` is the profile as

@@ -913,12 +913,17 @@ static HYDStatusCode retire(HYDEncoder *enc, int wait, int all) {
             }
         }
         if (rc == HYD_OK && c->is_lf_part) {
+            const double t0 = api_trace() ? now_ms() : 0;
             rc = of_collect_part(enc, c, blk ? blk : c->out_host, bytes);
             free(blk);
             hydb_engine_job_release(enc->gpu.engine, c->job);
             c->state = CH_FREE;
+            const double t1 = api_trace() ? now_ms() : 0;
             if (rc == HYD_OK && c->closes_image)
                 rc = of_assemble(enc);
+            if (api_trace())
+                fprintf(stderr, "[hydrium_b200] LF group %u: sections collected in %.3f ms%s%.3f ms (at %.2f ms)\n", c->lfid, t1 - t0,
+                        c->closes_image ? ", frame head assembled in " : ", -", now_ms() - t1, now_ms() - enc->tr_first);
         } else if (rc == HYD_OK) {
             hydb_engine_job_release(enc->gpu.engine, c->job);
             c->state = CH_DONE;

@@ -816,7 +816,8 @@ k_frame_finish(Workspace ws) {
 
 __global__ void __launch_bounds__(kLfThreads)
 k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32_t *scratch, uint32_t scratch_words,
-                  uint8_t *out, uint32_t head_cap, uint32_t hf_cap) {
+                  uint8_t *out, uint32_t head_cap, uint32_t hf_cap, uint32_t *ctx_cache, uint32_t ctx_cache_words,
+                  uint32_t ctx_cached_bits, uint32_t *perm_cache, uint32_t perm_cache_words, uint32_t perm_cached_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameShared &s = *reinterpret_cast<FrameShared *>(smem_raw);
     __shared__ uint32_t s_warp[64];
@@ -837,6 +838,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         if (tid == 0) { res[0] = res[1] = 0; res[2] = 1; }
         return;
     }
+    const long long tap0 = clock64();
     if (tid == 0) {   // calculate_toc_perm
         uint32_t idx = 0;
         toc[idx++] = 0;
@@ -866,6 +868,7 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     }
     __syncthreads();
     uint32_t err = 0;
+    const long long tap1 = clock64();
     // ---- HFGlobal section ------------------------------------------------------------------------------
     uint8_t *hf_bytes = out + head_cap;
     BitSink b2;
@@ -880,7 +883,16 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         b2.put_bool(0);
         b2.put_bool(1);                                       // move-to-front
     }
-    {
+    // The context map's stream depends on nothing but the number of presets: the engine keeps its bits from the
+    // first image of a geometry (ctx_cache) and later images splice them in (ctx_cached_bits != 0) instead of
+    // coding 1485 n entries again -- half of this kernel's time, on the tail of every one-frame image.
+    __shared__ uint32_t s_ctx_span[2];
+    if (ctx_cached_bits) {
+        if (tid == 0)
+            put_bits_from(b2, ctx_cache, ctx_cached_bits);
+    } else {
+        if (tid == 0)
+            s_ctx_span[0] = b2.bitlen();
         uint16_t *idx = reinterpret_cast<uint16_t *>(tokens + 1485u * n / 2 + 2048u);   // upper part of the token scratch
         for (uint32_t j = tid; j < 1485u * n; j += kLfThreads)
             idx[j] = (uint16_t)hf_map_mtf_index(j, K);
@@ -892,7 +904,25 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         p.split1 = 4; p.msb1 = 1; p.lsb1 = 0;
         err |= block_prefix_stream(s.work, b2, reinterpret_cast<uint32_t *>(hf_bytes), hf_cap / 4, tokens,
                                    1485u * n / 2 + 2048u, p, 1485u * n, ClusterMapMtf{idx}, s_warp, s_first);
+        if (tid == 0)
+            s_ctx_span[1] = b2.bitlen();
+        __syncthreads();
+        // keep the stream's bits, shifted down to bit 0, for the next image of this geometry
+        const uint32_t from = s_ctx_span[0], bits = s_ctx_span[1] - s_ctx_span[0];
+        const uint32_t words = (bits + 31) >> 5, sh = from & 31u;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(hf_bytes) + (from >> 5);
+        if (!err && words <= ctx_cache_words) {
+            for (uint32_t i = tid; i < words; i += kLfThreads) {
+                const uint32_t lo = src[i] >> sh, hi = sh ? src[i + 1] << (32u - sh) : 0u;   // src[i + 1]: at most the partial last word + 1, inside hf_cap
+                ctx_cache[i] = lo | hi;
+            }
+            if (tid == 0)
+                res[8] = bits;
+        } else if (tid == 0) {
+            res[8] = 0;
+        }
     }
+    const long long tap2 = clock64();
     // ---- head, part 1: [image header] frame header + TOC permutation (all threads) ----------------------
     uint32_t pre_bytes = 0;
     BitSink bh;
@@ -906,7 +936,14 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         bh.put_bool(1);                                       // permuted TOC
         s.work.error = 0;
     }
-    {
+    // the TOC permutation's stream depends on the geometry and the order the LF groups were sent in: the engine
+    // keeps its bits too (perm_cache; the host compares the order) -- an image sent like the one before splices them
+    if (perm_cached_bits) {
+        if (tid == 0)
+            put_bits_from(bh, perm_cache, perm_cached_bits);
+    } else {
+        if (tid == 0)
+            s_ctx_span[0] = bh.bitlen();
         PrefixParams p;
         p.num_plain_dists = 8;
         p.lz_min_symbol = 0;
@@ -915,9 +952,26 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
         p.split1 = 7; p.msb1 = 0; p.lsb1 = 0;
         err |= block_prefix_stream(s.work, bh, reinterpret_cast<uint32_t *>(out + 52), (head_cap - 52) / 4, tokens,
                                    scratch_words - fixed, p, 1 + toc_size, WordValues{leh}, s_warp, s_first);
+        if (tid == 0)
+            s_ctx_span[1] = bh.bitlen();
+        __syncthreads();
+        const uint32_t from = s_ctx_span[0], bits = s_ctx_span[1] - s_ctx_span[0];
+        const uint32_t words = (bits + 31) >> 5, sh = from & 31u;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(out + 52) + (from >> 5);
+        if (!err && words <= perm_cache_words) {
+            for (uint32_t i = tid; i < words; i += kLfThreads) {
+                const uint32_t lo = src[i] >> sh, hi = sh ? src[i + 1] << (32u - sh) : 0u;
+                perm_cache[i] = lo | hi;
+            }
+            if (tid == 0)
+                res[9] = bits;
+        } else if (tid == 0) {
+            res[9] = 0;
+        }
     }
     if (tid != 0)
         return;
+    const long long tap3 = clock64();
     const int log_alpha = max_alpha > 32 ? 6 : 5;          // entropy.c:952 with tokens < 64
     if (max_alpha > 64)
         err |= kErrAlphabet;
@@ -957,13 +1011,18 @@ k_oneframe_finish(const uint32_t *__restrict__ info, uint32_t info_words, uint32
     const uint32_t hb = bh.bitlen() >> 3;
     if (!ok || bh.overflow || s.work.error)
         err |= kErrSlab;
-    // close the gap between the container prefix (49 bytes, if any) and the header bits written at byte 52
-    if (!err)
-        for (uint32_t i = 0; i < hb; i++)
-            out[pre_bytes + i] = out[52 + i];
+    // the container prefix (49 bytes, if any) sits at byte 0, the header bits at byte 52: the host closes the gap
+    // when it copies the head out (a single thread moving ~1 KB byte by byte through global memory was most of
+    // this kernel's 0.69 ms)
     res[0] = pre_bytes + hb;
     res[1] = len2;
     res[2] = err;
+    res[3] = pre_bytes;
+    // phase tap (cycles): TOC permutation + Lehmer code, context-map stream, permutation stream, single-thread tail
+    res[4] = (uint32_t)(tap1 - tap0);
+    res[5] = (uint32_t)(tap2 - tap1);
+    res[6] = (uint32_t)(tap3 - tap2);
+    res[7] = (uint32_t)(clock64() - tap3);
 }
 
 // ---- image header of an ICC-tagged image (hyd_set_suggested_icc_profile) ----------------------------
@@ -1168,9 +1227,13 @@ void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H,
 }
 
 void launch_oneframe_finish(const uint32_t *d_info, uint32_t info_words, uint32_t *d_scratch, uint32_t scratch_words,
-                            uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, cudaStream_t st) {
+                            uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, uint32_t *d_ctx_cache, uint32_t ctx_cache_words,
+                            uint32_t ctx_cached_bits, uint32_t *d_perm_cache, uint32_t perm_cache_words, uint32_t perm_cached_bits,
+                            cudaStream_t st) {
     cudaFuncSetAttribute(k_oneframe_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameShared));
-    k_oneframe_finish<<<1, kLfThreads, sizeof(FrameShared), st>>>(d_info, info_words, d_scratch, scratch_words, d_out, head_cap, hf_cap);
+    k_oneframe_finish<<<1, kLfThreads, sizeof(FrameShared), st>>>(d_info, info_words, d_scratch, scratch_words, d_out, head_cap, hf_cap,
+                                                                  d_ctx_cache, ctx_cache_words, ctx_cached_bits, d_perm_cache,
+                                                                  perm_cache_words, perm_cached_bits);
 }
 
 void launch_frame_hist_sum(const Workspace &ws, uint32_t nslots, cudaStream_t st) {

@@ -82,7 +82,9 @@ void launch_frame_finish(const Workspace &ws, uint32_t nslots, cudaStream_t st);
 // one-frame image of several LF groups: head (header, TOC permutation, TOC, LFGlobal) and HFGlobal section;
 // out = [head: head_cap bytes][hf_global: hf_cap bytes][4 words: head_len, hf_len, error, -]
 void launch_oneframe_finish(const uint32_t *d_info, uint32_t info_words, uint32_t *d_scratch, uint32_t scratch_words,
-                            uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, cudaStream_t st);
+                            uint8_t *d_out, uint32_t head_cap, uint32_t hf_cap, uint32_t *d_ctx_cache, uint32_t ctx_cache_words,
+                            uint32_t ctx_cached_bits, uint32_t *d_perm_cache, uint32_t perm_cache_words, uint32_t perm_cached_bits,
+                            cudaStream_t st);
 // image header of an ICC-tagged image: [49-byte container prefix] signature, size, metadata, entropy-coded
 // profile, byte aligned; d_res = {bytes, error}
 void launch_icc_header(const uint8_t *d_icc, uint32_t n, uint32_t W, uint32_t H, uint32_t *d_bits, uint32_t bits_words,

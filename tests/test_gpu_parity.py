@@ -1011,3 +1011,19 @@ def test_host_side_under_address_sanitizer(product_lib, tmp_path):
         assert p.returncode == 0 and "ERROR: AddressSanitizer" not in p.stderr and "runtime error" not in p.stderr, (case, p.stderr[-3000:])
         subprocess.run([plain, "--reps", "1", "--warmup", "1", "--out", b] + case, check=True, capture_output=True, timeout=600)
         assert open(a, "rb").read() == open(b, "rb").read(), case
+
+
+@pytest.mark.gpu
+def test_one_frame_head_streams_reused_across_images(product_lib, reflib):
+    """The engine keeps the bits of the HF context map's stream (a function of the number of LF groups) and of
+    the TOC permutation's stream (geometry + send order) from one image to the next (k_oneframe_finish).  Same
+    geometry with different pixels, another send order, back again, another geometry, a first image (with image
+    header) against the same cache: always the reference's bytes."""
+    a = synth_image(2304, 2100, 8, seed=31, smooth=True)
+    b = synth_image(2304, 2100, 8, seed=32, smooth=True)
+    c = synth_image(4200, 300, 8, seed=33, smooth=True)
+    raster = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    other = [(1, 1), (0, 0), (1, 0), (0, 1)]
+    for img, order in ((a, raster), (b, raster), (a, other), (b, other), (b, raster), (c, [(0, 0), (1, 0), (2, 0)]),
+                       (c, [(2, 0), (1, 0), (0, 0)]), (a, raster)):
+        assert _encode_in_order(product_lib, img, 0, order) == _encode_in_order(reflib, img, 0, order), (img.shape, order)
