@@ -146,3 +146,23 @@ def test_staging_copy_pool(tmp_path):
                    check=True)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and res.stdout.strip() == "0", res.stdout + res.stderr
+
+
+def test_staging_copy_pool_under_thread_sanitizer(tmp_path):
+    """The same driver built with -fsanitize=thread: the claim protocol (descriptor published word by word, rows
+    claimed through the 64-bit ticket) must be free of data races, not only produce the right bytes."""
+    import os
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(ROOT, "tests", "host_harness", "stage_pool_test.c")
+    inc = os.path.join(ROOT, "hydrium_b200", "csrc")
+    exe = str(tmp_path / "stage_pool_tsan")
+    b = subprocess.run(["gcc", "-std=c99", "-O1", "-g", "-fsanitize=thread", "-I", inc, "-o", exe, src,
+                        os.path.join(inc, "stage_pool.c"), "-lpthread"], capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + b.stderr[-200:])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    if "FATAL: ThreadSanitizer" in res.stderr:   # e.g. unsupported address-space layout in this container
+        pytest.skip(res.stderr[-200:])
+    assert res.returncode == 0 and "WARNING: ThreadSanitizer" not in res.stderr and res.stdout.strip().endswith("0"), \
+        res.stdout[-500:] + res.stderr[-3000:]
