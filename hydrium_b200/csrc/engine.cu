@@ -90,6 +90,8 @@ struct HydbEngine {
         uint32_t slot0 = 0, n = 0;
         bool busy = false;
         uint64_t *h_res = nullptr;   // page-locked [2]: bytes gathered, error bits | overflow << 31
+        cudaEvent_t trace_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // HYDRIUM_B200_JOBTRACE
+        bool traced = false;
         uint32_t *d_ovf = nullptr;
     };
     static constexpr int kJobs = 16;
@@ -320,6 +322,8 @@ void hydb_engine_destroy(HydbEngine *eng) {
         if (jb.ev_front) cudaEventDestroy(jb.ev_front);
         if (jb.ev_lf) cudaEventDestroy(jb.ev_lf);
         if (jb.ev_done) cudaEventDestroy(jb.ev_done);
+        for (cudaEvent_t e : jb.trace_ev)
+            if (e) cudaEventDestroy(e);
     }
     if (eng->h_job_res) cudaFreeHost(eng->h_job_res);
     if (eng->d_job_ovf) cudaFree(eng->d_job_ovf);
@@ -805,9 +809,45 @@ HYDStatusCode hydb_engine_submit_frames(HydbEngine *eng, const HydbFrame *frames
         eng->launches++;
         return HYD_OK;
     };
+    // HYDRIUM_B200_JOBTRACE=1: timestamps between the stages of every classic-tile job (no graphs then),
+    // printed when the job is polled done -- where a job's latency goes while other jobs' chains fill the GPU
+    static const bool job_trace = [] { const char *e = getenv("HYDRIUM_B200_JOBTRACE"); return e && *e && *e != '0'; }();
     static const bool graphs_on = [] { const char *e = getenv("HYDRIUM_B200_GRAPHS"); return !(e && e[0] == '0'); }();
     bool done = false;
-    if (graphs_on && !any_multi) {
+    jb.traced = false;
+    if (job_trace && !any_multi) {
+        for (cudaEvent_t &e : jb.trace_ev)
+            if (!e) CK(cudaEventCreate(&e));
+        cudaStream_t st = jb.st;
+        CK(cudaEventRecord(jb.trace_ev[0], st));
+        if (h_src && h2d_bytes)
+            CK(cudaMemcpyAsync(d_dst, h_src, h2d_bytes, cudaMemcpyHostToDevice, st));
+        HYDStatusCode rc = prepare_tiles(eng, tiles.data(), slots, st, extra.data(), slot0, jb.d_ovf, nullptr, true, kPrepUpload);
+        if (rc != HYD_OK)
+            return rc;
+        CK(cudaEventRecord(jb.trace_ev[1], st));
+        launch_xyb_dct_quant(v, eng->luts, slots, st);
+        CK(cudaEventRecord(jb.trace_ev[2], st));
+        CK(cudaEventRecord(jb.ev_front, st));
+        CK(cudaStreamWaitEvent(jb.st2, jb.ev_front, 0));
+        launch_lf_group(v, slots, jb.st2);
+        CK(cudaEventRecord(jb.ev_lf, jb.st2));
+        launch_hf_tokens(v, slots, st);
+        CK(cudaEventRecord(jb.trace_ev[3], st));
+        launch_ans_chain(v, slots, st, !any_float, 0, true);
+        CK(cudaEventRecord(jb.trace_ev[4], st));
+        CK(cudaStreamWaitEvent(st, jb.ev_lf, 0));
+        CK(cudaEventRecord(jb.trace_ev[5], st));
+        launch_ans_pack(v, eng->templ, slots, st);
+        CK(cudaEventRecord(jb.trace_ev[6], st));
+        launch_gather(v, slots, out, out_cap, 0, jb.d_ovf, st);
+        launch_job_result(v.tile_err, slots, v.out_off + slots, jb.d_ovf, jb.h_res, st);
+        CK(cudaEventRecord(jb.trace_ev[7], st));
+        eng->launches += 8;
+        jb.traced = true;
+        done = true;
+    }
+    if (!done && graphs_on && !any_multi) {
         const HydbEngine::JobGraphKey key{j, slot0, slots, eng->ws.chain_mode, h_src, d_dst, h_src ? h2d_bytes : 0, out, out_cap, !any_float};
         HydbEngine::JobGraph *g = nullptr;
         for (HydbEngine::JobGraph &c : eng->job_graphs)
@@ -890,6 +930,14 @@ HYDStatusCode hydb_engine_job_poll(HydbEngine *eng, uint32_t job, int wait, uint
         if (q == cudaErrorNotReady)
             return HYD_DEFAULT;
         CK(q);
+    }
+    if (jb.traced) {
+        jb.traced = false;
+        float ms[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 7; i++)
+            cudaEventElapsedTime(&ms[i], jb.trace_ev[i], jb.trace_ev[i + 1]);
+        fprintf(stderr, "[hydrium_b200] job %u (%u tiles): copies %.3f, xyb_dct_quant %.3f, hf_tokens %.3f, ans_chain %.3f, wait for lf_group %.3f, "
+                "ans_pack %.3f, gather + result %.3f ms\n", job, jb.n, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6]);
     }
     const uint64_t res = reinterpret_cast<volatile uint64_t *>(jb.h_res)[1];
     if (bytes)
